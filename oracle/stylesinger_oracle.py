@@ -1,0 +1,649 @@
+"""ORACLE — test infrastructure only.  NOT part of the product path.
+
+A CPU fp32 restatement (torch functional ops, one utterance at a time = the reference's B=1
+semantics) of every function on StyleSinger's ph -> mel -> wav inference path
+(SURVEY.md §8a rows a1-a22).  Each function cites the reference file:line it follows.
+
+Pinning: the reference has NO tests / golden vectors for this path, so this oracle
+is pinned against outputs of the UNMODIFIED reference modules executed in the build container:
+tools/make_golden.py imports /root/reference, loads the synthetic checkpoints of
+stylesinger_b200/synth.py with strict=True, runs them with injected noise and writes
+tests/golden/*.npz; tests/test_oracle_golden.py checks this file against those fixtures.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module (as the checker / the timed CPU baseline).  The product package
+stylesinger_b200 never imports it.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------
+# noise plumbing: every torch.randn/rand draw of the path, in reference order
+# ----------------------------------------------------------------------------------------------
+_TORCH_RANDN, _TORCH_RAND = torch.randn, torch.rand  # bound early: tools/make_golden.py patches torch.*
+
+
+class NoiseSource:
+    """Sequential noise stream.  ``randn(shape)`` / ``rand(shape)`` return CPU fp32 tensors drawn
+    from one seeded generator, in call order; ``log`` records (kind, shape) so the reference run
+    (torch.randn* monkey-patched to this object) and the oracle run can be checked to consume
+    the identical sequence."""
+
+    def __init__(self, seed):
+        self.g = torch.Generator().manual_seed(int(seed))
+        self.log = []
+        self.record = None  # optional list collecting the drawn tensors
+
+    def randn(self, shape):
+        t = _TORCH_RANDN(tuple(shape), generator=self.g)
+        self.log.append(("randn", tuple(shape)))
+        if self.record is not None:
+            self.record.append(t)
+        return t
+
+    def rand(self, shape):
+        t = _TORCH_RAND(tuple(shape), generator=self.g)
+        self.log.append(("rand", tuple(shape)))
+        if self.record is not None:
+            self.record.append(t)
+        return t
+
+
+# ----------------------------------------------------------------------------------------------
+# a5/a6: LayerNorm, sinusoidal positions
+# ----------------------------------------------------------------------------------------------
+def layer_norm(x, w, b, eps=1e-5):
+    """nn.LayerNorm over the last dim (reference modules/commons/common_layers.py:75-82)."""
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def layer_norm_ch(x, w, b, eps=1e-5):
+    """tts_modules.LayerNorm(dim=1): normalise the channel dim of [B,C,T]
+    (reference modules/fastspeech/tts_modules.py:37-56)."""
+    return layer_norm(x.transpose(1, -1), w, b, eps).transpose(1, -1)
+
+
+def sinusoid_table(n, dim, padding_idx=0):
+    """reference modules/commons/common_layers.py:111-127 (get_embedding)."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+    e = torch.arange(n, dtype=torch.float).unsqueeze(1) * e.unsqueeze(0)
+    e = torch.cat([torch.sin(e), torch.cos(e)], dim=1).view(n, -1)
+    if padding_idx is not None:
+        e[padding_idx, :] = 0
+    return e
+
+
+def make_positions(t, padding_idx=0):
+    """reference utils/tts_utils.py:6-18."""
+    mask = t.ne(padding_idx).int()
+    return (torch.cumsum(mask, dim=1).type_as(mask) * mask).long() + padding_idx
+
+
+def sinusoid_positions(x, dim=256, padding_idx=0):
+    """SinusoidalPositionalEmbedding.forward (reference common_layers.py:129-148). x: [B,L] tokens
+    or channel 0 of a float tensor."""
+    B, L = x.shape[:2]
+    tab = sinusoid_table(padding_idx + 1 + L, dim, padding_idx)
+    pos = make_positions(x, padding_idx)
+    return tab.index_select(0, pos.view(-1)).view(B, L, -1)
+
+
+# ----------------------------------------------------------------------------------------------
+# a2-a4: FFT block
+# ----------------------------------------------------------------------------------------------
+def mha(query, key, value, in_w, in_b, out_w, out_b, num_heads=2, key_padding_mask=None):
+    """F.multi_head_attention_forward as called by the reference fast path
+    (common_layers.py:277-286) and by nn.MultiheadAttention (lse.py:19,41).
+    query [L,B,E], key/value [S,B,E].  Returns [L,B,E]."""
+    L, B, E = query.shape
+    S = key.shape[0]
+    hd = E // num_heads
+    wq, wk, wv = in_w[:E], in_w[E:2 * E], in_w[2 * E:]
+    bq = bk = bv = None
+    if in_b is not None:
+        bq, bk, bv = in_b[:E], in_b[E:2 * E], in_b[2 * E:]
+    q = F.linear(query, wq, bq)
+    k = F.linear(key, wk, bk)
+    v = F.linear(value, wv, bv)
+    q = q * (float(hd) ** -0.5)
+    q = q.contiguous().view(L, B * num_heads, hd).transpose(0, 1)
+    k = k.contiguous().view(S, B * num_heads, hd).transpose(0, 1)
+    v = v.contiguous().view(S, B * num_heads, hd).transpose(0, 1)
+    w = torch.bmm(q, k.transpose(1, 2))
+    if key_padding_mask is not None:
+        w = w.view(B, num_heads, L, S).masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+        w = w.view(B * num_heads, L, S)
+    w = F.softmax(w, dim=-1)
+    o = torch.bmm(w, v).transpose(0, 1).contiguous().view(L, B, E)
+    return F.linear(o, out_w, out_b)
+
+
+def ffn_layer(x, sd, p, k):
+    """TransformerFFNLayer.forward (common_layers.py:558-582): Conv1d(k, SAME)*k^-0.5 -> GELU(erf) -> Linear.
+    x [T,B,C]."""
+    y = F.conv1d(x.permute(1, 2, 0), sd[p + "ffn_1.weight"], sd[p + "ffn_1.bias"], padding=k // 2).permute(2, 0, 1)
+    y = y * k ** -0.5
+    y = F.gelu(y)
+    return F.linear(y, sd[p + "ffn_2.weight"], sd[p + "ffn_2.bias"])
+
+
+def enc_sa_layer(x, pad_mask, sd, p, k):
+    """EncSALayer.forward (common_layers.py:649-673). x [T,B,C]; pad_mask bool [B,T]."""
+    keep = (1 - pad_mask.float()).transpose(0, 1)[..., None]
+    res = x
+    x = layer_norm(x, sd[p + "layer_norm1.weight"], sd[p + "layer_norm1.bias"])
+    x = mha(x, x, x, sd[p + "self_attn.in_proj_weight"], None, sd[p + "self_attn.out_proj.weight"], None,
+            2, pad_mask)
+    x = (res + x) * keep
+    res = x
+    x = layer_norm(x, sd[p + "layer_norm2.weight"], sd[p + "layer_norm2.bias"])
+    x = ffn_layer(x, sd, p + "ffn.", k)
+    return (res + x) * keep
+
+
+def fft_blocks(x, sd, p, n_layers, k, pad_mask=None, use_pos_embed=True):
+    """FFTBlocks.forward (tts_modules.py:281-306). x [B,T,C] -> [B,T,C]."""
+    pad_mask = x.abs().sum(-1).eq(0) if pad_mask is None else pad_mask
+    keep = 1 - pad_mask.transpose(0, 1).float()[:, :, None]
+    if use_pos_embed:
+        x = x + sd[p + "pos_embed_alpha"] * sinusoid_positions(x[..., 0], x.shape[-1])
+    x = x.transpose(0, 1) * keep
+    for i in range(n_layers):
+        x = enc_sa_layer(x, pad_mask, sd, f"{p}layers.{i}.op.", k) * keep
+    x = layer_norm(x, sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"]) * keep
+    return x.transpose(0, 1)
+
+
+def fastspeech_encoder(txt, sd, hp):
+    """FastspeechEncoder.forward (tts_modules.py:326-346). txt int64 [B,P]."""
+    H = hp["hidden_size"]
+    x = math.sqrt(H) * F.embedding(txt, sd["encoder.embed_tokens.weight"], padding_idx=0)
+    x = x + sinusoid_positions(txt, H)
+    return fft_blocks(x, sd, "encoder.", hp["enc_layers"], hp["enc_ffn_kernel_size"], txt.eq(0), use_pos_embed=False)
+
+
+def fastspeech_decoder(x, sd, hp):
+    """FastspeechDecoder (tts_modules.py:349-355) = FFTBlocks with learned pos_embed_alpha."""
+    return fft_blocks(x, sd, "decoder.", hp["dec_layers"], hp["dec_ffn_kernel_size"])
+
+
+# ----------------------------------------------------------------------------------------------
+# a7/a8: note encoder, duration, length regulator, expand
+# ----------------------------------------------------------------------------------------------
+def note_encoder(note, note_dur, note_type, sd, H=256):
+    """NoteEncoder.forward (stylesinger.py:31-36)."""
+    x = F.embedding(note, sd["note_encoder.emb.weight"], padding_idx=0) * math.sqrt(H)
+    ty = F.embedding(note_type, sd["note_encoder.type_emb.weight"], padding_idx=0) * math.sqrt(H)
+    du = F.linear(note_dur.unsqueeze(-1), sd["note_encoder.dur_ln.weight"], sd["note_encoder.dur_ln.bias"])
+    return x + du + ty
+
+
+def duration_predictor(xs, pad_mask, sd, hp):
+    """DurationPredictor.inference (tts_modules.py:105-130). xs [B,P,H] -> (dur int64 [B,P], log-dur [B,P,1])."""
+    k = hp["dur_predictor_kernel"]
+    xs = xs.transpose(1, -1)
+    for i in range(hp["dur_predictor_layers"]):
+        xs = F.pad(xs, ((k - 1) // 2, (k - 1) // 2))
+        xs = F.conv1d(xs, sd[f"dur_predictor.conv.{i}.1.weight"], sd[f"dur_predictor.conv.{i}.1.bias"])
+        xs = F.relu(xs)
+        xs = layer_norm_ch(xs, sd[f"dur_predictor.conv.{i}.3.weight"], sd[f"dur_predictor.conv.{i}.3.bias"])
+        xs = xs * (1 - pad_mask.float())[:, None, :]
+    xs = F.linear(xs.transpose(1, -1), sd["dur_predictor.linear.weight"], sd["dur_predictor.linear.bias"])
+    xs = xs * (1 - pad_mask.float())[:, :, None]
+    dur = torch.clamp(torch.round(xs.squeeze(-1).exp() - 1.0), min=0).long()
+    return dur, xs
+
+
+def length_regulator(dur, pad_mask):
+    """LengthRegulator.forward (tts_modules.py:158-188), alpha=1."""
+    dur = torch.round(dur.float()).long() * (1 - pad_mask.long())
+    tok = torch.arange(1, dur.shape[1] + 1)[None, :, None]
+    cs = torch.cumsum(dur, 1)
+    cs_prev = F.pad(cs, [1, -1])
+    pos = torch.arange(int(dur.sum(-1).max()))[None, None]
+    m = (pos >= cs_prev[:, :, None]) & (pos < cs[:, :, None])
+    return (tok * m.long()).sum(1)
+
+
+def expand_states(h, mel2ph):
+    """fs2.py:258-262."""
+    h = F.pad(h, [0, 0, 1, 0])
+    return torch.gather(h, 1, mel2ph[..., None].repeat([1, 1, h.shape[-1]]))
+
+
+# ----------------------------------------------------------------------------------------------
+# a10/a11/a12: style adaptor, RVQ, aligner
+# ----------------------------------------------------------------------------------------------
+def fold_weight_norm(g, v):
+    """torch.nn.utils.weight_norm (dim=0): w = g * v / ||v||, norm over all dims but 0."""
+    n = v.reshape(v.shape[0], -1).norm(dim=1).reshape([-1] + [1] * (v.dim() - 1))
+    return v * (g / n)
+
+
+def wn_forward(x, x_mask, sd, p="style_extractor.wavenet."):
+    """WN.forward with g=None (wavenet.py:54-78; called at lse.py:110). x [B,80,T], x_mask [B,80,T]."""
+    Hc = 80
+    out = torch.zeros_like(x)
+    for i in range(4):
+        w = fold_weight_norm(sd[f"{p}in_layers.{i}.weight_g"], sd[f"{p}in_layers.{i}.weight_v"])
+        x_in = F.conv1d(x, w, sd[f"{p}in_layers.{i}.bias"], padding=1)
+        acts = torch.tanh(x_in[:, :Hc]) * torch.sigmoid(x_in[:, Hc:])
+        w = fold_weight_norm(sd[f"{p}res_skip_layers.{i}.weight_g"], sd[f"{p}res_skip_layers.{i}.weight_v"])
+        rs = F.conv1d(acts, w, sd[f"{p}res_skip_layers.{i}.bias"])
+        if i < 3:
+            x = (x + rs[:, :Hc]) * x_mask
+            out = out + rs[:, Hc:]
+        else:
+            out = out + rs
+    return out * x_mask
+
+
+def conv_blocks(x, sd, p="style_extractor.encoder."):
+    """ConvBlocks.forward (lse.py:229-240) with 5x ResidualBlock (lse.py:192-200), k=5, LN eps 1e-5.
+    x [B,T,80] -> [B,T,256]."""
+    x = x.transpose(1, 2)
+    nonpad = (x.abs().sum(1) > 0).float()[:, None, :]
+    for i in range(5):
+        np_i = (x.abs().sum(1) > 0).float()[:, None, :]
+        for j in range(2):
+            q = f"{p}res_blocks.{i}.blocks.{j}."
+            y = layer_norm_ch(x, sd[q + "0.weight"], sd[q + "0.bias"], 1e-5)
+            y = F.conv1d(y, sd[q + "1.weight"], sd[q + "1.bias"], padding=2)
+            y = y * 5 ** -0.5
+            y = F.gelu(y)
+            y = F.conv1d(y, sd[q + "4.weight"], sd[q + "4.bias"])
+            x = (x + y) * np_i
+    x = x * nonpad
+    x = layer_norm_ch(x, sd[p + "last_norm.weight"], sd[p + "last_norm.bias"], 1e-5) * nonpad
+    x = F.conv1d(x, sd[p + "post_net1.weight"], sd[p + "post_net1.bias"], padding=1) * nonpad
+    return x.transpose(1, 2)
+
+
+def rq_quantize(x, sd, depth=4, p="style_extractor.rqvae.codebooks."):
+    """RQBottleneck.quantize/forward + VQEmbedding.compute_distances (RQ.py:226-270,29-55).
+    x [B,R,256] -> (quants_trunc [B,R,256], codes int64 [B,R,depth])."""
+    res = x.detach().clone()
+    agg = torch.zeros_like(x)
+    codes = []
+    for d in range(depth):
+        cb = sd[f"{p}{d}.weight"][:-1]
+        cbt = cb.t()
+        flat = res.reshape(-1, res.shape[-1])
+        dist = torch.addmm(flat.pow(2.0).sum(dim=1, keepdim=True) + cbt.pow(2.0).sum(dim=0, keepdim=True),
+                           flat, cbt, alpha=-2.0)
+        idx = dist.argmin(dim=-1).reshape(res.shape[:-1])
+        q = F.embedding(idx, sd[f"{p}{d}.weight"])
+        res.sub_(q)
+        agg.add_(q)
+        codes.append(idx.unsqueeze(-1))
+    return x + (agg - x), torch.cat(codes, dim=-1)
+
+
+def local_style_adaptor(ref_mels, ref_f0, sd, hp):
+    """LocalStyleAdaptor.forward (lse.py:103-129). ref_mels [B,R,80], ref_f0 [B,R] or [R]."""
+    pad = ref_mels[:, :, 0].eq(0)
+    x = wn_forward(ref_mels.transpose(1, 2), (~pad).unsqueeze(1).repeat([1, 80, 1]).float(), sd).transpose(1, 2)
+    if ref_f0 is not None:
+        f = ref_f0.unsqueeze(ref_f0.dim()).repeat([1, 1, 80])
+        x = x + f
+    style = conv_blocks(x, sd)
+    return rq_quantize(style, sd, hp["rq_depth"])
+
+
+def cross_atten_layer(src, emo, key_pad, sd, p):
+    """CrossAttenLayer.forward, forcing=False (lse.py:28-47). src [F,B,H], emo [R,B,H]."""
+    a = mha(src, emo, emo, sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"],
+            sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"], 2, key_pad)
+    src = layer_norm(src + a, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+    y = F.linear(F.relu(F.linear(src, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+                 sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    return layer_norm(src + y, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+
+
+def get_style(decoder_inp, ref_mels, ref_f0, sd, hp):
+    """StyleSinger.get_style, infer / global_steps>=forcing (stylesinger.py:189-214).
+    Returns (style [B,F,H], codes)."""
+    z, codes = local_style_adaptor(ref_mels, ref_f0, sd, hp)
+    pos = sinusoid_positions(z[:, :, 0], hp["hidden_size"])
+    z = F.linear(torch.cat([z, pos], dim=-1), sd["l1.weight"], sd["l1.bias"])
+    key_pad = z[:, :, 0].eq(0)
+    out = decoder_inp.transpose(0, 1)
+    emo = z.transpose(0, 1)
+    for i in range(2):
+        out = cross_atten_layer(out, emo, key_pad, sd, f"align.layers.{i}.")
+    return out.transpose(0, 1), codes
+
+
+# ----------------------------------------------------------------------------------------------
+# a13/a18: denoisers
+# ----------------------------------------------------------------------------------------------
+def step_embedding(t, sd, p, C):
+    """SinusoidalPosEmb + mlp (net.py:31-44,92-97,114-115). t float/int [B] -> [B,C]."""
+    half = C // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half) * -e)
+    e = t[:, None] * e[None, :]
+    e = torch.cat((e.sin(), e.cos()), dim=-1)
+    h = F.linear(e, sd[p + "mlp.0.weight"], sd[p + "mlp.0.bias"])
+    h = h * torch.tanh(F.softplus(h))
+    return F.linear(h, sd[p + "mlp.2.weight"], sd[p + "mlp.2.bias"])
+
+
+def residual_stack(x, cond, dstep, sd, p, L, cycle):
+    """20x / 10x ResidualBlock.forward (net.py:66-78) + skip/out head (net.py:124-128)."""
+    skip = 0
+    for i in range(L):
+        q = f"{p}residual_layers.{i}."
+        dil = 2 ** (i % cycle)
+        d = F.linear(dstep, sd[q + "diffusion_projection.weight"], sd[q + "diffusion_projection.bias"]).unsqueeze(-1)
+        c = F.conv1d(cond, sd[q + "conditioner_projection.weight"], sd[q + "conditioner_projection.bias"])
+        y = F.conv1d(x + d, sd[q + "dilated_conv.weight"], sd[q + "dilated_conv.bias"], padding=dil, dilation=dil) + c
+        gate, filt = torch.chunk(y, 2, dim=1)
+        y = torch.sigmoid(gate) * torch.tanh(filt)
+        y = F.conv1d(y, sd[q + "output_projection.weight"], sd[q + "output_projection.bias"])
+        r, s = torch.chunk(y, 2, dim=1)
+        x = (x + r) / math.sqrt(2.0)
+        skip = skip + s
+    x = skip / math.sqrt(L)
+    x = F.relu(F.conv1d(x, sd[p + "skip_projection.weight"], sd[p + "skip_projection.bias"]))
+    return F.conv1d(x, sd[p + "output_projection.weight"], sd[p + "output_projection.bias"])
+
+
+def diffnet(spec, t, cond, sd, hp, p="postdiff.denoise_fn."):
+    """DiffNet.forward (net.py:107-130). spec [B,1,80,F], t [B], cond [B,256,F] -> [B,1,80,F]."""
+    C = hp["residual_channels"]
+    x = F.relu(F.conv1d(spec[:, 0], sd[p + "input_projection.weight"], sd[p + "input_projection.bias"]))
+    ds = step_embedding(t, sd, p, C)
+    return residual_stack(x, cond, ds, sd, p, hp["residual_layers"], hp["dilation_cycle_length"])[:, None]
+
+
+def ddiffnet(f0, uv, t, cond, sd, hp, p):
+    """DDiffNet.forward with nonpadding == 1 (net.py:242-266). f0 [B,1,F], uv int64 [B,F] -> [B,3,F]."""
+    C = hp["f0_residual_channels"]
+    a = F.conv1d(f0, sd[p + "input_projection.weight"], sd[p + "input_projection.bias"])
+    b = F.embedding(uv, sd[p + "uv_embed.weight"]).transpose(-1, -2)
+    x = torch.cat([a, b], dim=1)
+    ds = step_embedding(t, sd, p, C)
+    return residual_stack(x, cond, ds, sd, p, hp["f0_residual_layers"], hp["f0_dilation_cycle_length"])
+
+
+# ----------------------------------------------------------------------------------------------
+# a14/a19: samplers
+# ----------------------------------------------------------------------------------------------
+def _gauss_tables(T, max_beta):
+    from stylesinger_b200.schedules import gaussian_schedule  # host constants, shared with the product
+    return {k: torch.from_numpy(v) for k, v in gaussian_schedule(T, max_beta).items()}
+
+
+def _multi_tables(T, max_beta):
+    from stylesinger_b200.schedules import multinomial_schedule
+    return {k: torch.from_numpy(v) for k, v in multinomial_schedule(T, max_beta).items()}
+
+
+def mel_diffusion_sample(cond, coarse_mel, sd, hp, noise, return_steps=False):
+    """DiffusionDecoder.forward(infer=True) (shallow_diffusion_tts.py:284-307) with p_sample (:155-162),
+    p_mean_variance (:145-153), q_sample (:199-204), norm/denorm_spec (:271-275).
+    cond [B,F,256], coarse_mel [B,F,80] -> mel [B,F,80]."""
+    T = hp["timesteps"]
+    s = _gauss_tables(T, hp["max_beta"])
+    smin = torch.tensor(hp["spec_min"], dtype=torch.float32)[None, None, :hp["keep_bins"]]
+    smax = torch.tensor(hp["spec_max"], dtype=torch.float32)[None, None, :hp["keep_bins"]]
+    c = cond.transpose(1, 2)
+    x0 = ((coarse_mel - smin) / (smax - smin) * 2 - 1).transpose(1, 2)[:, None]
+    x = s["sqrt_alphas_cumprod"][T - 1] * x0 + s["sqrt_one_minus_alphas_cumprod"][T - 1] * noise.randn(x0.shape)
+    steps = []
+    B = x.shape[0]
+    for i in reversed(range(T)):
+        t = torch.full((B,), i, dtype=torch.long)
+        eps = diffnet(x, t, c, sd, hp)
+        x_recon = s["sqrt_recip_alphas_cumprod"][i] * x - s["sqrt_recipm1_alphas_cumprod"][i] * eps
+        x_recon = x_recon.clamp(-1.0, 1.0)
+        mean = s["posterior_mean_coef1"][i] * x_recon + s["posterior_mean_coef2"][i] * x
+        nz = noise.randn(x.shape)
+        x = mean + (0.0 if i == 0 else 1.0) * (0.5 * s["posterior_log_variance_clipped"][i]).exp() * nz
+        if return_steps:
+            steps.append(x.clone())
+    mel = (x[:, 0].transpose(1, 2) + 1) / 2 * (smax - smin) + smin
+    return (mel, steps) if return_steps else mel
+
+
+def _log_add_exp(a, b):
+    m = torch.max(a, b)
+    return m + torch.log(torch.exp(a - m) + torch.exp(b - m))
+
+
+def _index_to_log_onehot(x, K=2):
+    oh = F.one_hot(x, K).permute(0, 2, 1)
+    return torch.log(oh.float().clamp(min=1e-30))
+
+
+def _log_sample_categorical(logits, noise, K=2):
+    u = noise.rand(logits.shape)
+    g = -torch.log(-torch.log(u + 1e-30) + 1e-30)
+    return _index_to_log_onehot((g + logits).argmax(dim=1), K)
+
+
+def f0_diffusion_sample(cond, dyn_clip, sd, hp, p, noise):
+    """GaussianMultinomialDiffusion.sample (gaussian_multinomial_diffusion.py:921-942) with
+    gaussian_p_sample (:325-333), p_sample/p_pred/q_posterior (:398-413,374-396), q_pred (:352-362),
+    q_pred_one_timestep (:341-350), log_sample_categorical (:447-452).
+    cond [B,256,F]; dyn_clip (lo, hi) each [B,1,F].  Returns [B,F,2] float (f0_norm, uv)."""
+    T = hp["f0_timesteps"]
+    s = _gauss_tables(T, hp["f0_max_beta"])
+    m = _multi_tables(T, hp["f0_max_beta"])
+    B, _, Fr = cond.shape
+    shape = (B, 1, Fr)
+    log_z = _log_sample_categorical(torch.zeros(shape), noise)  # argmax over a size-1 dim -> class 0
+    z = noise.randn(shape)
+    ln2 = np.log(2)
+    for i in reversed(range(T)):
+        t = torch.full((B,), i, dtype=torch.long)
+        out = ddiffnet(z, log_z.argmax(1).long(), t, cond, sd, hp, p)
+        eps, logits = out[:, :1], out[:, 1:]
+        # gaussian half
+        x_recon = s["sqrt_recip_alphas_cumprod"][i] * z - s["sqrt_recipm1_alphas_cumprod"][i] * eps
+        x_recon = torch.max(torch.min(x_recon, dyn_clip[1]), dyn_clip[0])
+        mean = s["posterior_mean_coef1"][i] * x_recon + s["posterior_mean_coef2"][i] * z
+        nz = noise.randn(z.shape)
+        z = mean + (0.0 if i == 0 else 1.0) * (0.5 * s["posterior_log_variance_clipped"][i]).exp() * nz
+        # multinomial half
+        l0 = F.log_softmax(logits, dim=1)
+        tm1 = max(i - 1, 0)
+        ev = _log_add_exp(l0 + m["log_cumprod_alpha"][tm1], m["log_1_min_cumprod_alpha"][tm1] - ln2)
+        if i == 0:
+            ev = l0
+        un = ev + _log_add_exp(log_z + m["log_alpha"][i], m["log_1_min_alpha"][i] - ln2)
+        logp = un - torch.logsumexp(un, dim=1, keepdim=True)
+        log_z = _log_sample_categorical(logp, noise)
+    return torch.cat([z, log_z.argmax(1).unsqueeze(1)], dim=1).transpose(1, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# a15: pitch glue
+# ----------------------------------------------------------------------------------------------
+F0_BIN, F0_MAX, F0_MIN = 256, 1100.0, 50.0
+F0_MEL_MIN = 1127 * np.log(1 + F0_MIN / 700)
+F0_MEL_MAX = 1127 * np.log(1 + F0_MAX / 700)
+
+
+def f0_to_coarse(f0):
+    """utils/pitch_utils.py:22-31."""
+    mel = 1127 * (1 + f0 / 700).log()
+    mel = torch.where(mel > 0, (mel - F0_MEL_MIN) * (F0_BIN - 2) / (F0_MEL_MAX - F0_MEL_MIN) + 1, mel)
+    mel = torch.where(mel <= 1, torch.ones_like(mel), mel)
+    mel = torch.where(mel > F0_BIN - 1, torch.full_like(mel, F0_BIN - 1), mel)
+    return (mel + 0.5).long()
+
+
+def _minmax_norm(x):
+    x = torch.clamp(x, None, 10)
+    return (x - 6) / (10 - 6) * 2 - 1
+
+
+def midi_clip_band(midi):
+    """add_gmdiff_pitch, infer branch (stylesinger.py:274-283). midi float [B,1,F] -> (lo, hi)."""
+    hi = _minmax_norm((2 ** ((midi + 3 - 69) / 12) * 440).log2()).clamp(-1, 1)
+    lo = _minmax_norm((2 ** ((midi - 3 - 69) / 12) * 440).log2()).clamp(-1, 1)
+    return lo, hi
+
+
+def add_gmdiff_pitch(dec_inp, midi, sd, hp, which, noise):
+    """stylesinger.py:249-311, infer. Returns [B,F,2] (f0 log2-Hz, uv)."""
+    lo, hi = midi_clip_band(midi)
+    p = "gm_diffnet." if which == 0 else "gm_diffnet_inpainte."
+    pred = f0_diffusion_sample(dec_inp.transpose(-1, -2), (lo, hi), sd, hp, p, noise)
+    f0, uv = pred[:, :, 0], pred[:, :, 1].clone()
+    uv[midi[:, 0, :] == 0] = 1
+    f0 = (f0 + 1) / 2 * (10 - 6) + 6
+    return torch.cat([f0[:, :, None], uv[:, :, None]], dim=2)
+
+
+def inpaint_pitch(agn, spec, mel2ph, midi, sd, hp, noise, f0=None, uv=None):
+    """StyleSinger.inpaint_pitch (stylesinger.py:216-247). Returns dict."""
+    pad = mel2ph == 0
+    pa = add_gmdiff_pitch(agn, midi, sd, hp, 0, noise)
+    ps = add_gmdiff_pitch(spec, midi, sd, hp, 1, noise)
+    pred = ps / 2 + pa / 2
+    if f0 is None:
+        f0 = pred[:, :, 0]
+        uv = pred[:, :, 1] > 0
+    f0_denorm = 2 ** f0
+    f0_denorm = torch.where(uv > 0, torch.zeros_like(f0_denorm), f0_denorm)
+    f0_denorm = torch.where(pad, torch.zeros_like(f0_denorm), f0_denorm)
+    pitch = f0_to_coarse(f0_denorm)
+    emb = F.embedding(pitch, sd["pitch_embed.weight"], padding_idx=0)
+    return {"pitch_pred": pred, "f0_denorm": f0_denorm, "pitch": pitch, "pitch_embed": emb,
+            "pitch_agnostic": pa, "pitch_specific": ps}
+
+
+# ----------------------------------------------------------------------------------------------
+# a17 + whole model
+# ----------------------------------------------------------------------------------------------
+def stylesinger_forward(sd, hp, txt_tokens, note, note_dur, note_type, spk_embed, emo_embed, ref_mels, ref_f0,
+                        noise, mel2ph=None, f0=None, uv=None, skip_diffusion=False):
+    """StyleSinger.forward(infer=True, global_steps > diff_start) (stylesinger.py:119-187) for B=1.
+    All tensors carry a leading batch dim of 1 (ref_f0 may be [R])."""
+    ret = {}
+    enc = fastspeech_encoder(txt_tokens, sd, hp) + note_encoder(note, note_dur, note_type, sd, hp["hidden_size"])
+    src_np = (txt_tokens > 0).float()[:, :, None]
+    spk = F.linear(spk_embed, sd["spk_embed_proj.weight"], sd["spk_embed_proj.bias"])[:, None, :]
+    emo = F.linear(emo_embed, sd["emo_embed_proj.weight"], sd["emo_embed_proj.bias"])[:, None, :]
+    ret["spk_embed"], ret["emo_embed"] = spk, emo
+    dur_inp = (enc + spk + emo) * src_np
+    if mel2ph is None:
+        dur, xs = duration_predictor(dur_inp, txt_tokens == 0, sd, hp)
+        ret["dur"], ret["dur_choice"] = xs, dur
+        mel2ph = length_regulator(dur, txt_tokens == 0)
+    ret["mel2ph"] = mel2ph
+    tgt_np = (mel2ph > 0).float()[:, :, None]
+    dec = expand_states(enc, mel2ph)  # UMLN = identity in eval (umln.py:49-50)
+    ret["encoder_out"] = enc
+    style, codes = get_style(dec, ref_mels, ref_f0, sd, hp)
+    ret["style"], ret["rq_codes"] = style, codes
+    midi = expand_states(note[:, :, None], mel2ph).transpose(-1, -2)
+    agn = dec * tgt_np
+    spc = (dec + spk + emo + style) * tgt_np
+    pit = inpaint_pitch(agn, spc, mel2ph, midi.float() if midi.dtype != torch.float32 else midi, sd, hp, noise, f0, uv)
+    ret.update({"pitch_pred": pit["pitch_pred"], "f0_denorm": pit["f0_denorm"], "pitch": pit["pitch"]})
+    dec = (dec + spk + pit["pitch_embed"] + emo + style) * tgt_np
+    ret["decoder_inp"] = dec
+    coarse = F.linear(fastspeech_decoder(dec, sd, hp), sd["mel_out.weight"], sd["mel_out.bias"]) * tgt_np
+    ret["coarse_mel"] = coarse
+    Fr = coarse.shape[1]
+    g = torch.cat([coarse, dec, spk.repeat(1, Fr, 1), emo.repeat(1, Fr, 1), style], dim=-1)
+    g = F.linear(g, sd["ln_proj.weight"], sd["ln_proj.bias"])
+    ret["diff_cond"] = g
+    if not skip_diffusion:
+        ret["mel_out"] = mel_diffusion_sample(g, coarse, sd, hp, noise)
+    return ret
+
+
+# ----------------------------------------------------------------------------------------------
+# a20/a21: vocoder
+# ----------------------------------------------------------------------------------------------
+def sine_gen(f0, noise, sr=48000, harmonics=8, sine_amp=0.1, noise_std=0.003):
+    """SineGen.forward/_f02sine, second definition (source.py:348-441). f0 [B,N,1] -> [B,N,9], uv [B,N,1]."""
+    dim = harmonics + 1
+    fb = f0 * torch.arange(1, dim + 1, dtype=torch.float32)[None, None, :]
+    rad = (fb / sr) % 1
+    ini = noise.rand((f0.shape[0], dim))
+    ini[:, 0] = 0
+    rad[:, 0, :] = rad[:, 0, :] + ini
+    over = torch.cumsum(rad, 1) % 1
+    idx = (over[:, 1:, :] - over[:, :-1, :]) < 0
+    shift = torch.zeros_like(rad)
+    shift[:, 1:, :] = idx * -1.0
+    sines = torch.sin(torch.cumsum(rad + shift, dim=1) * 2 * np.pi) * sine_amp
+    uv = (f0 > 0).float()
+    namp = uv * noise_std + (1 - uv) * sine_amp / 3
+    nz = namp * noise.randn(sines.shape)
+    return sines * uv + nz, uv
+
+
+def source_module(f0_up, sd, noise):
+    """SourceModuleHnNSF.forward (source.py:518-531). f0_up [B,N,1] -> har [B,N,1]."""
+    sw, uv = sine_gen(f0_up, noise)
+    har = torch.tanh(F.linear(sw, sd["m_source.l_linear.weight"], sd["m_source.l_linear.bias"]))
+    noise.randn(uv.shape)  # noise branch: drawn by the reference, unused by the generator
+    return har
+
+
+def hifigan_generator(mel, f0, sd, h, noise):
+    """HifiGanGenerator.forward after remove_weight_norm (hifigan_nsf.py:144-178).
+    mel [B,80,F], f0 [B,F] or None -> wav [B,1,256F]."""
+    rates, ks = h["upsample_rates"], h["upsample_kernel_sizes"]
+    nk = len(h["resblock_kernel_sizes"])
+    W = lambda n: fold_weight_norm(sd[n + ".weight_g"], sd[n + ".weight_v"])
+    har = None
+    if f0 is not None:
+        up = f0[:, None].repeat_interleave(int(np.prod(rates)), dim=2).transpose(1, 2)
+        har = source_module(up, sd, noise).transpose(1, 2)
+    x = F.conv1d(mel, W("conv_pre"), sd["conv_pre.bias"], padding=3)
+    for i, (u, k) in enumerate(zip(rates, ks)):
+        x = F.leaky_relu(x, 0.1)
+        x = F.conv_transpose1d(x, W(f"ups.{i}"), sd[f"ups.{i}.bias"], stride=u, padding=(k - u) // 2)
+        if har is not None:
+            if i + 1 < len(rates):
+                s = int(np.prod(rates[i + 1:]))
+                x = x + F.conv1d(har, sd[f"noise_convs.{i}.weight"], sd[f"noise_convs.{i}.bias"], stride=s, padding=s // 2)
+            else:
+                x = x + F.conv1d(har, sd[f"noise_convs.{i}.weight"], sd[f"noise_convs.{i}.bias"])
+        xs = None
+        for j, (rk, rd) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
+            r = x
+            q = f"resblocks.{i * nk + j}."
+            for m_, d in enumerate(rd):
+                xt = F.leaky_relu(r, 0.1)
+                xt = F.conv1d(xt, W(f"{q}convs1.{m_}"), sd[f"{q}convs1.{m_}.bias"], padding=(rk * d - d) // 2, dilation=d)
+                xt = F.leaky_relu(xt, 0.1)
+                xt = F.conv1d(xt, W(f"{q}convs2.{m_}"), sd[f"{q}convs2.{m_}.bias"], padding=(rk - 1) // 2)
+                r = xt + r
+            xs = r if xs is None else xs + r
+        x = xs / nk
+    x = F.leaky_relu(x)  # default slope 0.01 (hifigan_nsf.py:165)
+    x = F.conv1d(x, W("conv_post"), sd["conv_post.bias"], padding=3)
+    return torch.tanh(x)
+
+
+def postprocess_mel(mel_out, f0_denorm, hp):
+    """StyleSingerInfer.forward_model glue (inference/StyleSinger.py:54-62). numpy in / numpy out."""
+    mel = mel_out
+    mask = np.abs(mel).sum(-1) > 0
+    mel = np.clip(mel[mask], hp["mel_vmin"], hp["mel_vmax"])
+    f0 = f0_denorm
+    if len(f0) > len(mask):
+        f0 = f0[:len(mask)]
+    return mel, f0[mask]
+
+
+def spec2wav(mel, f0, vsd, h, noise):
+    """HifiGAN.spec2wav (tasks/tts/vocoder_infer/hifigan_nsf.py:62-75). mel np [F,80], f0 np [F] -> wav np."""
+    c = torch.from_numpy(np.ascontiguousarray(mel)).float().unsqueeze(0).transpose(2, 1)
+    f = None if f0 is None else torch.from_numpy(np.ascontiguousarray(f0)).float()[None, :]
+    return hifigan_generator(c, f, vsd, h, noise).view(-1).numpy()
