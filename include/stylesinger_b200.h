@@ -1,0 +1,196 @@
+/* stylesinger_b200 — C ABI of the B200-native StyleSinger hot path (libstylesinger_b200.so).
+ *
+ * The reference (AaronZ345/StyleSinger) is pure Python/PyTorch and has NO FFI of its own
+ * (SURVEY.md §8b); its extension points are Python classes and registries.  This header is the
+ * boundary a binding for that path attaches to: each entry point replaces one reference interface,
+ * cited as file:line of /root/reference.  INTEGRATION.md shows the ctypes stubs and the
+ * reference-side registrations (DIFF_DECODERS / FS_ENCODERS / FS_DECODERS / register_vocoder).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *  - all DEVICE tensors are fp32 (or int32) row-major and "tight packed": a batch of B utterances
+ *    of lengths L_b is one [sum L_b, C] matrix; `*_offsets` are HOST int32 arrays of B+1 prefix
+ *    sums.  Every utterance is processed with true-length (the reference's B=1) semantics —
+ *    results do not depend on batch composition.
+ *  - the caller owns every device buffer including the workspace (`*_workspace_bytes`); entry
+ *    points enqueue on `stream`, never allocate device memory and never synchronise — except
+ *    ssb_model_create / ssb_vocoder_create / ssb_model_set_schedule, which own the packed weights.
+ *  - return 0 on success, negative on error with a message in ssb_last_error() (thread-local).
+ *  - noise: NULL noise pointers select the in-kernel counter-based generator (Philox, `seed`);
+ *    non-NULL pointers inject the noise explicitly (parity mode; SURVEY.md A.10 draw order).
+ */
+#ifndef STYLESINGER_B200_H
+#define STYLESINGER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssb_model ssb_model_t;     /* packed StyleSinger acoustic model (immutable after create) */
+typedef struct ssb_vocoder ssb_vocoder_t; /* packed HiFi-GAN(-NSF) generator */
+
+/* One named fp32 HOST tensor of a reference state_dict (names exactly as in the reference's
+ * checkpoints: utils/commons/ckpt_utils.py:26-67 loads state_dict['model']). */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} ssb_tensor_desc;
+
+/* egs/stylesinger.yaml keys the kernels are specialised on (reference egs/stylesinger.yaml:10-141). */
+typedef struct {
+  int32_t hidden_size;     /* 256 */
+  int32_t enc_layers, dec_layers;           /* 4, 4 */
+  int32_t enc_ffn_kernel, dec_ffn_kernel;   /* 9, 9 */
+  int32_t dur_layers, dur_kernel;           /* 2, 3 */
+  int32_t n_tokens;                         /* len(phone dictionary) */
+  int32_t n_rq, rq_depth;                   /* 128, 4 */
+  int32_t mel_channels, mel_layers, mel_cycle; /* residual_channels 256, residual_layers 20, dilation_cycle_length 4 */
+  int32_t f0_channels, f0_layers, f0_cycle;    /* 192, 10, 4 */
+  int32_t mel_bins;                         /* 80 */
+} ssb_hparams;
+
+/* HiFi-GAN generator config (checkpoints/hifigan/config.yaml keys read at
+ * tasks/tts/vocoder_infer/hifigan_nsf.py:48-60, modules/hifigan/hifigan_nsf.py:104-142). */
+typedef struct {
+  int32_t n_up;
+  int32_t up_rates[8];
+  int32_t up_kernels[8];
+  int32_t initial_channel;
+  int32_t n_res;
+  int32_t res_kernels[4];
+  int32_t res_dilations[4][3];
+  int32_t use_pitch_embed; /* NSF harmonic source */
+  int32_t sample_rate;
+} ssb_vocoder_config;
+
+int ssb_version(void);
+const char* ssb_last_error(void);
+
+/* Replaces StyleSinger.__init__ + load_ckpt (modules/StyleSinger/stylesinger.py:46-117,
+ * utils/commons/ckpt_utils.py:26-67).  Extra host-computed constant expected in `tensors`:
+ *   "__pos_table" [rows,256]: SinusoidalPositionalEmbedding.get_embedding(rows,256,0)
+ *   (modules/commons/common_layers.py:111-127), rows >= max sequence length + 2. */
+int ssb_model_create(ssb_model_t** out, const ssb_tensor_desc* tensors, int32_t n, const ssb_hparams* hp);
+void ssb_model_free(ssb_model_t* m);
+
+/* Diffusion schedules (GaussianDiffusion.__init__ modules/diff/shallow_diffusion_tts.py:68-122;
+ * GaussianMultinomialDiffusion.__init__ modules/diff/gaussian_multinomial_diffusion.py:208-284).
+ * which: 0 = mel denoiser, 1 = both F0 denoisers.  Host arrays:
+ *   step_emb [T, C]   SinusoidalPosEmb(t) (modules/diff/net.py:31-44), C = residual channels
+ *   gauss_tab [T, 8]  {sqrt_recip_ac, sqrt_recipm1_ac, post_coef1, post_coef2, sigma, sqrt_ac, sqrt_1m_ac, 0}
+ *   multi_tab [T, 8]  {log_alpha_t, log_1m_alpha_t, log_cumprod_alpha_{t-1}, log_1m_cumprod_alpha_{t-1}, ...} (which==1)
+ * Builds the per-layer step-bias table [T, L, C] on the device.  Synchronises `stream`. */
+int ssb_model_set_schedule(ssb_model_t* m, int32_t which, int32_t T, const float* step_emb, const float* gauss_tab,
+                           const float* multi_tab, void* stream);
+
+/* Inputs of StyleSinger.forward(..., infer=True) (modules/StyleSinger/stylesinger.py:119-187). */
+typedef struct {
+  int32_t B;
+  const int32_t* ph_offsets;    /* host [B+1] */
+  const int32_t* frame_offsets; /* host [B+1]; required by ssb_acoustic_forward */
+  const int32_t* ref_offsets;   /* host [B+1] */
+  const int32_t* txt_tokens;    /* dev [sumP] */
+  const int32_t* note;          /* dev [sumP] */
+  const int32_t* note_type;     /* dev [sumP] */
+  const float* note_dur;        /* dev [sumP] */
+  const float* spk_embed;       /* dev [B,256] */
+  const float* emo_embed;       /* dev [B,256] */
+  const float* ref_mels;        /* dev [sumR,80] */
+  const float* ref_f0;          /* dev [sumR] */
+  const int32_t* mel2ph;        /* dev [sumF] 1-based phone index per frame, or NULL -> use `dur` */
+  const int32_t* dur;           /* dev [sumP] frames per phone (from ssb_predict_durations), or NULL */
+  const float* f0;              /* dev [sumF] optional teacher-forced log2-Hz f0 (forward kwarg f0) */
+  const float* uv;              /* dev [sumF] optional teacher-forced uv */
+  const float* f0_gauss_noise[2]; /* dev [(T_f0+1), sumF]: z init then one per step t=T-1..0; NULL -> Philox */
+  const float* f0_unif_noise[2];  /* dev [T_f0, sumF, 2] */
+  const float* mel_noise;         /* dev [(T+1), sumF, 80]: q_sample then one per step */
+  uint64_t seed;
+  int32_t skip_mel_diffusion;     /* 1: stop after the coarse mel / diff_cond */
+} ssb_acoustic_inputs;
+
+/* Outputs (all optional except mel_out/f0_denorm when diffusion runs); device, tight packed. */
+typedef struct {
+  float* mel_out;       /* [sumF,80]   ret['mel_out'] */
+  float* f0_denorm;     /* [sumF]      ret['f0_denorm'] (Hz) */
+  float* encoder_out;   /* [sumP,256]  encoder(txt)+note_encoder */
+  float* style;         /* [sumF,256]  ret['style'] */
+  int32_t* rq_codes;    /* [sumR,4]    RVQ indices */
+  float* pitch_pred;    /* [sumF,2]    ret['pitch_pred'] */
+  float* decoder_inp;   /* [sumF,256]  ret['decoder_inp'] */
+  float* coarse_mel;    /* [sumF,80]   FFT-decoder mel before diffusion */
+  float* diff_cond;     /* [sumF,256]  ln_proj(cat[...]) */
+  int32_t* mel2ph;      /* [sumF] */
+  float* spk_proj;      /* [B,256] ret['spk_embed'] */
+  float* emo_proj;      /* [B,256] ret['emo_embed'] */
+} ssb_acoustic_outputs;
+
+/* FastSpeech2.add_dur -> DurationPredictor.inference (modules/fastspeech/fs2.py:151-174,
+ * modules/fastspeech/tts_modules.py:105-130): dur[p] = clamp(round(exp(x)-1), 0).
+ * The host reads `dur_out` back to size the frame axis (the reference syncs here too). */
+size_t ssb_durations_workspace_bytes(const ssb_model_t* m, const ssb_acoustic_inputs* in);
+int ssb_predict_durations(const ssb_model_t* m, const ssb_acoustic_inputs* in, int32_t* dur_out, float* logdur_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* StyleSinger.forward(infer=True, global_steps > diff_start): rows a1-a19 of SURVEY.md §8. */
+size_t ssb_acoustic_workspace_bytes(const ssb_model_t* m, const ssb_acoustic_inputs* in);
+int ssb_acoustic_forward(const ssb_model_t* m, const ssb_acoustic_inputs* in, const ssb_acoustic_outputs* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* DiffusionDecoder.forward(infer=True) alone (modules/diff/shallow_diffusion_tts.py:284-307):
+ * cond [sumF,256], coarse [sumF,80] -> mel [sumF,80]. */
+size_t ssb_mel_diffusion_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, int32_t B);
+int ssb_mel_diffusion_sample(const ssb_model_t* m, const float* cond, const float* coarse_mel,
+                             const int32_t* frame_offsets, int32_t B, const float* noise, uint64_t seed,
+                             float* mel_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One denoiser evaluation, DiffNet.forward / DDiffNet.forward (modules/diff/net.py:107-130,242-266).
+ * which: 0 mel (x [sumF,80] -> eps [sumF,80]); 1 / 2 F0 agnostic / specific (x = f0 [sumF], uv int32 [sumF]
+ * -> out [sumF,3]). */
+int ssb_denoiser_eval(const ssb_model_t* m, int32_t which, const float* x, const int32_t* uv, int32_t t,
+                      const float* cond, const int32_t* frame_offsets, int32_t B, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* GaussianMultinomialDiffusion.sample (modules/diff/gaussian_multinomial_diffusion.py:921-942).
+ * which: 0 agnostic net (gm_diffnet), 1 specific (gm_diffnet_inpainte). cond [sumF,256], clip lo/hi [sumF]
+ * -> f0_norm [sumF] (normalised), uv int32 [sumF]. */
+int ssb_f0_diffusion_sample(const ssb_model_t* m, int32_t which, const float* cond, const float* clip_lo,
+                            const float* clip_hi, const int32_t* frame_offsets, int32_t B, const float* gauss_noise,
+                            const float* unif_noise, uint64_t seed, float* f0_norm_out, int32_t* uv_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* RQBottleneck.forward / VQEmbedding.find_nearest_embedding (modules/StyleSinger/RQ.py:262-270,29-55). */
+int ssb_rvq_lookup(const ssb_model_t* m, const float* x /*[sumR,256]*/, const int32_t* ref_offsets, int32_t B,
+                   float* quant_out /*[sumR,256]*/, int32_t* codes_out /*[sumR,depth]*/, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* HifiGanGenerator (modules/hifigan/hifigan_nsf.py:104-178) with weight norm folded at pack time. */
+int ssb_vocoder_create(ssb_vocoder_t** out, const ssb_tensor_desc* tensors, int32_t n, const ssb_vocoder_config* cfg);
+void ssb_vocoder_free(ssb_vocoder_t* v);
+
+/* HifiGAN.spec2wav / HifiGanGenerator.forward (tasks/tts/vocoder_infer/hifigan_nsf.py:62-75,
+ * modules/hifigan/hifigan_nsf.py:144-169).  mel [sumF,80] (already masked/clipped as
+ * inference/StyleSinger.py:56-58 does), f0 [sumF] Hz or NULL.  rand_ini [B,9] / src_noise [sumF*hop, 9]:
+ * SineGen's torch.rand / torch.randn draws (modules/parallel_wavegan/models/source.py:357,436) or NULL.
+ * wav_out [sumF*hop]. */
+size_t ssb_vocoder_workspace_bytes(const ssb_vocoder_t* v, const int32_t* frame_offsets, int32_t B);
+int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* f0, const int32_t* frame_offsets,
+                         int32_t B, const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Unit-test granularity: one Conv1d over ragged rows with torch-layout HOST weights [N,Cin,k]
+ * (packs on the fly with cudaMalloc; not for production use).  act: 0 none 1 relu 2 gelu 3 leaky(0.1) 4 tanh. */
+int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
+                  const float* b_host, int32_t N, int32_t k, int32_t dilation, int32_t act, float* out, void* stream);
+/* Unit-test granularity: multi-head attention, 2 heads x 128; q [sumL,256], k/v [sumS,256]. */
+int ssb_op_attention(const float* q, const float* k, const float* v, const int32_t* q_offsets,
+                     const int32_t* k_offsets, int32_t B, float scale, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYLESINGER_B200_H */

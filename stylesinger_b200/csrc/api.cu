@@ -1,0 +1,532 @@
+// extern "C" boundary (include/stylesinger_b200.h) + the whole-model driver.
+#include <string.h>
+
+#include "stages.cuh"
+
+struct ssb_model { ssb::Model m; };
+struct ssb_vocoder { ssb::Vocoder v; };
+
+namespace ssb {
+
+#define RUN(x)                 \
+  do {                         \
+    int rc_ = (x);             \
+    if (rc_ != 0) return rc_;  \
+  } while (0)
+#define WS_OK(c) SSB_CHECK((c).dry || !(c).failed, "workspace too small")
+
+static int32_t* alloc_rows_i32(Ctx& c, const SeqDev& s, int C = 1) {
+  int32_t* p = c.alloc<int32_t>((size_t)s.rows * C);
+  if (!c.dry && p && !c.failed) cudaMemsetAsync(p, 0, (size_t)s.rows * C * sizeof(int32_t), c.stream);
+  return p;
+}
+
+// project per-utterance vectors (spk_embed_proj / emo_embed_proj, stylesinger.py:130-132)
+static int project_vec(Ctx& c, const Conv& w, const float* in_tight, int B, float* out_tight) {
+  Seq s1;
+  int32_t offs[2] = {0, B};
+  s1.build(offs, 1);
+  const size_t mk = c.mark();
+  SeqDev sd;
+  RUN(upload_layout(c, s1, 1, &sd));
+  float* a = alloc_rows(c, sd, 256);
+  float* o = alloc_rows(c, sd, 256);
+  WS_OK(c);
+  RUN(pack_rows(c, sd, in_tight, 256, a, 256, 256));
+  ConvGemm g = make_gemm(w, sd, a, 256);
+  g.e.out = o; g.e.ldo = 256;
+  RUN(conv_gemm(c, g));
+  RUN(unpack_rows(c, sd, o, 256, out_tight, 256, 256));
+  c.release(mk);
+  return 0;
+}
+
+// StyleSinger.forward(infer=True) (stylesinger.py:119-187); durations_only stops after add_dur.
+int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ssb_acoustic_outputs& out,
+                 bool durations_only, int32_t* dur_out, float* logdur_out) {
+  const int H = 256, B = in.B;
+  SSB_CHECK(B >= 1 && in.ph_offsets && in.ref_offsets, "acoustic: bad batch description");
+  SSB_CHECK(durations_only || in.frame_offsets, "acoustic: frame_offsets required");
+  SSB_CHECK(durations_only || in.mel2ph || in.dur, "acoustic: need mel2ph or dur");
+  Seq qp, qr, qf;
+  qp.build(in.ph_offsets, B);
+  qr.build(in.ref_offsets, B);
+  SSB_CHECK(qp.maxlen + 2 <= m.pos_rows && qr.maxlen + 2 <= m.pos_rows, "sequence longer than __pos_table");
+  SeqDev sp, sr, sf;
+  RUN(upload_layout(c, qp, 1, &sp));
+  RUN(upload_layout(c, qr, 1, &sr));
+  int32_t* tok = alloc_rows_i32(c, sp);
+  int32_t* note = alloc_rows_i32(c, sp);
+  int32_t* ntype = alloc_rows_i32(c, sp);
+  float* ndur = alloc_rows(c, sp, 1);
+  float* srcmask = alloc_rows(c, sp, 1);
+  float* enc = alloc_rows(c, sp, H);
+  float* spk = c.alloc<float>((size_t)B * H);
+  float* emo = c.alloc<float>((size_t)B * H);
+  WS_OK(c);
+  RUN(pack_rows_i32(c, sp, in.txt_tokens, tok));
+  RUN(pack_rows_i32(c, sp, in.note, note));
+  RUN(pack_rows_i32(c, sp, in.note_type, ntype));
+  RUN(pack_rows(c, sp, in.note_dur, 1, ndur, 1, 1));
+  RUN(project_vec(c, m.spk_proj, in.spk_embed, B, spk));
+  RUN(project_vec(c, m.emo_proj, in.emo_embed, B, emo));
+  if (out.spk_proj && !c.dry) SSB_CUDA(cudaMemcpyAsync(out.spk_proj, spk, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, c.stream));
+  if (out.emo_proj && !c.dry) SSB_CUDA(cudaMemcpyAsync(out.emo_proj, emo, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, c.stream));
+  RUN(run_encoder(c, m, sp, tok, note, ntype, ndur, srcmask, enc));
+  if (out.encoder_out) RUN(unpack_rows(c, sp, enc, H, out.encoder_out, H, H));
+
+  if (durations_only) {
+    float* dinp = alloc_rows(c, sp, H);
+    float* logdur = alloc_rows(c, sp, 1);
+    int32_t* dur = alloc_rows_i32(c, sp);
+    WS_OK(c);
+    CombineArgs a;  // dur_inp = (encoder_out + spk + emo) * src_nonpadding (stylesinger.py:134-138)
+    a.m[0] = enc; a.ldm[0] = H; a.v[0] = spk; a.v[1] = emo; a.rowmask = srcmask; a.out = dinp; a.ldo = H; a.C = H;
+    RUN(combine_rows(c, sp, a));
+    RUN(run_duration_predictor(c, m, sp, dinp, srcmask, logdur, dur));
+    if (dur_out) RUN(unpack_rows_i32(c, sp, dur, dur_out));
+    if (logdur_out) RUN(unpack_rows(c, sp, logdur, 1, logdur_out, 1, 1));
+    return 0;
+  }
+
+  qf.build(in.frame_offsets, B);
+  SSB_CHECK(qf.maxlen + 2 <= m.pos_rows, "frame sequence longer than __pos_table");
+  RUN(upload_layout(c, qf, 1, &sf));
+  int32_t* mel2ph = alloc_rows_i32(c, sf);
+  int32_t* midi = alloc_rows_i32(c, sf);
+  float* tgt = alloc_rows(c, sf, 1);
+  float* dec0 = alloc_rows(c, sf, H);
+  float* ref = alloc_rows(c, sr, 80);
+  float* reff0 = alloc_rows(c, sr, 1);
+  float* style = alloc_rows(c, sf, H);
+  int32_t* codes = alloc_rows_i32(c, sr, m.hp.rq_depth);
+  WS_OK(c);
+  if (in.mel2ph) {
+    RUN(pack_rows_i32(c, sf, in.mel2ph, mel2ph));
+  } else {
+    int32_t* dur = alloc_rows_i32(c, sp);
+    WS_OK(c);
+    RUN(pack_rows_i32(c, sp, in.dur, dur));
+    RUN(length_regulate(c, sf, sp, dur, mel2ph));
+  }
+  if (out.mel2ph) RUN(unpack_rows_i32(c, sf, mel2ph, out.mel2ph));
+  RUN(expand_states(c, sf, sp, mel2ph, enc, H, dec0, H, H, note, midi, tgt));
+  RUN(pack_rows(c, sr, in.ref_mels, 80, ref, 80, 80));
+  RUN(pack_rows(c, sr, in.ref_f0, 1, reff0, 1, 1));
+  RUN(run_style(c, m, sf, sr, dec0, ref, reff0, style, codes, nullptr));
+  if (out.style) RUN(unpack_rows(c, sf, style, H, out.style, H, H));
+  if (out.rq_codes) {
+    // codes are [rows, depth] int32: unpack column by column through the i32 row copier
+    for (int d = 0; d < m.hp.rq_depth; ++d) RUN(unpack_cols_i32(c, sr, codes, m.hp.rq_depth, d, out.rq_codes));
+  }
+
+  // ---- pitch (inpaint_pitch, stylesinger.py:216-247)
+  float* pitch_pred = alloc_rows(c, sf, 2);
+  float* f0_denorm = alloc_rows(c, sf, 1);
+  int32_t* pitch = alloc_rows_i32(c, sf);
+  float* f0_in = nullptr;
+  float* uv_in = nullptr;
+  WS_OK(c);
+  {
+    const size_t mk = c.mark();
+    float* za = alloc_rows(c, sf, 1);
+    float* zs = alloc_rows(c, sf, 1);
+    int32_t* uva = alloc_rows_i32(c, sf);
+    int32_t* uvs = alloc_rows_i32(c, sf);
+    WS_OK(c);
+    if (in.f0) {
+      // teacher forcing: the reference skips the samplers when f0 is passed (add_gmdiff_pitch :251-254)
+      f0_in = alloc_rows(c, sf, 1);
+      uv_in = alloc_rows(c, sf, 1);
+      WS_OK(c);
+      RUN(pack_rows(c, sf, in.f0, 1, f0_in, 1, 1));
+      if (in.uv) RUN(pack_rows(c, sf, in.uv, 1, uv_in, 1, 1));
+    } else {
+      float* lo = alloc_rows(c, sf, 1);
+      float* hi = alloc_rows(c, sf, 1);
+      float* cond = alloc_rows(c, sf, H);
+      WS_OK(c);
+      RUN(midi_clip_band(c, sf, midi, lo, hi));
+      {
+        CombineArgs a;  // pitch_inp_domain_agnostic = decoder_inp * tgt_nonpadding (:156)
+        a.m[0] = dec0; a.ldm[0] = H; a.rowmask = tgt; a.out = cond; a.ldo = H; a.C = H;
+        RUN(combine_rows(c, sf, a));
+      }
+      RUN(run_f0_diffusion(c, m, 0, sf, cond, lo, hi, in.f0_gauss_noise[0], in.f0_unif_noise[0], in.seed, za, uva));
+      {
+        CombineArgs a;  // (decoder_inp + spk + emo + style) * tgt_nonpadding (:157-162)
+        a.m[0] = dec0; a.ldm[0] = H; a.m[1] = style; a.ldm[1] = H; a.v[0] = spk; a.v[1] = emo;
+        a.rowmask = tgt; a.out = cond; a.ldo = H; a.C = H;
+        RUN(combine_rows(c, sf, a));
+      }
+      RUN(run_f0_diffusion(c, m, 1, sf, cond, lo, hi, in.f0_gauss_noise[1], in.f0_unif_noise[1], in.seed, zs, uvs));
+    }
+    PitchGlueArgs pg;
+    pg.za = za; pg.uva = uva; pg.zs = zs; pg.uvs = uvs; pg.midi = midi; pg.mel2ph = mel2ph;
+    pg.f0_in = f0_in; pg.uv_in = in.uv ? uv_in : nullptr;
+    pg.pitch_pred = pitch_pred; pg.f0_denorm = f0_denorm; pg.pitch = pitch;
+    RUN(pitch_glue(c, sf, pg));
+    c.release(mk);
+  }
+  if (out.pitch_pred) RUN(unpack_rows(c, sf, pitch_pred, 2, out.pitch_pred, 2, 2));
+  if (out.f0_denorm) RUN(unpack_rows(c, sf, f0_denorm, 1, out.f0_denorm, 1, 1));
+
+  // ---- decoder input (:165-172)
+  float* dec = alloc_rows(c, sf, H);
+  float* pemb = alloc_rows(c, sf, H);
+  WS_OK(c);
+  RUN(embed_rows(c, sf, pitch, m.pitch_emb, 300, 1.0f, pemb, H, H, 0));
+  {
+    CombineArgs a;
+    a.m[0] = dec0; a.ldm[0] = H; a.m[1] = pemb; a.ldm[1] = H; a.m[2] = style; a.ldm[2] = H;
+    a.v[0] = spk; a.v[1] = emo; a.rowmask = tgt; a.out = dec; a.ldo = H; a.C = H;
+    RUN(combine_rows(c, sf, a));
+  }
+  if (out.decoder_inp) RUN(unpack_rows(c, sf, dec, H, out.decoder_inp, H, H));
+
+  // ---- FFT decoder + mel_out (fs2.py:233-237, tts_modules.py:281-306)
+  float* coarse = alloc_rows(c, sf, 80);
+  float* cond = alloc_rows(c, sf, H);
+  WS_OK(c);
+  {
+    const size_t mk = c.mark();
+    float* xd = alloc_rows(c, sf, H);
+    float* keep = alloc_rows(c, sf, 1);
+    float* c0 = alloc_rows(c, sf, 1);
+    int32_t* pos = alloc_rows_i32(c, sf);
+    WS_OK(c);
+    if (!c.dry) SSB_CUDA(cudaMemcpyAsync(xd, dec, (size_t)sf.rows * H * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+    RUN(row_nonzero_mask(c, sf, dec, H, H, keep));
+    RUN(col0_nonzero_mask(c, sf, dec, H, c0));
+    RUN(positions_from_mask(c, sf, c0, pos));
+    RUN(add_positional(c, sf, xd, H, H, pos, m.pos_table, m.pos_rows, m.dec.pos_alpha));
+    {
+      CombineArgs a;
+      a.m[0] = xd; a.ldm[0] = H; a.rowmask = keep; a.out = xd; a.ldo = H; a.C = H;
+      RUN(combine_rows(c, sf, a));
+    }
+    RUN(fft_blocks(c, m.dec, sf, xd, keep));
+    {
+      ConvGemm g = make_gemm(m.mel_out, sf, xd, H);
+      g.e.rowmask = tgt; g.e.out = coarse; g.e.ldo = 80;
+      RUN(conv_gemm(c, g));
+    }
+    // run_diffsinger: g = ln_proj(cat[coarse, decoder_inp, spk, emo, style]) (stylesinger.py:313-327)
+    float* cat = alloc_rows(c, sf, 1104);
+    WS_OK(c);
+    RUN(concat_cond(c, sf, coarse, dec, spk, emo, style, cat));
+    {
+      ConvGemm g = make_gemm(m.ln_proj, sf, cat, 1104);
+      g.e.out = cond; g.e.ldo = H;
+      RUN(conv_gemm(c, g));
+    }
+    c.release(mk);
+  }
+  if (out.coarse_mel) RUN(unpack_rows(c, sf, coarse, 80, out.coarse_mel, 80, 80));
+  if (out.diff_cond) RUN(unpack_rows(c, sf, cond, H, out.diff_cond, H, H));
+  if (!in.skip_mel_diffusion) {
+    SSB_CHECK(out.mel_out != nullptr, "acoustic: mel_out required");
+    RUN(run_mel_diffusion(c, m, sf, cond, coarse, in.mel_noise, in.seed, out.mel_out));
+  }
+  return 0;
+}
+
+int denoiser_eval_api(Ctx& c, const Model& m, int which, const SeqDev& s, const float* x_tight, const int32_t* uv_tight,
+                      int t, const float* cond_tight, float* out_tight) {
+  const Denoiser& d = which == 0 ? m.melnet : m.f0net[which - 1];
+  SSB_CHECK(d.T > 0, "denoiser_eval: schedule not set");
+  float* cond = alloc_rows(c, s, 256);
+  float* x = alloc_rows(c, s, d.C);
+  float* y = alloc_rows(c, s, d.C);
+  float* zg = alloc_rows(c, s, d.C);
+  float* skip = alloc_rows(c, s, d.C);
+  float* sb = alloc_rows(c, s, d.C);
+  const int ldh = (d.out_dims + 3) & ~3;
+  float* head = alloc_rows(c, s, ldh);
+  float* condall = alloc_rows(c, s, d.L * 2 * d.C, false);
+  WS_OK(c);
+  RUN(pack_rows(c, s, cond_tight, 256, cond, 256, 256));
+  {
+    ConvGemm g = make_gemm(d.cond_all, s, cond, 256);
+    g.e.out = condall; g.e.ldo = d.L * 2 * d.C;
+    RUN(conv_gemm(c, g));
+  }
+  const float* dt = d.dtab + (size_t)t * d.L * d.C;
+  if (which == 0) {
+    float* x80 = alloc_rows(c, s, 80);
+    WS_OK(c);
+    RUN(pack_rows(c, s, x_tight, 80, x80, 80, 80));
+    ConvGemm g = make_gemm(d.in_proj, s, x80, 80);
+    g.e.act = ACT_RELU; g.e.out = x; g.e.ldo = d.C; g.e.out2 = y; g.e.ldo2 = d.C; g.e.vec2 = dt;
+    RUN(conv_gemm(c, g));
+  } else {
+    float* z = alloc_rows(c, s, 1);
+    int32_t* uv = alloc_rows_i32(c, s);
+    WS_OK(c);
+    RUN(pack_rows(c, s, x_tight, 1, z, 1, 1));
+    RUN(pack_rows_i32(c, s, uv_tight, uv));
+    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, x, y, d.C));
+  }
+  RUN(denoiser_stack(c, d, s, t, x, y, condall, zg, skip, sb, head, ldh));
+  RUN(unpack_rows(c, s, head, ldh, out_tight, d.out_dims, d.out_dims));
+  return 0;
+}
+
+}  // namespace ssb
+
+// ================================================================================================
+using namespace ssb;
+
+static int to_map(const ssb_tensor_desc* t, int n, TensorMap* tm) {
+  for (int i = 0; i < n; ++i) {
+    SSB_CHECK(t[i].name && t[i].data && t[i].ndim >= 1 && t[i].ndim <= 4, "bad tensor descriptor");
+    HostTensor h;
+    h.data = t[i].data;
+    for (int d = 0; d < t[i].ndim; ++d) h.shape.push_back(t[i].shape[d]);
+    tm->t[t[i].name] = h;
+  }
+  return 0;
+}
+static Ctx make_ctx(void* ws, size_t bytes, void* stream, bool dry = false) {
+  Ctx c;
+  c.base = (char*)ws; c.cap = bytes; c.stream = (cudaStream_t)stream; c.dry = dry;
+  return c;
+}
+
+extern "C" {
+
+int ssb_version(void) { return 100; }
+const char* ssb_last_error(void) { return ssb::last_error(); }
+
+int ssb_model_create(ssb_model_t** out, const ssb_tensor_desc* tensors, int32_t n, const ssb_hparams* hp) {
+  SSB_CHECK(out && tensors && hp, "ssb_model_create: null argument");
+  TensorMap tm;
+  if (to_map(tensors, n, &tm)) return -1;
+  ssb_model* m = new ssb_model();
+  if (build_model(tm, *hp, &m->m) != 0) {
+    delete m;
+    return -1;
+  }
+  *out = m;
+  return 0;
+}
+void ssb_model_free(ssb_model_t* m) { delete m; }
+
+int ssb_model_set_schedule(ssb_model_t* m, int32_t which, int32_t T, const float* step_emb, const float* gauss_tab,
+                           const float* multi_tab, void* stream) {
+  SSB_CHECK(m, "null model");
+  return set_schedule(&m->m, which, T, step_emb, gauss_tab, multi_tab, (cudaStream_t)stream);
+}
+
+size_t ssb_durations_workspace_bytes(const ssb_model_t* m, const ssb_acoustic_inputs* in) {
+  Ctx c = make_ctx(nullptr, 0, nullptr, true);
+  ssb_acoustic_outputs o;
+  memset(&o, 0, sizeof(o));
+  if (run_acoustic(c, m->m, *in, o, true, nullptr, nullptr) != 0) return 0;
+  return c.high + 4096;
+}
+int ssb_predict_durations(const ssb_model_t* m, const ssb_acoustic_inputs* in, int32_t* dur_out, float* logdur_out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && in && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  ssb_acoustic_outputs o;
+  memset(&o, 0, sizeof(o));
+  return run_acoustic(c, m->m, *in, o, true, dur_out, logdur_out);
+}
+size_t ssb_acoustic_workspace_bytes(const ssb_model_t* m, const ssb_acoustic_inputs* in) {
+  Ctx c = make_ctx(nullptr, 0, nullptr, true);
+  ssb_acoustic_outputs o;
+  memset(&o, 0, sizeof(o));
+  o.mel_out = (float*)(uintptr_t)256;
+  if (run_acoustic(c, m->m, *in, o, false, nullptr, nullptr) != 0) return 0;
+  return c.high + 4096;
+}
+int ssb_acoustic_forward(const ssb_model_t* m, const ssb_acoustic_inputs* in, const ssb_acoustic_outputs* out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && in && out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  return run_acoustic(c, m->m, *in, *out, false, nullptr, nullptr);
+}
+
+static int mel_diff_impl(Ctx& c, const Model& m, const float* cond, const float* coarse, const int32_t* offs, int B,
+                         const float* noise, uint64_t seed, float* mel_out) {
+  Seq q;
+  q.build(offs, B);
+  SeqDev s;
+  RUN(upload_layout(c, q, 1, &s));
+  float* cg = alloc_rows(c, s, 256);
+  float* co = alloc_rows(c, s, 80);
+  WS_OK(c);
+  RUN(pack_rows(c, s, cond, 256, cg, 256, 256));
+  RUN(pack_rows(c, s, coarse, 80, co, 80, 80));
+  return run_mel_diffusion(c, m, s, cg, co, noise, seed, mel_out);
+}
+size_t ssb_mel_diffusion_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, int32_t B) {
+  Ctx c = make_ctx(nullptr, 0, nullptr, true);
+  if (mel_diff_impl(c, m->m, nullptr, nullptr, frame_offsets, B, nullptr, 0, nullptr) != 0) return 0;
+  return c.high + 4096;
+}
+int ssb_mel_diffusion_sample(const ssb_model_t* m, const float* cond, const float* coarse_mel,
+                             const int32_t* frame_offsets, int32_t B, const float* noise, uint64_t seed,
+                             float* mel_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && cond && coarse_mel && frame_offsets && mel_out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  return mel_diff_impl(c, m->m, cond, coarse_mel, frame_offsets, B, noise, seed, mel_out);
+}
+
+int ssb_denoiser_eval(const ssb_model_t* m, int32_t which, const float* x, const int32_t* uv, int32_t t,
+                      const float* cond, const int32_t* frame_offsets, int32_t B, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && x && cond && frame_offsets && out && workspace && which >= 0 && which <= 2, "bad argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  Seq q;
+  q.build(frame_offsets, B);
+  SeqDev s;
+  RUN(upload_layout(c, q, 1, &s));
+  return denoiser_eval_api(c, m->m, which, s, x, uv, t, cond, out);
+}
+
+int ssb_f0_diffusion_sample(const ssb_model_t* m, int32_t which, const float* cond, const float* clip_lo,
+                            const float* clip_hi, const int32_t* frame_offsets, int32_t B, const float* gauss_noise,
+                            const float* unif_noise, uint64_t seed, float* f0_norm_out, int32_t* uv_out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && cond && clip_lo && clip_hi && frame_offsets && f0_norm_out && uv_out && workspace, "null argument");
+  SSB_CHECK(which == 0 || which == 1, "which must be 0 or 1");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  Seq q;
+  q.build(frame_offsets, B);
+  SeqDev s;
+  RUN(upload_layout(c, q, 1, &s));
+  float* cg = alloc_rows(c, s, 256);
+  float* lo = alloc_rows(c, s, 1);
+  float* hi = alloc_rows(c, s, 1);
+  float* z = alloc_rows(c, s, 1);
+  int32_t* uv = alloc_rows_i32(c, s);
+  WS_OK(c);
+  RUN(pack_rows(c, s, cond, 256, cg, 256, 256));
+  RUN(pack_rows(c, s, clip_lo, 1, lo, 1, 1));
+  RUN(pack_rows(c, s, clip_hi, 1, hi, 1, 1));
+  RUN(run_f0_diffusion(c, m->m, which, s, cg, lo, hi, gauss_noise, unif_noise, seed, z, uv));
+  RUN(unpack_rows(c, s, z, 1, f0_norm_out, 1, 1));
+  RUN(unpack_rows_i32(c, s, uv, uv_out));
+  return 0;
+}
+
+int ssb_rvq_lookup(const ssb_model_t* m, const float* x, const int32_t* ref_offsets, int32_t B, float* quant_out,
+                   int32_t* codes_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && x && ref_offsets && quant_out && codes_out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  Seq q;
+  q.build(ref_offsets, B);
+  SeqDev s;
+  RUN(upload_layout(c, q, 1, &s));
+  const int D = m->m.hp.rq_depth;
+  float* xg = alloc_rows(c, s, 256);
+  float* zq = alloc_rows(c, s, 256);
+  int32_t* codes = alloc_rows_i32(c, s, D);
+  WS_OK(c);
+  RUN(pack_rows(c, s, x, 256, xg, 256, 256));
+  RUN(rvq_lookup(c, s, xg, 256, m->m.codebooks, m->m.cb_norm2, m->m.hp.n_rq, D, zq, 256, codes));
+  RUN(unpack_rows(c, s, zq, 256, quant_out, 256, 256));
+  for (int d = 0; d < D; ++d) RUN(unpack_cols_i32(c, s, codes, D, d, codes_out));
+  return 0;
+}
+
+int ssb_vocoder_create(ssb_vocoder_t** out, const ssb_tensor_desc* tensors, int32_t n, const ssb_vocoder_config* cfg) {
+  SSB_CHECK(out && tensors && cfg, "ssb_vocoder_create: null argument");
+  TensorMap tm;
+  if (to_map(tensors, n, &tm)) return -1;
+  ssb_vocoder* v = new ssb_vocoder();
+  if (build_vocoder(tm, *cfg, &v->v) != 0) {
+    delete v;
+    return -1;
+  }
+  *out = v;
+  return 0;
+}
+void ssb_vocoder_free(ssb_vocoder_t* v) { delete v; }
+
+size_t ssb_vocoder_workspace_bytes(const ssb_vocoder_t* v, const int32_t* frame_offsets, int32_t B) {
+  Ctx c = make_ctx(nullptr, 0, nullptr, true);
+  Seq q;
+  q.build(frame_offsets, B);
+  if (run_vocoder(c, v->v, q, nullptr, (const float*)(uintptr_t)256, nullptr, nullptr, 0, nullptr) != 0) return 0;
+  return c.high + 4096;
+}
+int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* f0, const int32_t* frame_offsets,
+                         int32_t B, const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(v && mel && frame_offsets && wav_out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  Seq q;
+  q.build(frame_offsets, B);
+  return run_vocoder(c, v->v, q, mel, f0, rand_ini, src_noise, seed, wav_out);
+}
+
+int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
+                  const float* b_host, int32_t N, int32_t k, int32_t dilation, int32_t act, float* out, void* stream) {
+  SSB_CHECK(x && offsets && w_host && out, "null argument");
+  DevicePool pool;
+  HostTensor w, b;
+  w.data = w_host; w.shape = {N, Cin, k};
+  b.data = b_host; b.shape = {N};
+  Conv cv;
+  if (pack_conv(pool, &w, b_host ? &b : nullptr, dilation, PACK_PLAIN, &cv)) return -1;
+  Seq q;
+  q.build(offsets, B);
+  const size_t bytes = ((size_t)q.rows() * (Cin + N + 8) + 8 * (size_t)q.ntiles() + 1024) * sizeof(float) + (1 << 16);
+  void* ws = nullptr;
+  SSB_CUDA(cudaMalloc(&ws, bytes));
+  Ctx c = make_ctx(ws, bytes, stream);
+  int rc = 0;
+  SeqDev s;
+  rc = upload_layout(c, q, 1, &s);
+  float* xg = alloc_rows(c, s, Cin);
+  float* og = alloc_rows(c, s, N);
+  if (rc == 0 && c.failed) rc = -1;
+  if (rc == 0) rc = pack_rows(c, s, x, Cin, xg, Cin, Cin);
+  if (rc == 0) {
+    ConvGemm g = make_gemm(cv, s, xg, Cin);
+    g.e.act = act; g.e.out = og; g.e.ldo = N;
+    rc = conv_gemm(c, g);
+  }
+  if (rc == 0) rc = unpack_rows(c, s, og, N, out, N, N);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(ws);
+  return rc;
+}
+
+int ssb_op_attention(const float* q, const float* k, const float* v, const int32_t* q_offsets,
+                     const int32_t* k_offsets, int32_t B, float scale, float* out, void* stream) {
+  SSB_CHECK(q && k && v && q_offsets && k_offsets && out, "null argument");
+  Seq sq, sk;
+  sq.build(q_offsets, B);
+  sk.build(k_offsets, B);
+  const size_t bytes = ((size_t)sq.rows() * 512 + (size_t)sk.rows() * 512 + 4096) * sizeof(float) + (1 << 16);
+  void* ws = nullptr;
+  SSB_CUDA(cudaMalloc(&ws, bytes));
+  Ctx c = make_ctx(ws, bytes, stream);
+  SeqDev dq, dk;
+  int rc = upload_layout(c, sq, 1, &dq);
+  if (rc == 0) rc = upload_layout(c, sk, 1, &dk);
+  float* qg = alloc_rows(c, dq, 256);
+  float* og = alloc_rows(c, dq, 256);
+  float* kg = alloc_rows(c, dk, 256);
+  float* vg = alloc_rows(c, dk, 256);
+  if (rc == 0 && c.failed) rc = -1;
+  if (rc == 0) rc = pack_rows(c, dq, q, 256, qg, 256, 256);
+  if (rc == 0) rc = pack_rows(c, dk, k, 256, kg, 256, 256);
+  if (rc == 0) rc = pack_rows(c, dk, v, 256, vg, 256, 256);
+  if (rc == 0) {
+    AttnArgs a;
+    a.utt_q = dq.utt; a.utt_k = dk.utt; a.B = B; a.max_q = dq.maxlen; a.heads = 2;
+    a.Q = qg; a.ldq = 256; a.K = kg; a.ldk = 256; a.V = vg; a.ldv = 256; a.scale = scale; a.out = og; a.ldo = 256;
+    rc = attention(c, a);
+  }
+  if (rc == 0) rc = unpack_rows(c, dq, og, 256, out, 256, 256);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(ws);
+  return rc;
+}
+
+}  // extern "C"

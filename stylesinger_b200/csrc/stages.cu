@@ -1,0 +1,508 @@
+// Stage drivers: compose the kernels into the reference's modules (one function per SURVEY.md §8a group).
+#include "stages.cuh"
+
+namespace ssb {
+
+ConvGemm make_gemm(const Conv& c, const SeqDev& s, const float* A, int lda) {
+  ConvGemm g;
+  g.A = A; g.lda = lda; g.Cin = c.Cin; g.taps = c.taps; g.dil = c.dil; g.center = c.center;
+  g.W = c.W; g.N = c.N; g.Npad = c.Npad; g.tiles = s.tiles; g.ntiles = s.ntiles;
+  g.e.bias = c.bias;
+  return g;
+}
+
+int upload_layout(Ctx& c, const Seq& s, int rate, SeqDev* out) {
+  const int nt = s.ntiles(rate);
+  int2* tiles = c.alloc<int2>((size_t)nt + 1);
+  int4* utt = c.alloc<int4>((size_t)s.B + 1);
+  out->tiles = tiles; out->ntiles = nt; out->utt = utt; out->B = s.B; out->rows = s.rows(rate);
+  out->total = s.total * rate; out->maxlen = s.maxlen * rate; out->rate = rate;
+  if (c.dry) return 0;
+  SSB_CHECK(!c.failed && tiles && utt, "workspace too small (layout tables)");
+  std::vector<int2> ht((size_t)nt + 1);
+  std::vector<int4> hu((size_t)s.B + 1);
+  int k = 0;
+  int64_t tight = 0;
+  for (int b = 0; b < s.B; ++b) {
+    const int len = s.len[b] * rate;
+    const int rs = s.rs[b] * rate;
+    hu[b] = make_int4(rs, len, (int)tight, 0);
+    tight += len;
+    for (int t0 = 0; t0 < len; t0 += TILE_M) ht[k++] = make_int2(rs + t0, (len - t0) < TILE_M ? (len - t0) : TILE_M);
+  }
+  SSB_CUDA(cudaMemcpyAsync(tiles, ht.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice, c.stream));
+  SSB_CUDA(cudaMemcpyAsync(utt, hu.data(), sizeof(int4) * s.B, cudaMemcpyHostToDevice, c.stream));
+  // pageable-source async copies are staged before returning, so the host vectors may die here
+  return 0;
+}
+
+float* alloc_rows(Ctx& c, const SeqDev& s, int C, bool zero) {
+  float* p = c.alloc<float>((size_t)s.rows * C);
+  if (!c.dry && p && !c.failed && zero) cudaMemsetAsync(p, 0, (size_t)s.rows * C * sizeof(float), c.stream);
+  return p;
+}
+static int32_t* alloc_rows_i32(Ctx& c, const SeqDev& s, int C = 1) {
+  int32_t* p = c.alloc<int32_t>((size_t)s.rows * C);
+  if (!c.dry && p && !c.failed) cudaMemsetAsync(p, 0, (size_t)s.rows * C * sizeof(int32_t), c.stream);
+  return p;
+}
+
+#define RUN(x)                 \
+  do {                         \
+    int rc_ = (x);             \
+    if (rc_ != 0) return rc_;  \
+  } while (0)
+#define WS_OK(c) SSB_CHECK((c).dry || !(c).failed, "workspace too small")
+
+// ------------------------------------------------------------------------------------------------
+// a2-a5: FFTBlocks body (tts_modules.py:293-305 + EncSALayer common_layers.py:649-673)
+// x [rows,256] in/out; keep = 1 - padding_mask (row mask, also the key mask)
+int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* keep) {
+  const int H = 256;
+  const size_t mk = c.mark();
+  float* h = alloc_rows(c, s, H);
+  float* qkv = alloc_rows(c, s, 3 * H);
+  float* att = alloc_rows(c, s, H);
+  float* ff = alloc_rows(c, s, 4 * H);
+  WS_OK(c);
+  for (size_t i = 0; i < f.layers.size(); ++i) {
+    const FFTLayer& L = f.layers[i];
+    RUN(layernorm_rows(c, s, x, H, h, H, H, L.ln1_g, L.ln1_b, 1e-5f, nullptr));
+    {
+      ConvGemm g = make_gemm(L.qkv, s, h, H);
+      g.e.out = qkv; g.e.ldo = 3 * H;
+      RUN(conv_gemm(c, g));
+    }
+    {
+      AttnArgs a;
+      a.utt_q = s.utt; a.utt_k = s.utt; a.B = s.B; a.max_q = s.maxlen; a.heads = 2;
+      a.Q = qkv; a.ldq = 3 * H; a.K = qkv + H; a.ldk = 3 * H; a.V = qkv + 2 * H; a.ldv = 3 * H;
+      a.keymask = keep; a.scale = 0.08838834764831845f;  // 128^-0.5
+      a.out = att; a.ldo = H;
+      RUN(attention(c, a));
+    }
+    {
+      ConvGemm g = make_gemm(L.out, s, att, H);
+      g.e.res = x; g.e.ld_res = H; g.e.rowmask = keep; g.e.out = x; g.e.ldo = H;
+      RUN(conv_gemm(c, g));
+    }
+    RUN(layernorm_rows(c, s, x, H, h, H, H, L.ln2_g, L.ln2_b, 1e-5f, nullptr));
+    {
+      ConvGemm g = make_gemm(L.ffn1, s, h, H);
+      g.e.alpha = 1.0f / sqrtf((float)f.kernel); g.e.act = ACT_GELU; g.e.out = ff; g.e.ldo = 4 * H;
+      RUN(conv_gemm(c, g));
+    }
+    {
+      ConvGemm g = make_gemm(L.ffn2, s, ff, 4 * H);
+      g.e.res = x; g.e.ld_res = H; g.e.rowmask = keep; g.e.out = x; g.e.ldo = H;
+      RUN(conv_gemm(c, g));
+    }
+  }
+  // final LN * mask, in place via h
+  RUN(layernorm_rows(c, s, x, H, h, H, H, f.ln_g, f.ln_b, 1e-5f, keep));
+  if (!c.dry) SSB_CUDA(cudaMemcpyAsync(x, h, (size_t)s.rows * H * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  c.release(mk);
+  return 0;
+}
+
+// a1 + a7: encoder_out = FastspeechEncoder(txt) + NoteEncoder(note, dur, type)
+int run_encoder(Ctx& c, const Model& m, const SeqDev& sp, const int32_t* tok_g, const int32_t* note_g,
+                const int32_t* type_g, const float* ndur_g, float* srcmask, float* enc_out) {
+  const int H = 256;
+  const size_t mk = c.mark();
+  int32_t* pos = alloc_rows_i32(c, sp);
+  WS_OK(c);
+  RUN(token_nonzero_mask(c, sp, tok_g, srcmask));
+  RUN(positions_from_mask(c, sp, srcmask, pos));
+  RUN(embed_rows(c, sp, tok_g, m.tok_emb, m.n_tokens, 16.0f, enc_out, H, H, 0));
+  RUN(add_positional(c, sp, enc_out, H, H, pos, m.pos_table, m.pos_rows, nullptr));
+  // FFTBlocks.forward: x = x.transpose * nonpadding (tts_modules.py:293)
+  {
+    CombineArgs a;
+    a.m[0] = enc_out; a.ldm[0] = H; a.rowmask = srcmask; a.out = enc_out; a.ldo = H; a.C = H;
+    RUN(combine_rows(c, sp, a));
+  }
+  RUN(fft_blocks(c, m.enc, sp, enc_out, srcmask));
+  RUN(note_encoder(c, sp, note_g, type_g, ndur_g, m.note_emb, m.type_emb, m.dur_w, m.dur_b, 16.0f, enc_out, H, H, 1));
+  c.release(mk);
+  return 0;
+}
+
+// a8: DurationPredictor.inference (tts_modules.py:105-130)
+int run_duration_predictor(Ctx& c, const Model& m, const SeqDev& sp, const float* dur_inp, const float* srcmask,
+                           float* logdur /*[rows]*/, int32_t* dur /*[rows]*/) {
+  const int H = 256;
+  const size_t mk = c.mark();
+  float* a = alloc_rows(c, sp, H);
+  float* b = alloc_rows(c, sp, H);
+  WS_OK(c);
+  const float* cur = dur_inp;
+  for (int i = 0; i < m.dp_layers; ++i) {
+    ConvGemm g = make_gemm(m.dp_conv[i], sp, cur, H);
+    g.e.act = ACT_RELU; g.e.out = a; g.e.ldo = H;
+    RUN(conv_gemm(c, g));
+    RUN(layernorm_rows(c, sp, a, H, b, H, H, m.dp_ln_g[i], m.dp_ln_b[i], 1e-5f, srcmask));
+    cur = b;  // next conv reads b and writes a; the LN after it overwrites b only once that conv has finished
+  }
+  {
+    ConvGemm g = make_gemm(m.dp_lin, sp, cur, H);
+    g.e.rowmask = srcmask; g.e.out = logdur; g.e.ldo = 1;
+    RUN(conv_gemm(c, g));
+  }
+  RUN(dur_from_logits(c, sp, logdur, srcmask, dur));
+  c.release(mk);
+  return 0;
+}
+
+// a10-a12: get_style (stylesinger.py:189-214)
+int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const float* dec0, const float* ref_g /*[rows,80]*/,
+              const float* reff0_g /*[rows]*/, float* style /*[rows_f,256]*/, int32_t* codes /*[rows_r,depth] guarded*/,
+              float* rq_in_out /*optional guarded [rows_r,256]*/) {
+  const int H = 256;
+  const size_t mk = c.mark();
+  float* rmask = alloc_rows(c, sr, 1);
+  float* x = alloc_rows(c, sr, 80);
+  float* z = alloc_rows(c, sr, 80);
+  float* wout = alloc_rows(c, sr, 80);
+  float* h80 = alloc_rows(c, sr, 80);
+  float* g160 = alloc_rows(c, sr, 160);
+  float* np0 = alloc_rows(c, sr, 1);
+  float* npi = alloc_rows(c, sr, 1);
+  float* st = alloc_rows(c, sr, H);
+  float* zq = alloc_rows(c, sr, H);
+  float* cat = alloc_rows(c, sr, 2 * H);
+  float* zl = alloc_rows(c, sr, H);
+  float* kmask = alloc_rows(c, sr, 1);
+  int32_t* pos = alloc_rows_i32(c, sr);
+  float* kv = alloc_rows(c, sr, 2 * H);
+  float* q = alloc_rows(c, sf, H);
+  float* att = alloc_rows(c, sf, H);
+  float* tmp = alloc_rows(c, sf, H);
+  float* hid = alloc_rows(c, sf, 2048);
+  WS_OK(c);
+  // LocalStyleAdaptor.forward (lse.py:103-129)
+  RUN(col0_nonzero_mask(c, sr, ref_g, 80, rmask));
+  if (!c.dry) SSB_CUDA(cudaMemcpyAsync(x, ref_g, (size_t)sr.rows * 80 * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  for (int i = 0; i < 4; ++i) {  // WN.forward (wavenet.py:54-78), g=None
+    {
+      ConvGemm g = make_gemm(m.wn_in[i], sr, x, 80);
+      g.e.mode = EPI_GATE; g.e.out = z; g.e.ldo = 80;
+      RUN(conv_gemm(c, g));
+    }
+    ConvGemm g = make_gemm(m.wn_rs[i], sr, z, 80);
+    if (i < 3) {
+      g.e.mode = EPI_RES_SKIP; g.e.C = 80; g.e.res = x; g.e.ld_res = 80; g.e.beta = 1.0f; g.e.rowmask = rmask;
+      g.e.out = x; g.e.ldo = 80; g.e.skip = wout; g.e.ld_skip = 80; g.e.skip_init = (i == 0);
+    } else {
+      g.e.out = wout; g.e.ldo = 80; g.e.accum = 1; g.e.gamma = 1.0f;
+    }
+    RUN(conv_gemm(c, g));
+  }
+  // ref_ph = wn_out * mask + ref_f0 broadcast (lse.py:110,121-123)
+  RUN(scale_mask_add_rowscalar(c, sr, wout, 80, 80, rmask, reff0_g, x, 80));
+  // ConvBlocks (lse.py:229-240)
+  RUN(row_nonzero_mask(c, sr, x, 80, 80, np0));
+  for (int i = 0; i < 5; ++i) {
+    RUN(row_nonzero_mask(c, sr, x, 80, 80, npi));
+    for (int j = 0; j < 2; ++j) {
+      const Model::CB& b = m.cb[i * 2 + j];
+      RUN(layernorm_rows(c, sr, x, 80, h80, 80, 80, b.ln_g, b.ln_b, 1e-5f, nullptr));
+      {
+        ConvGemm g = make_gemm(b.c1, sr, h80, 80);
+        g.e.alpha = 1.0f / sqrtf(5.0f); g.e.act = ACT_GELU; g.e.out = g160; g.e.ldo = 160;
+        RUN(conv_gemm(c, g));
+      }
+      {
+        ConvGemm g = make_gemm(b.c2, sr, g160, 160);
+        g.e.res = x; g.e.ld_res = 80; g.e.rowmask = npi; g.e.out = x; g.e.ldo = 80;
+        RUN(conv_gemm(c, g));
+      }
+    }
+  }
+  {
+    CombineArgs a;
+    a.m[0] = x; a.ldm[0] = 80; a.rowmask = np0; a.out = x; a.ldo = 80; a.C = 80;
+    RUN(combine_rows(c, sr, a));
+  }
+  RUN(layernorm_rows(c, sr, x, 80, h80, 80, 80, m.cb_last_g, m.cb_last_b, 1e-5f, np0));
+  {
+    ConvGemm g = make_gemm(m.cb_post, sr, h80, 80);
+    g.e.rowmask = np0; g.e.out = st; g.e.ldo = H;
+    RUN(conv_gemm(c, g));
+  }
+  if (rq_in_out && !c.dry)
+    SSB_CUDA(cudaMemcpyAsync(rq_in_out, st, (size_t)sr.rows * H * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  RUN(rvq_lookup(c, sr, st, H, m.codebooks, m.cb_norm2, m.hp.n_rq, m.hp.rq_depth, zq, H, codes));
+  // positions + l1 (stylesinger.py:198-200)
+  RUN(col0_nonzero_mask(c, sr, zq, H, kmask));
+  RUN(positions_from_mask(c, sr, kmask, pos));
+  RUN(concat2_pos(c, sr, zq, H, pos, m.pos_table, m.pos_rows, cat, 2 * H));
+  {
+    ConvGemm g = make_gemm(m.l1, sr, cat, 2 * H);
+    g.e.out = zl; g.e.ldo = H;
+    RUN(conv_gemm(c, g));
+  }
+  RUN(col0_nonzero_mask(c, sr, zl, H, kmask));  // style_key_padding_mask = zl[:,:,0].eq(0) (:204) -> attend where != 0
+  // ProsodyAligner (lse.py:59-81), forcing=False
+  if (!c.dry) SSB_CUDA(cudaMemcpyAsync(style, dec0, (size_t)sf.rows * H * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  for (int i = 0; i < 2; ++i) {
+    const AlignLayer& L = m.align[i];
+    {
+      ConvGemm g = make_gemm(L.q, sf, style, H);
+      g.e.out = q; g.e.ldo = H;
+      RUN(conv_gemm(c, g));
+    }
+    {
+      ConvGemm g = make_gemm(L.kv, sr, zl, H);
+      g.e.out = kv; g.e.ldo = 2 * H;
+      RUN(conv_gemm(c, g));
+    }
+    {
+      AttnArgs a;
+      a.utt_q = sf.utt; a.utt_k = sr.utt; a.B = sf.B; a.max_q = sf.maxlen; a.heads = 2;
+      a.Q = q; a.ldq = H; a.K = kv; a.ldk = 2 * H; a.V = kv + H; a.ldv = 2 * H;
+      a.keymask = kmask; a.scale = 0.08838834764831845f; a.out = att; a.ldo = H;
+      RUN(attention(c, a));
+    }
+    {
+      ConvGemm g = make_gemm(L.out, sf, att, H);
+      g.e.res = style; g.e.ld_res = H; g.e.out = tmp; g.e.ldo = H;
+      RUN(conv_gemm(c, g));
+    }
+    RUN(layernorm_rows(c, sf, tmp, H, style, H, H, L.n1_g, L.n1_b, 1e-5f, nullptr));
+    {
+      ConvGemm g = make_gemm(L.lin1, sf, style, H);
+      g.e.act = ACT_RELU; g.e.out = hid; g.e.ldo = 2048;
+      RUN(conv_gemm(c, g));
+    }
+    {
+      ConvGemm g = make_gemm(L.lin2, sf, hid, 2048);
+      g.e.res = style; g.e.ld_res = H; g.e.out = tmp; g.e.ldo = H;
+      RUN(conv_gemm(c, g));
+    }
+    RUN(layernorm_rows(c, sf, tmp, H, style, H, H, L.n2_g, L.n2_b, 1e-5f, nullptr));
+  }
+  c.release(mk);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a13/a18: the denoiser residual stack for one diffusion step.
+// x [rows,C] (residual stream, overwritten), y = x + d[t][0] [rows,C] (overwritten), condall [rows, L*2C]
+// -> head [rows, out_dims(pad 4)]
+int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, float* x, float* y, const float* condall,
+                   float* zg, float* skip, float* sbuf, float* head, int ld_head) {
+  const int C = d.C, L = d.L;
+  SSB_CHECK(d.dtab != nullptr && t >= 0 && t < d.T, "denoiser: schedule not set (ssb_model_set_schedule) or bad t");
+  const float* dt = d.dtab + (size_t)t * L * C;
+  for (int l = 0; l < L; ++l) {
+    {
+      ConvGemm g = make_gemm(d.layers[l].dil, s, y, C);
+      g.e.mode = EPI_GATE; g.e.add = condall + (size_t)l * 2 * C; g.e.ld_add = L * 2 * C; g.e.out = zg; g.e.ldo = C;
+      RUN(conv_gemm(c, g));
+    }
+    {
+      ConvGemm g = make_gemm(d.layers[l].outp, s, zg, C);
+      g.e.mode = EPI_RES_SKIP; g.e.C = C; g.e.res = x; g.e.ld_res = C; g.e.beta = 0.70710678118654752440f;
+      g.e.out = x; g.e.ldo = C;
+      if (l + 1 < L) { g.e.out2 = y; g.e.ldo2 = C; g.e.vec2 = dt + (size_t)(l + 1) * C; }
+      g.e.skip = skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
+      RUN(conv_gemm(c, g));
+    }
+  }
+  {
+    ConvGemm g = make_gemm(d.skip_proj, s, skip, C);
+    g.a_scale = 1.0f / sqrtf((float)L);
+    g.e.act = ACT_RELU; g.e.out = sbuf; g.e.ldo = C;
+    RUN(conv_gemm(c, g));
+  }
+  {
+    ConvGemm g = make_gemm(d.out_proj, s, sbuf, C);
+    g.e.out = head; g.e.ldo = ld_head;
+    RUN(conv_gemm(c, g));
+  }
+  return 0;
+}
+
+struct DenoiserBufs {
+  float *x, *y, *zg, *skip, *sbuf, *head, *condall;
+  int ld_head;
+};
+static int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, DenoiserBufs* b) {
+  b->x = alloc_rows(c, s, d.C);
+  b->y = alloc_rows(c, s, d.C);
+  b->zg = alloc_rows(c, s, d.C);
+  b->skip = alloc_rows(c, s, d.C);
+  b->sbuf = alloc_rows(c, s, d.C);
+  b->ld_head = (d.out_dims + 3) & ~3;
+  b->head = alloc_rows(c, s, b->ld_head);
+  b->condall = alloc_rows(c, s, d.L * 2 * d.C, false);
+  WS_OK(c);
+  return 0;
+}
+static int hoist_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, float* condall) {
+  ConvGemm g = make_gemm(d.cond_all, s, cond_g, 256);
+  g.e.out = condall; g.e.ldo = d.L * 2 * d.C;
+  return conv_gemm(c, g);
+}
+
+// a18 entry for one evaluation (mel): x80 [rows,80] guarded -> head
+static int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const float* x80, DenoiserBufs& b) {
+  ConvGemm g = make_gemm(d.in_proj, s, x80, 80);
+  g.e.act = ACT_RELU; g.e.out = b.x; g.e.ldo = d.C; g.e.out2 = b.y; g.e.ldo2 = d.C;
+  g.e.vec2 = d.dtab + (size_t)t * d.L * d.C;
+  RUN(conv_gemm(c, g));
+  return denoiser_stack(c, d, s, t, b.x, b.y, b.condall, b.zg, b.skip, b.sbuf, b.head, b.ld_head);
+}
+
+// a18+a19: DiffusionDecoder.forward(infer=True) (shallow_diffusion_tts.py:284-307)
+int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
+                      const float* noise /*tight [(T+1), total, 80] or null*/, uint64_t seed, float* mel_tight) {
+  const Denoiser& d = m.melnet;
+  SSB_CHECK(d.T > 0, "mel schedule not set: call ssb_model_set_schedule(which=0)");
+  const size_t mk = c.mark();
+  DenoiserBufs b;
+  RUN(alloc_denoiser(c, d, s, &b));
+  float* xm = alloc_rows(c, s, 80);
+  WS_OK(c);
+  RUN(hoist_cond(c, d, s, cond_g, b.condall));
+  const int T = d.T;
+  const size_t per = (size_t)s.total * 80;
+  const float sa = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 5], s1a = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 6];
+  RUN(mel_q_sample(c, s, coarse_g, 80, noise, m.spec_min, m.spec_max, sa, s1a, xm, 80, seed, 1000));
+  for (int t = T - 1; t >= 0; --t) {
+    RUN(mel_denoiser_eval(c, d, s, t, xm, b));
+    const float* nz = noise ? noise + per * (size_t)(T - t) : nullptr;
+    RUN(mel_p_sample(c, s, xm, 80, b.head, b.ld_head, nz, d.gtab + (size_t)t * 8, seed, 1001 + (uint64_t)t));
+  }
+  RUN(mel_denorm(c, s, xm, 80, m.spec_min, m.spec_max, nullptr, mel_tight, 80));
+  c.release(mk);
+  return 0;
+}
+
+// a13+a14: GaussianMultinomialDiffusion.sample (gaussian_multinomial_diffusion.py:921-942)
+int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const float* cond_g, const float* lo,
+                     const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv) {
+  const Denoiser& d = m.f0net[which];
+  SSB_CHECK(d.T > 0, "f0 schedule not set: call ssb_model_set_schedule(which=1)");
+  const size_t mk = c.mark();
+  DenoiserBufs b;
+  RUN(alloc_denoiser(c, d, s, &b));
+  RUN(hoist_cond(c, d, s, cond_g, b.condall));
+  const int T = d.T;
+  const size_t per = (size_t)s.total;
+  const uint64_t sbase = 2000 + (uint64_t)which * 100000;
+  RUN(f0_init(c, s, z, uv, gnoise, seed, sbase));
+  for (int t = T - 1; t >= 0; --t) {
+    const float* dt = d.dtab + (size_t)t * d.L * d.C;
+    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.x, b.y, d.C));
+    RUN(denoiser_stack(c, d, s, t, b.x, b.y, b.condall, b.zg, b.skip, b.sbuf, b.head, b.ld_head));
+    F0StepArgs a;
+    a.z = z; a.uv = uv; a.out3 = b.head; a.ld3 = b.ld_head; a.lo = lo; a.hi = hi;
+    a.gnoise = gnoise ? gnoise + per * (size_t)(T - t) : nullptr;
+    a.unoise = unoise ? unoise + per * 2 * (size_t)(T - 1 - t) : nullptr;
+    a.gtab = d.gtab + (size_t)t * 8; a.mtab = d.mtab + (size_t)t * 8; a.t = t; a.log_eps = m.log_eps;
+    a.seed = seed; a.stream_id = sbase + 10 + 2 * (uint64_t)t;
+    RUN(f0_p_sample(c, s, a));
+  }
+  c.release(mk);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a20/a21: HifiGanGenerator.forward (hifigan_nsf.py:144-169)
+int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight, const float* f0_tight,
+                const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_tight) {
+  const size_t mk0 = c.mark();
+  int hop = 1;
+  for (auto& st : v.stages) hop *= st.u;
+  SeqDev s1, s256;
+  RUN(upload_layout(c, seq, 1, &s1));
+  RUN(upload_layout(c, seq, hop, &s256));
+  float* mel = alloc_rows(c, s1, 80);
+  float* f0g = alloc_rows(c, s1, 1);
+  float* har = nullptr;
+  WS_OK(c);
+  RUN(pack_rows(c, s1, mel_tight, 80, mel, 80, 80));
+  const bool nsf = v.nsf && f0_tight != nullptr;
+  if (nsf) {
+    RUN(pack_rows(c, s1, f0_tight, 1, f0g, 1, 1));
+    har = alloc_rows(c, s256, 1);
+    const size_t mk = c.mark();
+    double* scratch = c.alloc<double>(nsf_scratch_doubles(s256));
+    WS_OK(c);
+    RUN(nsf_source(c, s1, s256, f0g, v.lin_w, v.lin_b, rand_ini, src_noise, har, scratch, seed, hop, (float)v.cfg.sample_rate));
+    c.release(mk);
+  }
+  int C = v.cfg.initial_channel;
+  float* x = alloc_rows(c, s1, C);
+  WS_OK(c);
+  {
+    ConvGemm g = make_gemm(v.pre, s1, mel, 80);
+    g.e.out = x; g.e.ldo = C;
+    RUN(conv_gemm(c, g));
+  }
+  int rate = 1;
+  SeqDev sin = s1;
+  float* xin = x;
+  for (size_t i = 0; i < v.stages.size(); ++i) {
+    const VocStage& st = v.stages[i];
+    const int Co = st.Cout;
+    const int rate_out = rate * st.u;
+    SeqDev so;
+    RUN(upload_layout(c, seq, rate_out, &so));
+    float* xu = alloc_rows(c, so, Co);
+    float* xt = alloc_rows(c, so, Co);
+    float* r = alloc_rows(c, so, Co);
+    float* acc = alloc_rows(c, so, Co);
+    WS_OK(c);
+    {  // x = ups[i](leaky_relu(x, 0.1))
+      ConvGemm g = make_gemm(st.up, sin, xin, C);
+      g.a_act = ACT_LRELU; g.a_slope = 0.1f;
+      g.e.out = xu; g.e.ldo = st.u * Co;
+      RUN(conv_gemm(c, g));
+    }
+    if (nsf) RUN(noise_conv_add(c, so, s256, xu, Co, Co, har, st.nc_w, st.nc_b, st.nc_s));
+    for (int j = 0; j < v.nk; ++j) {  // MRF: mean of the resblocks
+      const float* rin = xu;
+      for (int mI = 0; mI < 3; ++mI) {
+        {
+          ConvGemm g = make_gemm(st.rb[j].c1[mI], so, rin, Co);
+          g.a_act = ACT_LRELU; g.a_slope = 0.1f;
+          g.e.out = xt; g.e.ldo = Co;
+          RUN(conv_gemm(c, g));
+        }
+        ConvGemm g = make_gemm(st.rb[j].c2[mI], so, xt, Co);
+        g.a_act = ACT_LRELU; g.a_slope = 0.1f;
+        g.e.res = rin; g.e.ld_res = Co;
+        if (mI < 2) {
+          g.e.out = r; g.e.ldo = Co;
+        } else {
+          g.e.out = acc; g.e.ldo = Co;
+          g.e.accum = (j > 0);
+          g.e.gamma = (j == v.nk - 1) ? 1.0f / (float)v.nk : 1.0f;
+          if (j == 0 && v.nk == 1) g.e.gamma = 1.0f;
+        }
+        RUN(conv_gemm(c, g));
+        rin = r;
+      }
+    }
+    // NOTE: for nk == 1 the mean is the identity; for nk > 1 the last accumulation applies 1/nk.
+    xin = acc; sin = so; C = Co; rate = rate_out;
+    // buffers of the previous stage stay allocated until the end (bump allocator); sizes are bounded by
+    // 4 * rows * C which is constant from stage 1 on.
+  }
+  {
+    float* y = alloc_rows(c, sin, 4);
+    WS_OK(c);
+    ConvGemm g = make_gemm(v.post, sin, xin, C);
+    g.a_act = ACT_LRELU; g.a_slope = 0.01f;  // F.leaky_relu default slope (hifigan_nsf.py:165)
+    g.e.out = y; g.e.ldo = 4;
+    RUN(conv_gemm(c, g));
+    RUN(tanh_out(c, sin, y, 4, wav_tight));
+  }
+  c.release(mk0);
+  return 0;
+}
+
+}  // namespace ssb

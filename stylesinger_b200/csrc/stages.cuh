@@ -1,0 +1,26 @@
+#pragma once
+#include "model.cuh"
+
+namespace ssb {
+
+int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* keep);
+int run_encoder(Ctx& c, const Model& m, const SeqDev& sp, const int32_t* tok_g, const int32_t* note_g,
+                const int32_t* type_g, const float* ndur_g, float* srcmask, float* enc_out);
+int run_duration_predictor(Ctx& c, const Model& m, const SeqDev& sp, const float* dur_inp, const float* srcmask,
+                           float* logdur, int32_t* dur);
+int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const float* dec0, const float* ref_g,
+              const float* reff0_g, float* style, int32_t* codes, float* rq_in_out);
+int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, float* x, float* y, const float* condall,
+                   float* zg, float* skip, float* sbuf, float* head, int ld_head);
+int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
+                      const float* noise, uint64_t seed, float* mel_tight);
+int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const float* cond_g, const float* lo,
+                     const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv);
+int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight, const float* f0_tight,
+                const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_tight);
+int denoiser_eval_api(Ctx& c, const Model& m, int which, const SeqDev& s, const float* x_tight, const int32_t* uv_tight,
+                      int t, const float* cond_tight, float* out_tight);
+int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ssb_acoustic_outputs& out, bool durations_only,
+                 int32_t* dur_out, float* logdur_out);
+
+}  // namespace ssb

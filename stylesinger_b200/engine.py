@@ -1,0 +1,384 @@
+"""Host-side engine: checkpoint packing, ragged batches, workspaces and the calls into the C ABI.
+
+PyTorch is used here only for device memory, streams and host<->device copies; every arithmetic
+operation of the path runs in libstylesinger_b200.so (see include/stylesinger_b200.h).
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AcousticInputs, AcousticOutputs, HParams, TensorDesc, VocoderConfig, check, lib
+from .hparams import DEFAULT_VOCODER_CONFIG, resolve
+from .schedules import multinomial_table, sampler_table
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.SsbError("stylesinger_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _descs(named: Dict[str, torch.Tensor]):
+    """ssb_tensor_desc array over fp32 contiguous CPU copies (kept alive by the returned list)."""
+    keep, arr = [], (TensorDesc * len(named))()
+    for i, (k, v) in enumerate(named.items()):
+        t = v.detach().to("cpu", torch.float32).contiguous()
+        if t.dim() == 0:
+            t = t.reshape(1)
+        if t.dim() > 4:
+            raise ValueError(f"{k}: rank > 4")
+        keep.append(t)
+        kb = k.encode()
+        keep.append(kb)
+        arr[i].name = kb
+        arr[i].data = t.data_ptr()
+        arr[i].ndim = t.dim()
+        for d in range(t.dim()):
+            arr[i].shape[d] = t.shape[d]
+    return arr, keep
+
+
+def sinusoid_table(n, dim=256, padding_idx=0):
+    """SinusoidalPositionalEmbedding.get_embedding (reference modules/commons/common_layers.py:111-127),
+    computed on the host exactly like the reference does at module construction."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+    e = torch.arange(n, dtype=torch.float).unsqueeze(1) * e.unsqueeze(0)
+    e = torch.cat([torch.sin(e), torch.cos(e)], dim=1).view(n, -1)
+    e[padding_idx, :] = 0
+    return e
+
+
+def step_embedding(T, C_):
+    """SinusoidalPosEmb(t) for t = 0..T-1 (reference modules/diff/net.py:31-44)."""
+    half = C_ // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half) * -e)
+    e = torch.arange(T)[:, None] * e[None, :]
+    return torch.cat((e.sin(), e.cos()), dim=-1).float().contiguous()
+
+
+@dataclass
+class PackedBatch:
+    """A ragged batch in the library's tight layout. Offsets are host int32 arrays [B+1]."""
+    B: int
+    ph_offsets: np.ndarray
+    ref_offsets: np.ndarray
+    frame_offsets: Optional[np.ndarray]
+    t: Dict[str, torch.Tensor] = field(default_factory=dict)  # txt_tokens, note, note_type (int32), note_dur,
+    # spk_embed, emo_embed, ref_mels, ref_f0, [mel2ph int32], [f0], [uv]
+
+    def to(self, device, non_blocking=True):
+        return PackedBatch(self.B, self.ph_offsets, self.ref_offsets, self.frame_offsets,
+                           {k: v.to(device, non_blocking=non_blocking) for k, v in self.t.items()})
+
+    def h2d_bytes(self):
+        return int(sum(v.numel() * v.element_size() for v in self.t.values()))
+
+    @property
+    def total_frames(self):
+        return int(self.frame_offsets[-1]) if self.frame_offsets is not None else 0
+
+
+def pack_batch(utts: List[dict], use_mel2ph=True, pin=False) -> PackedBatch:
+    """Concatenate per-utterance CPU tensors (as produced by synth.make_utterance) into one PackedBatch."""
+    def offs(lens):
+        return np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+
+    B = len(utts)
+    po = offs([len(u["txt_tokens"]) for u in utts])
+    ro = offs([u["ref_mels"].shape[0] for u in utts])
+    fo = offs([len(u["mel2ph"]) for u in utts]) if use_mel2ph else None
+    cat = lambda k, dt: torch.cat([u[k].reshape(-1) if u[k].dim() == 1 else u[k] for u in utts]).to(dt).contiguous()
+    t = {"txt_tokens": cat("txt_tokens", torch.int32), "note": cat("note", torch.int32),
+         "note_type": cat("note_type", torch.int32), "note_dur": cat("note_dur", torch.float32),
+         "spk_embed": torch.stack([u["spk_embed"] for u in utts]).float().contiguous(),
+         "emo_embed": torch.stack([u["emo_embed"] for u in utts]).float().contiguous(),
+         "ref_mels": cat("ref_mels", torch.float32), "ref_f0": cat("ref_f0", torch.float32)}
+    if use_mel2ph:
+        t["mel2ph"] = cat("mel2ph", torch.int32)
+    if pin and torch.cuda.is_available():
+        t = {k: v.pin_memory() for k, v in t.items()}
+    return PackedBatch(B, po, ro, fo, t)
+
+
+class _Workspace:
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+class AcousticModel:
+    """Packed StyleSinger acoustic model on one GPU (ssb_model_t)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], hparams=None, device=None, max_positions=4096):
+        _require_cuda()
+        self.hp = resolve(hparams)
+        self.device = torch.device(device if device is not None else "cuda:0")
+        torch.cuda.set_device(self.device)
+        sd = {k: v for k, v in state_dict.items() if isinstance(v, torch.Tensor)}
+        sd = dict(sd)
+        sd["__pos_table"] = sinusoid_table(max_positions, self.hp["hidden_size"])
+        if "encoder.embed_tokens.weight" not in sd and "encoder_embed_tokens.weight" in sd:
+            sd["encoder.embed_tokens.weight"] = sd["encoder_embed_tokens.weight"]
+        hp = self.hp
+        h = HParams(hp["hidden_size"], hp["enc_layers"], hp["dec_layers"], hp["enc_ffn_kernel_size"],
+                    hp["dec_ffn_kernel_size"], hp["dur_predictor_layers"], hp["dur_predictor_kernel"],
+                    int(sd["encoder.embed_tokens.weight"].shape[0]), hp["nRQ"], hp["rq_depth"],
+                    hp["residual_channels"], hp["residual_layers"], hp["dilation_cycle_length"],
+                    hp["f0_residual_channels"], hp["f0_residual_layers"], hp["f0_dilation_cycle_length"],
+                    hp["audio_num_mel_bins"])
+        arr, keep = _descs(sd)
+        handle = C.c_void_p()
+        check(lib.ssb_model_create(C.byref(handle), arr, len(sd), C.byref(h)), "ssb_model_create")
+        self._h = handle
+        self._ws = _Workspace(self.device)
+        self.T = self.f0_T = None
+        self.set_timesteps(hp["timesteps"], hp["f0_timesteps"])
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.ssb_model_free(h)
+            self._h = None
+
+    # -- schedules -------------------------------------------------------------------------------
+    def set_timesteps(self, T=None, f0_T=None):
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if T is not None and T != self.T:
+            emb = step_embedding(T, self.hp["residual_channels"])
+            g = np.ascontiguousarray(sampler_table(T, self.hp["max_beta"]))
+            check(lib.ssb_model_set_schedule(self._h, 0, T, C.c_void_p(emb.data_ptr()), g.ctypes.data_as(C.c_void_p),
+                                             None, stream), "ssb_model_set_schedule(mel)")
+            self.T = T
+        if f0_T is not None and f0_T != self.f0_T:
+            emb = step_embedding(f0_T, self.hp["f0_residual_channels"])
+            g = np.ascontiguousarray(sampler_table(f0_T, self.hp["f0_max_beta"]))
+            m = np.ascontiguousarray(multinomial_table(f0_T, self.hp["f0_max_beta"]))
+            check(lib.ssb_model_set_schedule(self._h, 1, f0_T, C.c_void_p(emb.data_ptr()),
+                                             g.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), stream),
+                  "ssb_model_set_schedule(f0)")
+            self.f0_T = f0_T
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _inputs(self, pb: PackedBatch, noise=None, seed=0, skip_mel=False, dur=None, f0=None, uv=None):
+        a = AcousticInputs()
+        a.B = pb.B
+        self._keep = [np.ascontiguousarray(pb.ph_offsets, np.int32), np.ascontiguousarray(pb.ref_offsets, np.int32)]
+        a.ph_offsets = self._keep[0].ctypes.data
+        a.ref_offsets = self._keep[1].ctypes.data
+        if pb.frame_offsets is not None:
+            fo = np.ascontiguousarray(pb.frame_offsets, np.int32)
+            self._keep.append(fo)
+            a.frame_offsets = fo.ctypes.data
+        t = pb.t
+        for k in ("txt_tokens", "note", "note_type", "note_dur", "spk_embed", "emo_embed", "ref_mels", "ref_f0"):
+            assert t[k].is_cuda and t[k].is_contiguous(), k
+            setattr(a, k, t[k].data_ptr())
+        if "mel2ph" in t and dur is None:
+            a.mel2ph = t["mel2ph"].data_ptr()
+        if dur is not None:
+            a.dur = dur.data_ptr()
+        f0 = f0 if f0 is not None else t.get("f0")
+        uv = uv if uv is not None else t.get("uv")
+        if f0 is not None:
+            a.f0 = f0.data_ptr()
+            if uv is not None:
+                a.uv = uv.data_ptr()
+        if noise:
+            for i in range(2):
+                if noise.get("f0_gauss") is not None:
+                    a.f0_gauss_noise[i] = noise["f0_gauss"][i].data_ptr()
+                    a.f0_unif_noise[i] = noise["f0_unif"][i].data_ptr()
+            if noise.get("mel") is not None:
+                a.mel_noise = noise["mel"].data_ptr()
+        a.seed = int(seed)
+        a.skip_mel_diffusion = 1 if skip_mel else 0
+        return a
+
+    # -- entry points ------------------------------------------------------------------------------
+    def predict_durations(self, pb: PackedBatch):
+        """DurationPredictor.inference; returns (dur int32 [sumP], log-dur f32 [sumP]) on the device."""
+        a = self._inputs(pb)
+        n = lib.ssb_durations_workspace_bytes(self._h, C.byref(a))
+        if n == 0:
+            check(-1, "ssb_durations_workspace_bytes")
+        ws = self._ws.get(n)
+        P = int(pb.ph_offsets[-1])
+        dur = torch.empty(P, dtype=torch.int32, device=self.device)
+        logdur = torch.empty(P, dtype=torch.float32, device=self.device)
+        check(lib.ssb_predict_durations(self._h, C.byref(a), _ptr(dur), _ptr(logdur), _ptr(ws), ws.numel(), self._stream()),
+              "ssb_predict_durations")
+        return dur, logdur
+
+    def forward(self, pb: PackedBatch, noise=None, seed=0, skip_mel_diffusion=False, dur=None,
+                want=("mel_out", "f0_denorm")):
+        """StyleSinger.forward(infer=True). `pb` must carry frame_offsets (+ mel2ph, or pass `dur`).
+        Returns a dict of tight device tensors for the keys in `want`."""
+        assert pb.frame_offsets is not None, "frame_offsets required (run predict_durations first)"
+        a = self._inputs(pb, noise, seed, skip_mel_diffusion, dur)
+        Fs, Ps, Rs = int(pb.frame_offsets[-1]), int(pb.ph_offsets[-1]), int(pb.ref_offsets[-1])
+        shapes = {"mel_out": (Fs, 80), "f0_denorm": (Fs,), "encoder_out": (Ps, 256), "style": (Fs, 256),
+                  "rq_codes": (Rs, self.hp["rq_depth"]), "pitch_pred": (Fs, 2), "decoder_inp": (Fs, 256),
+                  "coarse_mel": (Fs, 80), "diff_cond": (Fs, 256), "mel2ph": (Fs,), "spk_proj": (pb.B, 256),
+                  "emo_proj": (pb.B, 256)}
+        o = AcousticOutputs()
+        out = {}
+        want = set(want)
+        if not skip_mel_diffusion:
+            want.add("mel_out")
+        for k in want:
+            dt = torch.int32 if k in ("rq_codes", "mel2ph") else torch.float32
+            out[k] = torch.empty(shapes[k], dtype=dt, device=self.device)
+            setattr(o, k, out[k].data_ptr())
+        n = lib.ssb_acoustic_workspace_bytes(self._h, C.byref(a))
+        if n == 0:
+            check(-1, "ssb_acoustic_workspace_bytes")
+        ws = self._ws.get(n)
+        check(lib.ssb_acoustic_forward(self._h, C.byref(a), C.byref(o), _ptr(ws), ws.numel(), self._stream()),
+              "ssb_acoustic_forward")
+        return out
+
+    def mel_diffusion(self, cond, coarse, frame_offsets, noise=None, seed=0):
+        fo = np.ascontiguousarray(frame_offsets, np.int32)
+        B = len(fo) - 1
+        n = lib.ssb_mel_diffusion_workspace_bytes(self._h, fo.ctypes.data, B)
+        if n == 0:
+            check(-1, "ssb_mel_diffusion_workspace_bytes")
+        ws = self._ws.get(n)
+        mel = torch.empty((int(fo[-1]), 80), dtype=torch.float32, device=self.device)
+        check(lib.ssb_mel_diffusion_sample(self._h, _ptr(cond), _ptr(coarse), fo.ctypes.data, B, _ptr(noise), int(seed),
+                                           _ptr(mel), _ptr(ws), ws.numel(), self._stream()), "ssb_mel_diffusion_sample")
+        return mel
+
+    def denoiser_eval(self, which, x, uv, t, cond, frame_offsets):
+        fo = np.ascontiguousarray(frame_offsets, np.int32)
+        B, Fs = len(fo) - 1, int(fo[-1])
+        C_ = self.hp["residual_channels"] if which == 0 else self.hp["f0_residual_channels"]
+        L_ = self.hp["residual_layers"] if which == 0 else self.hp["f0_residual_layers"]
+        rows = Fs + 16 * (B + 1) + 512
+        ws = self._ws.get(rows * (6 * C_ + 2 * C_ * L_ + 512) * 4 + (1 << 20))
+        out = torch.empty((Fs, 80 if which == 0 else 3), dtype=torch.float32, device=self.device)
+        check(lib.ssb_denoiser_eval(self._h, which, _ptr(x), _ptr(uv), int(t), _ptr(cond), fo.ctypes.data, B, _ptr(out),
+                                    _ptr(ws), ws.numel(), self._stream()), "ssb_denoiser_eval")
+        return out
+
+    def f0_diffusion(self, which, cond, lo, hi, frame_offsets, gauss_noise=None, unif_noise=None, seed=0):
+        fo = np.ascontiguousarray(frame_offsets, np.int32)
+        B, Fs = len(fo) - 1, int(fo[-1])
+        C_, L_ = self.hp["f0_residual_channels"], self.hp["f0_residual_layers"]
+        rows = Fs + 16 * (B + 1) + 512
+        ws = self._ws.get(rows * (6 * C_ + 2 * C_ * L_ + 300) * 4 + (1 << 20))
+        z = torch.empty(Fs, dtype=torch.float32, device=self.device)
+        uv = torch.empty(Fs, dtype=torch.int32, device=self.device)
+        check(lib.ssb_f0_diffusion_sample(self._h, which, _ptr(cond), _ptr(lo), _ptr(hi), fo.ctypes.data, B,
+                                          _ptr(gauss_noise), _ptr(unif_noise), int(seed), _ptr(z), _ptr(uv), _ptr(ws),
+                                          ws.numel(), self._stream()), "ssb_f0_diffusion_sample")
+        return z, uv
+
+    def rvq(self, x, ref_offsets):
+        ro = np.ascontiguousarray(ref_offsets, np.int32)
+        B, Rs = len(ro) - 1, int(ro[-1])
+        D = self.hp["rq_depth"]
+        ws = self._ws.get((Rs + 16 * (B + 1) + 512) * (512 + D + 8) * 4 + (1 << 20))
+        q = torch.empty((Rs, 256), dtype=torch.float32, device=self.device)
+        codes = torch.empty((Rs, D), dtype=torch.int32, device=self.device)
+        check(lib.ssb_rvq_lookup(self._h, _ptr(x), ro.ctypes.data, B, _ptr(q), _ptr(codes), _ptr(ws), ws.numel(),
+                                 self._stream()), "ssb_rvq_lookup")
+        return q, codes
+
+
+class Vocoder:
+    """Packed HiFi-GAN(-NSF) generator on one GPU (ssb_vocoder_t)."""
+
+    def __init__(self, state_dict, config=None, device=None):
+        _require_cuda()
+        self.cfg = dict(DEFAULT_VOCODER_CONFIG, **(config or {}))
+        self.device = torch.device(device if device is not None else "cuda:0")
+        torch.cuda.set_device(self.device)
+        h = self.cfg
+        if str(h.get("resblock", "1")) != "1":
+            raise NotImplementedError("only ResBlock1 generators are supported")
+        vc = VocoderConfig()
+        vc.n_up = len(h["upsample_rates"])
+        for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
+            vc.up_rates[i], vc.up_kernels[i] = u, k
+        vc.initial_channel = h["upsample_initial_channel"]
+        vc.n_res = len(h["resblock_kernel_sizes"])
+        for j, (k, d) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
+            vc.res_kernels[j] = k
+            for m in range(3):
+                vc.res_dilations[j][m] = d[m]
+        vc.use_pitch_embed = 1 if h.get("use_pitch_embed") else 0
+        vc.sample_rate = h.get("audio_sample_rate", 48000)
+        self.hop = int(np.prod(h["upsample_rates"]))
+        sd = {k: v for k, v in state_dict.items() if isinstance(v, torch.Tensor)}
+        arr, keep = _descs(sd)
+        handle = C.c_void_p()
+        check(lib.ssb_vocoder_create(C.byref(handle), arr, len(sd), C.byref(vc)), "ssb_vocoder_create")
+        self._h = handle
+        self._ws = _Workspace(self.device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.ssb_vocoder_free(h)
+            self._h = None
+
+    def generate(self, mel, f0, frame_offsets, rand_ini=None, src_noise=None, seed=0):
+        """mel [sumF,80], f0 [sumF] or None (device, tight) -> wav [sumF*hop] (device)."""
+        fo = np.ascontiguousarray(frame_offsets, np.int32)
+        B = len(fo) - 1
+        n = lib.ssb_vocoder_workspace_bytes(self._h, fo.ctypes.data, B)
+        if n == 0:
+            check(-1, "ssb_vocoder_workspace_bytes")
+        ws = self._ws.get(n)
+        wav = torch.empty(int(fo[-1]) * self.hop, dtype=torch.float32, device=self.device)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib.ssb_hifigan_generate(self._h, _ptr(mel), _ptr(f0), fo.ctypes.data, B, _ptr(rand_ini), _ptr(src_noise),
+                                       int(seed), _ptr(wav), _ptr(ws), ws.numel(), stream), "ssb_hifigan_generate")
+        return wav
+
+
+# unit-test granularity ops -------------------------------------------------------------------------
+def op_conv1d(x, offsets, w, b, dilation=1, act=0):
+    _require_cuda()
+    off = np.ascontiguousarray(offsets, np.int32)
+    N, Cin, k = w.shape
+    wc = w.detach().cpu().float().contiguous()
+    bc = None if b is None else b.detach().cpu().float().contiguous()
+    out = torch.empty((x.shape[0], N), dtype=torch.float32, device=x.device)
+    stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    check(lib.ssb_op_conv1d(_ptr(x), off.ctypes.data, len(off) - 1, Cin, C.c_void_p(wc.data_ptr()),
+                            None if bc is None else C.c_void_p(bc.data_ptr()), N, k, dilation, act, _ptr(out), stream),
+          "ssb_op_conv1d")
+    return out
+
+
+def op_attention(q, k, v, q_offsets, k_offsets, scale):
+    _require_cuda()
+    qo = np.ascontiguousarray(q_offsets, np.int32)
+    ko = np.ascontiguousarray(k_offsets, np.int32)
+    out = torch.empty_like(q)
+    stream = C.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+    check(lib.ssb_op_attention(_ptr(q), _ptr(k), _ptr(v), qo.ctypes.data, ko.ctypes.data, len(qo) - 1, float(scale),
+                               _ptr(out), stream), "ssb_op_attention")
+    return out
