@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — StyleSinger ph -> mel -> wav hot path on B200 (driver contract; see the task statement).
+
+    python bench.py --gpus 1 --steps K --warmup W [--workload utt10s|batch64] [--T 100]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU arm: the oracle port of the reference, host cores
+
+A "step" is one pass of the whole hot path (encoder, style adaptor + RVQ, two F0/UV diffusions, FFT
+decoder, T-step mel diffusion, HiFi-GAN-NSF) over one batch of seeded synthetic utterances
+ with synthetic (seed 0) checkpoints.  `value` = mel frames of all ranks / step time with
+the inputs resident in HBM; `e2e` = the same pass through StyleSingerInfer.infer_packed with pinned HOST
+inputs (H2D inside the timed region) and the waveform copied back to the host (D2H inside).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "mel_frames_per_sec_ph2wav_T100"
+UNIT = "frames/s"
+
+# FLOPs per frame-step of the mel denoiser as executed here (the step-invariant
+# conditioner projection is hoisted out of the T loop and costs 20*2*256*512 once per frame)
+MEL_STEP_FLOPS = 2 * 80 * 256 + 20 * (2 * 768 * 512 + 2 * 256 * 512) + 2 * 256 * 256 + 2 * 256 * 80
+MEL_HOIST_FLOPS = 20 * 2 * 256 * 512
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def lpt_assign(lengths, world):
+    """Longest-processing-time-first assignment of utterances to ranks."""
+    order = np.argsort(-np.asarray(lengths))
+    loads, bins = [0.0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = int(np.argmin(loads))
+        bins[r].append(int(i))
+        loads[r] += float(lengths[i])
+    return bins
+
+
+def make_workload(name, rank, world):
+    from stylesinger_b200 import synth
+    if name == "utt10s":
+        return [synth.make_utterance(10.0, utt_idx=rank)], "single 10 s utterance per GPU (BASELINE.json configs[1])"
+    n_per = {"batch64": 64, "batch8": 8}[name]
+    secs = synth.batch_seconds(n_per * world, seed=1234)
+    mine = lpt_assign(secs, world)[rank]
+    utts = [synth.make_utterance(float(secs[i]), utt_idx=i) for i in mine]
+    return utts, f"{n_per} variable-length (2-15 s) utterances per GPU, LPT-sharded (BASELINE.json configs[2]/[3])"
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_pass(seconds, T, threads):
+    """The reference's algorithm on the host cores: the oracle port (the reference is Python and does not
+    travel to the GPU box).  Returns (frames, elapsed_s)."""
+    from oracle import stylesinger_oracle as O
+    from stylesinger_b200 import synth
+    from stylesinger_b200.hparams import DEFAULT_VOCODER_CONFIG, resolve
+    torch.set_num_threads(threads)
+    hp = resolve(timesteps=T, K_step=T, f0_timesteps=T)
+    if not hasattr(cpu_reference_pass, "sd"):
+        cpu_reference_pass.sd = synth.acoustic_state_dict(hp, seed=0)
+        cpu_reference_pass.vsd = synth.vocoder_state_dict(DEFAULT_VOCODER_CONFIG, seed=0)
+    sd, vsd = cpu_reference_pass.sd, cpu_reference_pass.vsd
+    u = synth.make_utterance(seconds, utt_idx=0)
+    ns = O.NoiseSource(0)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        r = O.stylesinger_forward(sd, hp, u["txt_tokens"][None], u["note"][None], u["note_dur"][None],
+                                  u["note_type"][None], u["spk_embed"][None], u["emo_embed"][None], u["ref_mels"][None],
+                                  u["ref_f0"], ns, mel2ph=u["mel2ph"][None])
+        mel, f0 = O.postprocess_mel(r["mel_out"][0].numpy(), r["f0_denorm"][0].numpy(), hp)
+        O.spec2wav(mel, f0, vsd, DEFAULT_VOCODER_CONFIG, ns)
+    return int(u["mel2ph"].shape[0]), time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_s = args.cpu_sample_seconds
+    cpu_reference_pass(0.3, 2, threads)  # warm-up (thread pools, allocator)
+    for _ in range(max(args.warmup - 1, 0)):
+        pass  # further warm-up passes would only burn minutes of CPU; the pass above is enough
+    times, frames = [], 0
+    for _ in range(args.steps):
+        frames, dt = cpu_reference_pass(sample_s, args.T, threads)
+        times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    val = frames / (ms / 1000.0)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"CPU oracle port of the reference (reference is Python, cannot travel): one "
+                                   f"{sample_s:g} s utterance, T={args.T} (mel + 2 F0 loops) + HiFi-GAN-NSF, per step"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample_s:g} s utterance ({frames} frames), full ph->wav, T={args.T}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from stylesinger_b200 import synth
+    from stylesinger_b200._lib import lib
+    from stylesinger_b200.engine import pack_batch
+    from stylesinger_b200.hparams import DEFAULT_VOCODER_CONFIG, resolve
+    from stylesinger_b200.infer import StyleSingerInfer
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    T = args.T
+    hp = resolve(timesteps=T, K_step=T, f0_timesteps=T)
+    eng = StyleSingerInfer(hp, dev, synth.acoustic_state_dict(hp, seed=0),
+                           synth.vocoder_state_dict(DEFAULT_VOCODER_CONFIG, seed=0), DEFAULT_VOCODER_CONFIG)
+    utts, wl_desc = make_workload(args.workload, rank, world)
+    pb_host = pack_batch(utts, use_mel2ph=True, pin=True)
+    pb_dev = pb_host.to(dev)
+    frames = pb_host.total_frames
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s in range(steps):
+            flush.zero_()  # flush L2 between timed iterations (outside the event pair)
+            evs[s][0].record()
+            fn(s)
+            evs[s][1].record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up
+    for s in range(args.warmup):
+        eng.run_device(pb_dev, seed=s)
+    torch.cuda.synchronize(dev)
+
+    # ---- value: device-resident inputs
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = lib.ssb_launch_count()
+    ms = timed(lambda s: eng.run_device(pb_dev, seed=100 + s), args.steps)
+    launches = int(lib.ssb_launch_count() - l0)
+    clk = clocks.stop()
+
+    # ---- e2e: host buffers in, host waveform out
+    wav_bytes = frames * 256 * 4
+    ms_e2e = timed(lambda s: eng.infer_packed(pb_host, seed=200 + s), args.steps)
+
+    # ---- roofline of the dominant kernel (mel denoiser GEMMs), timed live on the stream
+    out = eng.model.forward(pb_dev, seed=1, skip_mel_diffusion=True, want=("coarse_mel", "diff_cond"))
+    cond, coarse = out["diff_cond"], out["coarse_mel"]
+    eng.model.mel_diffusion(cond, coarse, pb_dev.frame_offsets, seed=2)
+    l1 = lib.ssb_launch_count()
+    ms_mel = timed(lambda s: eng.model.mel_diffusion(cond, coarse, pb_dev.frame_offsets, seed=3 + s), max(1, min(args.steps, 3)))
+    n_mel = int(lib.ssb_launch_count() - l1) // max(1, min(args.steps, 3))
+    pk = peaks()
+    flops = frames * (T * MEL_STEP_FLOPS + MEL_HOIST_FLOPS)
+    achieved = flops / (ms_mel / 1000.0) / 1e12
+    gemm_launches = T * (2 * hp["residual_layers"] + 3) + 1
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"] + " (cuBLAS bf16, sustained)",
+            "kernel": "conv_gemm_kernel (mel denoiser stage: %d GEMM launches of %d total per sampler call)" % (gemm_launches, n_mel),
+            "avg_launch_us": 1000.0 * ms_mel / max(n_mel, 1), "stage_ms": ms_mel,
+            "note": "fp32 FFMA implicit-GEMM path; FLOPs as executed (conditioner projection hoisted out of the T loop)"}
+
+    tot = torch.tensor([float(frames)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_frames = float(tot.item())
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cpu_reference_pass(0.3, 2, threads)
+            f, dt = cpu_reference_pass(args.cpu_sample_seconds, T, threads)
+            cpu = {"value": f / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_sample_seconds:g} s utterance ({f} frames), full ph->wav, T={T}, 1 pass ({dt:.1f} s)"}
+        val = total_frames / (ms / 1000.0)
+        audio_s = total_frames * 256 / 48000.0
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "impl": "b200",
+                "config": {"workload": f"{args.workload}: {wl_desc}; T={T} mel + 2x{T} F0 steps; full ph->mel->wav",
+                           "frames_per_step": total_frames, "utterances_per_gpu": len(utts), "parallelism": f"dp{world} (utterance sharding, no data-path collective)",
+                           "l2": "256 MiB flush between timed iterations", "rtf": (ms / 1000.0) / audio_s},
+                "clocks": clk,
+                "e2e": {"value": total_frames / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": pb_host.h2d_bytes(),
+                        "d2h_bytes_per_step": int(wav_bytes), "ms_per_step": ms_e2e},
+                "gpu_launches": launches, "roofline": roof}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="utt10s", choices=["utt10s", "batch64", "batch8"])
+    ap.add_argument("--T", type=int, default=100)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=2.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

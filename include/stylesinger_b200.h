@@ -182,6 +182,14 @@ int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* 
                          int32_t B, const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* StyleSingerInfer.forward_model glue between model and vocoder (inference/StyleSinger.py:56-58):
+ * clips mel [n_frames,80] in place to [vmin, vmax] and counts the frames with sum|mel| > 0 into
+ * *nonzero_frames (device int32; the reference drops all-zero frames, which only padding can produce). */
+int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, int32_t* nonzero_frames, void* stream);
+
+/* Number of kernels this library has launched in this process so far (bench.py reports the delta). */
+int64_t ssb_launch_count(void);
+
 /* Unit-test granularity: one Conv1d over ragged rows with torch-layout HOST weights [N,Cin,k]
  * (packs on the fly with cudaMalloc; not for production use).  act: 0 none 1 relu 2 gelu 3 leaky(0.1) 4 tanh. */
 int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,

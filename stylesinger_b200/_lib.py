@@ -53,7 +53,7 @@ EXPORTS = [
     "ssb_durations_workspace_bytes", "ssb_predict_durations", "ssb_acoustic_workspace_bytes", "ssb_acoustic_forward",
     "ssb_mel_diffusion_workspace_bytes", "ssb_mel_diffusion_sample", "ssb_denoiser_eval", "ssb_f0_diffusion_sample",
     "ssb_rvq_lookup", "ssb_vocoder_create", "ssb_vocoder_free", "ssb_vocoder_workspace_bytes", "ssb_hifigan_generate",
-    "ssb_op_conv1d", "ssb_op_attention",
+    "ssb_op_conv1d", "ssb_op_attention", "ssb_mel_postprocess", "ssb_launch_count",
 ]
 
 
@@ -85,6 +85,8 @@ def _load():
         "ssb_hifigan_generate": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, u64, vp, vp, sz, vp]),
         "ssb_op_conv1d": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
         "ssb_op_attention": (C.c_int, [vp, vp, vp, vp, vp, i32, C.c_float, vp, vp]),
+        "ssb_mel_postprocess": (C.c_int, [vp, C.c_int64, C.c_float, C.c_float, vp, vp]),
+        "ssb_launch_count": (C.c_int64, []),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

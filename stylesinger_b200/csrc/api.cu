@@ -463,6 +463,12 @@ int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* 
   return run_vocoder(c, v->v, q, mel, f0, rand_ini, src_noise, seed, wav_out);
 }
 
+int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, int32_t* nonzero_frames, void* stream) {
+  SSB_CHECK(mel && nonzero_frames && n_frames >= 0, "bad argument");
+  return mel_postprocess_flat((cudaStream_t)stream, mel, n_frames, vmin, vmax, nonzero_frames);
+}
+int64_t ssb_launch_count(void) { return (int64_t)ssb::g_launches; }
+
 int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
                   const float* b_host, int32_t N, int32_t k, int32_t dilation, int32_t act, float* out, void* stream) {
   SSB_CHECK(x && offsets && w_host && out, "null argument");

@@ -164,6 +164,7 @@ int attention(Ctx& ctx, const AttnArgs& a) {
   dim3 grid((a.max_q + BQ - 1) / BQ, a.heads, a.B);
   attention_kernel<<<grid, 256, sizeof(AttnSmem), ctx.stream>>>(a);
   SSB_CUDA(cudaGetLastError());
+  ++g_launches;
   return 0;
 }
 

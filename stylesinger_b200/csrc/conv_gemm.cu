@@ -214,6 +214,7 @@ int conv_gemm(Ctx& ctx, const ConvGemm& p) {
     conv_gemm_kernel<64><<<grid, 256, 0, ctx.stream>>>(p);
   }
   SSB_CUDA(cudaGetLastError());
+  ++g_launches;
   return 0;
 }
 

@@ -534,13 +534,37 @@ __global__ void k_mel_post(const int4* utt, float* mel, int ld, float* f0, float
   for (int c = threadIdx.x; c < 80; c += 32) mel[r * ld + c] = fminf(fmaxf(mel[r * ld + c], vmin), vmax);
 }
 
+__global__ void k_mel_post_flat(float* mel, int64_t n, float vmin, float vmax, int32_t* cnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+  if (r >= n) return;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < 80; c += 32) {
+    const float v = mel[r * 80 + c];
+    s += fabsf(v);
+    mel[r * 80 + c] = fminf(fmaxf(v, vmin), vmax);
+  }
+  s = warp_sum(s);
+  if (threadIdx.x == 0 && s > 0.f) atomicAdd(cnt, 1);
+}
+
 }  // namespace
+
+int mel_postprocess_flat(cudaStream_t st, float* mel, int64_t n, float vmin, float vmax, int32_t* cnt) {
+  SSB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t), st));
+  if (n > 0) {
+    k_mel_post_flat<<<(unsigned)((n + 7) / 8), dim3(32, 8), 0, st>>>(mel, n, vmin, vmax, cnt);
+    SSB_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  return 0;
+}
 
 #define LAUNCH_ROWS(kern, s, ...)                                            \
   do {                                                                       \
     if (!ctx.dry && s.B > 0 && s.maxlen > 0) {                               \
       kern<<<row_grid(s), dim3(32, RPB), 0, ctx.stream>>>(s.utt, __VA_ARGS__); \
       SSB_CUDA(cudaGetLastError());                                          \
+      ++g_launches;                                                          \
     }                                                                        \
   } while (0)
 
@@ -588,6 +612,7 @@ int token_nonzero_mask(Ctx& ctx, const SeqDev& s, const int32_t* tok, float* mas
 int positions_from_mask(Ctx& ctx, const SeqDev& s, const float* mask, int32_t* pos) {
   if (!ctx.dry && s.B > 0) {
     k_positions<<<s.B, 32, 0, ctx.stream>>>(s.utt, s.B, mask, pos);
+    ++g_launches;
     SSB_CUDA(cudaGetLastError());
   }
   return 0;
@@ -642,6 +667,7 @@ int dur_from_logits(Ctx& ctx, const SeqDev& s, const float* logdur, const float*
 int length_regulate(Ctx& ctx, const SeqDev& fr, const SeqDev& ph, const int32_t* dur, int32_t* mel2ph) {
   if (!ctx.dry && fr.B > 0) {
     k_length_regulate<<<fr.B, 256, (size_t)ph.maxlen * sizeof(int), ctx.stream>>>(fr.utt, ph.utt, dur, mel2ph);
+    ++g_launches;
     SSB_CUDA(cudaGetLastError());
   }
   return 0;
@@ -706,18 +732,21 @@ int nsf_source(Ctx& ctx, const SeqDev& s1, const SeqDev& s256, const float* f0, 
   k_nsf_merge<<<dim3((s256.maxlen + 255) / 256, s1.B), 256, 0, ctx.stream>>>(s1.utt, s256.utt, f0, sines, noise, lw, lb,
                                                                             har, seed, upp);
   SSB_CUDA(cudaGetLastError());
+  g_launches += 2;
   return 0;
 }
 int noise_conv_add(Ctx& ctx, const SeqDev& sx, const SeqDev& s256, float* x, int ld, int C, const float* har,
                    const float* w, const float* b, int s) {
   if (ctx.dry || sx.B == 0) return 0;
   k_noise_conv_add<<<row_grid(sx), dim3(32, RPB), 0, ctx.stream>>>(sx.utt, s256.utt, x, ld, C, har, w, b, s);
+    ++g_launches;
   SSB_CUDA(cudaGetLastError());
   return 0;
 }
 int tanh_out(Ctx& ctx, const SeqDev& s, const float* x, int ld, float* wav) {
   if (ctx.dry || s.B == 0) return 0;
   k_tanh_out<<<dim3((s.maxlen + 255) / 256, s.B), 256, 0, ctx.stream>>>(s.utt, x, ld, wav);
+    ++g_launches;
   SSB_CUDA(cudaGetLastError());
   return 0;
 }

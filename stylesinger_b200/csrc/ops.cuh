@@ -139,4 +139,6 @@ int tanh_out(Ctx&, const SeqDev&, const float* x, int ld, float* wav_tight);
 // mask/clip mel (inference/StyleSinger.py:56-58) in place on guarded rows; f0 masked the same way
 int mel_postprocess(Ctx&, const SeqDev&, float* mel, int ld, float* f0, float vmin, float vmax);
 
+int mel_postprocess_flat(cudaStream_t st, float* mel, int64_t n, float vmin, float vmax, int32_t* cnt);
+
 }  // namespace ssb

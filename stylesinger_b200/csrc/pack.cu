@@ -9,6 +9,7 @@
 
 namespace ssb {
 
+long long g_launches = 0;
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }

@@ -1,0 +1,95 @@
+"""Drop-in mirror of the reference's inference driver (reference inference/StyleSinger.py:21-179).
+
+``StyleSingerInfer`` keeps the reference's method names and argument meaning (``forward_model(inp)``
+with the dict produced by ``preprocess_input``; ``input_to_batch``) and adds ``infer_batch`` for ragged
+batches.  Model + vocoder run in libstylesinger_b200.so; the mel / f0 hand-off between them stays on
+the device (the reference round-trips through numpy, inference/StyleSinger.py:54-63).
+"""
+import ctypes as C
+from typing import List
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .engine import AcousticModel, PackedBatch, Vocoder, pack_batch
+from .hparams import resolve
+
+
+class StyleSingerInfer:
+    def __init__(self, hparams=None, device=None, model_state_dict=None, vocoder_state_dict=None, vocoder_config=None,
+                 ph_encoder=None):
+        """``model_state_dict`` / ``vocoder_state_dict``: the reference checkpoints' ``state_dict['model']`` and
+        ``state_dict['model_gen']`` (utils/commons/ckpt_utils.py:26-67, vocoder_infer/hifigan_nsf.py:24-40)."""
+        self.hparams = resolve(hparams)
+        self.device = torch.device(device if device is not None else "cuda:0")
+        self.ph_encoder = ph_encoder
+        if model_state_dict is None or vocoder_state_dict is None:
+            raise ValueError("state dicts required (reference checkpoints or stylesinger_b200.synth.*_state_dict)")
+        self.model = AcousticModel(model_state_dict, self.hparams, self.device)
+        self.vocoder = Vocoder(vocoder_state_dict, vocoder_config, self.device)
+        self._cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    # ---- reference-compatible single-utterance path ------------------------------------------------
+    def input_to_batch(self, item) -> PackedBatch:
+        """reference inference/StyleSinger.py:139-170 (B=1 assembly)."""
+        u = {"txt_tokens": torch.as_tensor(item["ph_token"]).long(), "note": torch.as_tensor(item["note"]).long(),
+             "note_dur": torch.as_tensor(item["note_dur"]).float(), "note_type": torch.as_tensor(item["note_type"]).long(),
+             "spk_embed": torch.as_tensor(item["spk_embed"]).float(), "emo_embed": torch.as_tensor(item["emo_embed"]).float(),
+             "ref_mels": torch.as_tensor(item["mel"]).float(), "ref_f0": torch.as_tensor(item["f0"]).float()}
+        if item.get("mel2ph") is not None:
+            u["mel2ph"] = torch.as_tensor(item["mel2ph"]).long()
+        return pack_batch([u], use_mel2ph="mel2ph" in u)
+
+    def forward_model(self, inp, seed=0):
+        """reference inference/StyleSinger.py:41-64: returns the waveform (np.float32 [T*hop])."""
+        return self.infer_packed(self.input_to_batch(inp), seed=seed)[0]
+
+    # ---- batched path --------------------------------------------------------------------------------
+    def infer_batch(self, utts: List[dict], seed=0, use_mel2ph=True, return_mel=False):
+        return self.infer_packed(pack_batch(utts, use_mel2ph=use_mel2ph, pin=True), seed=seed, return_mel=return_mel)
+
+    def run_device(self, pb_dev: PackedBatch, seed=0, noise=None, voc_noise=None):
+        """Device-resident ph -> mel -> wav: returns (mel [sumF,80] raw model output, f0 [sumF],
+        wav [sumF'*hop], frame_offsets of the wav) as device tensors."""
+        dur = None
+        if pb_dev.frame_offsets is None:
+            dur, _ = self.model.predict_durations(pb_dev)
+            d = dur.cpu().numpy()  # the host needs the frame count (the reference syncs here too)
+            po = pb_dev.ph_offsets
+            lens = [int(d[po[i]:po[i + 1]].sum()) for i in range(pb_dev.B)]
+            pb_dev.frame_offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        out = self.model.forward(pb_dev, noise=noise, seed=seed, dur=dur, want=("mel_out", "f0_denorm"))
+        mel, f0 = out["mel_out"], out["f0_denorm"]
+        fo = pb_dev.frame_offsets
+        n = int(fo[-1])
+        # inference/StyleSinger.py:56-62: clip to [mel_vmin, mel_vmax]; drop all-zero (padding) frames
+        melc = mel.clone()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib.ssb_mel_postprocess(C.c_void_p(melc.data_ptr()), n, float(self.hparams["mel_vmin"]),
+                                      float(self.hparams["mel_vmax"]), C.c_void_p(self._cnt.data_ptr()), stream),
+              "ssb_mel_postprocess")
+        fo_v, f0_v = fo, f0
+        if int(self._cnt.item()) != n:  # rare: explicit mel2ph with zeros -> compact on the host side
+            keep = (mel.abs().sum(-1) > 0)
+            k = keep.cpu().numpy()
+            lens = [int(k[fo[i]:fo[i + 1]].sum()) for i in range(pb_dev.B)]
+            fo_v = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            melc, f0_v = melc[keep].contiguous(), f0[keep].contiguous()
+        vn = voc_noise or {}
+        wav = self.vocoder.generate(melc, f0_v if self.hparams.get("use_nsf") else None, fo_v,
+                                    rand_ini=vn.get("rand_ini"), src_noise=vn.get("src_noise"), seed=seed)
+        return mel, f0, wav, fo_v
+
+    def infer_packed(self, pb: PackedBatch, seed=0, return_mel=False, noise=None, voc_noise=None):
+        """Host buffers in, host buffers out (H2D of the inputs, D2H of the waveform)."""
+        pb_dev = pb.to(self.device)
+        mel, f0, wav, fo_v = self.run_device(pb_dev, seed=seed, noise=noise, voc_noise=voc_noise)
+        wav_h = wav.cpu().numpy()
+        hop = self.vocoder.hop
+        wavs = [wav_h[fo_v[i] * hop:fo_v[i + 1] * hop] for i in range(pb_dev.B)]
+        if return_mel:
+            mel_h = mel.cpu().numpy()
+            fo = pb_dev.frame_offsets
+            return wavs, [mel_h[fo[i]:fo[i + 1]] for i in range(pb_dev.B)]
+        return wavs

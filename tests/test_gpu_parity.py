@@ -24,7 +24,7 @@ def _maxabs(a, b):
 
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cin,n,k,dil,act", [(80, 256, 1, 1, 0), (256, 512, 3, 8, 1), (256, 1024, 9, 1, 2),
-                                             (80, 160, 5, 1, 2), (192, 3, 1, 1, 0), (32, 32, 11, 5, 3),
+                                             (80, 160, 5, 1, 2), (192, 3, 1, 1, 0), (32, 32, 11, 1, 3), (32, 64, 3, 5, 3),
                                              (1104, 256, 1, 1, 0), (64, 80, 7, 1, 4)])
 def test_conv1d_op_matches_torch(cin, n, k, dil, act):
     from stylesinger_b200.engine import op_conv1d
