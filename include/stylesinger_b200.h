@@ -182,6 +182,14 @@ int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* 
                          int32_t B, const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Select the GEMM path of the denoiser layers: 1 = tcgen05 tensor cores on fp16 hi/lo split operands
+ * (3 MMAs per product, fp32 accumulate; default when available), 0 = fp32 FFMA.  Returns the mode in effect. */
+int ssb_model_set_tensor_cores(ssb_model_t* m, int32_t enable);
+
+/* Unit-test granularity: ssb_op_conv1d through the tcgen05 path (Cin % 64 == 0, N % 128 == 0, no activation). */
+int ssb_op_conv1d_tc(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
+                     const float* b_host, int32_t N, int32_t k, int32_t dilation, float* out, void* stream);
+
 /* StyleSingerInfer.forward_model glue between model and vocoder (inference/StyleSinger.py:56-58):
  * clips mel [n_frames,80] in place to [vmin, vmax] and counts the frames with sum|mel| > 0 into
  * *nonzero_frames (device int32; the reference drops all-zero frames, which only padding can produce). */

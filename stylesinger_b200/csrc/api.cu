@@ -236,39 +236,26 @@ int denoiser_eval_api(Ctx& c, const Model& m, int which, const SeqDev& s, const 
   const Denoiser& d = which == 0 ? m.melnet : m.f0net[which - 1];
   SSB_CHECK(d.T > 0, "denoiser_eval: schedule not set");
   float* cond = alloc_rows(c, s, 256);
-  float* x = alloc_rows(c, s, d.C);
-  float* y = alloc_rows(c, s, d.C);
-  float* zg = alloc_rows(c, s, d.C);
-  float* skip = alloc_rows(c, s, d.C);
-  float* sb = alloc_rows(c, s, d.C);
-  const int ldh = (d.out_dims + 3) & ~3;
-  float* head = alloc_rows(c, s, ldh);
-  float* condall = alloc_rows(c, s, d.L * 2 * d.C, false);
-  WS_OK(c);
+  DenoiserBufs b;
+  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
   RUN(pack_rows(c, s, cond_tight, 256, cond, 256, 256));
-  {
-    ConvGemm g = make_gemm(d.cond_all, s, cond, 256);
-    g.e.out = condall; g.e.ldo = d.L * 2 * d.C;
-    RUN(conv_gemm(c, g));
-  }
-  const float* dt = d.dtab + (size_t)t * d.L * d.C;
+  RUN(hoist_cond(c, d, s, cond, b.condall));
   if (which == 0) {
     float* x80 = alloc_rows(c, s, 80);
     WS_OK(c);
     RUN(pack_rows(c, s, x_tight, 80, x80, 80, 80));
-    ConvGemm g = make_gemm(d.in_proj, s, x80, 80);
-    g.e.act = ACT_RELU; g.e.out = x; g.e.ldo = d.C; g.e.out2 = y; g.e.ldo2 = d.C; g.e.vec2 = dt;
-    RUN(conv_gemm(c, g));
+    RUN(mel_denoiser_eval(c, d, s, t, x80, b));
   } else {
     float* z = alloc_rows(c, s, 1);
     int32_t* uv = alloc_rows_i32(c, s);
     WS_OK(c);
     RUN(pack_rows(c, s, x_tight, 1, z, 1, 1));
     RUN(pack_rows_i32(c, s, uv_tight, uv));
-    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, x, y, d.C));
+    const float* dt = d.dtab + (size_t)t * d.L * d.C;
+    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.x, b.y, d.C, b.yh, b.yl));
+    RUN(denoiser_stack(c, d, s, t, b));
   }
-  RUN(denoiser_stack(c, d, s, t, x, y, condall, zg, skip, sb, head, ldh));
-  RUN(unpack_rows(c, s, head, ldh, out_tight, d.out_dims, d.out_dims));
+  RUN(unpack_rows(c, s, b.head, b.ld_head, out_tight, d.out_dims, d.out_dims));
   return 0;
 }
 
@@ -461,6 +448,56 @@ int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* 
   Seq q;
   q.build(frame_offsets, B);
   return run_vocoder(c, v->v, q, mel, f0, rand_ini, src_noise, seed, wav_out);
+}
+
+int ssb_model_set_tensor_cores(ssb_model_t* m, int32_t enable) {
+  SSB_CHECK(m, "null model");
+  m->m.use_tc = enable != 0 && tc_available();
+  return m->m.use_tc ? 1 : 0;
+}
+
+int ssb_op_conv1d_tc(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
+                     const float* b_host, int32_t N, int32_t k, int32_t dilation, float* out, void* stream) {
+  SSB_CHECK(x && offsets && w_host && out, "null argument");
+  SSB_CHECK(tc_available(), "tensor-core path unavailable (cuTensorMapEncodeTiled)");
+  DevicePool pool;
+  HostTensor w, b;
+  w.data = w_host; w.shape = {N, Cin, k};
+  b.data = b_host; b.shape = {N};
+  Conv cv;
+  ConvTC ct;
+  if (pack_conv(pool, &w, b_host ? &b : nullptr, dilation, PACK_PLAIN, &cv)) return -1;
+  if (pack_conv_tc(pool, &w, dilation, PACK_PLAIN, cv.bias, &ct)) return -1;
+  SSB_CHECK(ct.ok, "shape not eligible for the tensor-core path (Cin % 64, N % 128)");
+  Seq q;
+  q.build(offsets, B);
+  const size_t bytes = ((size_t)q.rows() * (2 * Cin + N + 8) + 8 * (size_t)q.ntiles() + 1024) * sizeof(float) + (1 << 16);
+  void* ws = nullptr;
+  SSB_CUDA(cudaMalloc(&ws, bytes));
+  Ctx c = make_ctx(ws, bytes, stream);
+  SeqDev s;
+  int rc = upload_layout(c, q, 1, &s);
+  float* xg = alloc_rows(c, s, Cin);
+  float* og = alloc_rows(c, s, N);
+  __half* xh = c.alloc<__half>((size_t)s.rows * Cin);
+  __half* xl = c.alloc<__half>((size_t)s.rows * Cin);
+  if (rc == 0 && c.failed) rc = -1;
+  if (rc == 0) rc = pack_rows(c, s, x, Cin, xg, Cin, Cin);
+  if (rc == 0) rc = split_planes(c, xg, Cin, s.rows, Cin, 1.0f, xh, xl);
+  if (rc == 0) {
+    GemmTC g;
+    g.A_hi = xh; g.A_lo = xl; g.rows_total = s.rows; g.w = &ct; g.tiles = s.tiles; g.ntiles = s.ntiles;
+    g.e.mode = EPI_GENERIC; g.e.out = og; g.e.ldo = N;
+    rc = conv_gemm_tc(c, g);
+  }
+  if (rc == 0) rc = unpack_rows(c, s, og, N, out, N, N);
+  cudaError_t se = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(ws);
+  if (rc == 0 && se != cudaSuccess) {
+    ssb::set_error(std::string("ssb_op_conv1d_tc: ") + cudaGetErrorString(se));
+    rc = -2;
+  }
+  return rc;
 }
 
 int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, int32_t* nonzero_frames, void* stream) {

@@ -77,6 +77,12 @@ __device__ __forceinline__ void epilogue4(const Epi& e, int64_t r, int n, int N,
     if (e.accum) x = (x + e.out[r * e.ldo + nn]) * e.gamma;
     e.out[r * e.ldo + nn] = x;
     if (e.out2) e.out2[r * e.ldo2 + nn] = x + (e.vec2 ? e.vec2[nn] : 0.0f);
+    if (e.out2_h) {
+      const float y = x + (e.vec2 ? e.vec2[nn] : 0.0f);
+      const __half h = __float2half_rn(y);
+      e.out2_h[r * e.ldh + nn] = h;
+      e.out2_l[r * e.ldh + nn] = __float2half_rn(y - __half2float(h));
+    }
   }
 }
 

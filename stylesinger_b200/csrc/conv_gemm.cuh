@@ -32,6 +32,9 @@ struct Epi {
   float* out2 = nullptr;         // out2[r, n] = v + vec2[n]
   int ldo2 = 0;
   const float* vec2 = nullptr;
+  __half* out2_h = nullptr;      // optional: (v + vec2) additionally split into fp16 hi/lo planes [rows, ldh]
+  __half* out2_l = nullptr;      // (A operand of the tensor-core GEMM that consumes it)
+  int ldh = 0;
   // EPI_RES_SKIP: columns [0,C) -> residual path (res/beta/rowmask/out/out2), [C,2C) -> skip
   float* skip = nullptr;
   int ld_skip = 0;

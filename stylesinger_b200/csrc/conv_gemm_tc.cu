@@ -1,0 +1,380 @@
+// tcgen05 + TMA + TMEM implicit-GEMM conv1d (see conv_gemm_tc.cuh).  sm_100a only.
+//
+// CTA = 256 threads, persistent over (M-tile, N-tile) pairs:
+//   warp 0 (1 lane)  TMA producer: per K block loads A_hi, A_lo [128x64] and W_hi, W_lo [128x64] (128B swizzle)
+//   warp 1 (1 lane)  MMA issuer:   4 K-steps x 3 products of tcgen05.mma.kind::f16 (M128 N128 K16), fp32 in TMEM
+//   warp 2           TMEM allocator (256 columns = 2 accumulator buffers)
+//   warps 4-7        epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+// smem ring: 3 stages x 64 KB; mbarriers: full/empty per stage, tmem_full/tmem_empty per accumulator buffer.
+#include <cuda_fp16.h>
+
+#include "conv_gemm_tc.cuh"
+
+namespace ssb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;        // 16 KB (A and B tiles have the same size)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr uint32_t TMEM_COLS = 256;
+
+struct TCParams {
+  const int2* tiles;
+  int ntiles, NT, taps, kchunks, dil, center, N;
+  EpiTC e;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s watchdog: fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// K-major, 128B-swizzled tile (rows of 128 bytes, 8-row atoms of 1024 bytes): shared-memory matrix descriptor
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address
+  d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* z) {
+  // 16 consecutive values -> two 32-byte stores per plane
+  __align__(16) __half h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    h[j] = __float2half_rn(z[j]);
+    l[j] = __float2half_rn(z[j] - __half2float(h[j]));
+  }
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(&h[0]);
+  *reinterpret_cast<uint4*>(hi + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+  *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(&l[0]);
+  *reinterpret_cast<uint4*>(lo + 8) = *reinterpret_cast<const uint4*>(&l[8]);
+}
+
+// fused epilogue for 32 consecutive columns [n, n+32) of row r
+__device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, const uint32_t (&raw)[32]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n + j) : 0.0f);
+  if (e.mode == EPI_GATE) {
+    const float4* ap = reinterpret_cast<const float4*>(e.add + r * e.ld_add + n);
+    float z[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 a = __ldg(ap + q);
+      z[2 * q] = sigmoidf_(v[4 * q] + a.x) * tanhf(v[4 * q + 1] + a.y);
+      z[2 * q + 1] = sigmoidf_(v[4 * q + 2] + a.z) * tanhf(v[4 * q + 3] + a.w);
+    }
+    split_store16(e.oh + r * e.ldh + (n >> 1), e.ol + r * e.ldh + (n >> 1), z);
+    return;
+  }
+  if (e.mode == EPI_RES_SKIP) {
+    if (n < e.C) {
+      const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
+      float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 x0 = rp[q];
+        v[4 * q] = (v[4 * q] + x0.x) * e.beta;
+        v[4 * q + 1] = (v[4 * q + 1] + x0.y) * e.beta;
+        v[4 * q + 2] = (v[4 * q + 2] + x0.z) * e.beta;
+        v[4 * q + 3] = (v[4 * q + 3] + x0.w) * e.beta;
+        op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (e.oh) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __ldg(e.vec2 + n + j);
+        split_store16(e.oh + r * e.ldh + n, e.ol + r * e.ldh + n, v);
+        split_store16(e.oh + r * e.ldh + n + 16, e.ol + r * e.ldh + n + 16, v + 16);
+      }
+    } else {
+      float4* sp = reinterpret_cast<float4*>(e.skip + r * e.ld_skip + (n - e.C));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 s = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        if (!e.skip_init) {
+          const float4 o = sp[q];
+          s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        }
+        sp[q] = s;
+      }
+    }
+    return;
+  }
+  float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+__global__ void __launch_bounds__(256, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const TCParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int total = p.ntiles * p.NT;
+  const int nk = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int mt = tile / p.NT, nt = tile - mt * p.NT;
+        const int row0 = p.tiles[mt].x;
+        for (int kb = 0; kb < nk; ++kb) {
+          const int tap = kb / p.kchunks;
+          const int c0 = (kb - tap * p.kchunks) * BK;
+          const int arow = row0 + (tap - p.center) * p.dil;
+          const int brow = tap * p.N + nt * BN;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t fb = full0 + 8 * stage;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sa = sbase + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmA_hi, fb, c0, arow);
+          tma_load_2d(sa + TILE_BYTES, &tmA_lo, fb, c0, arow);
+          tma_load_2d(sa + 2 * TILE_BYTES, &tmB_hi, fb, c0, brow);
+          tma_load_2d(sa + 3 * TILE_BYTES, &tmB_lo, fb, c0, brow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=F16, both K-major, N=128, M=128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * a, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * STAGE_BYTES;
+          const uint64_t dah = make_sdesc(sa), dal = make_sdesc(sa + TILE_BYTES);
+          const uint64_t dbh = make_sdesc(sa + 2 * TILE_BYTES), dbl = make_sdesc(sa + 3 * TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t off = (uint64_t)((ks * 32) >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle atom
+            tc_mma(d_tmem, dah + off, dbh + off, idesc, (kb | ks) != 0 ? 1u : 0u);
+            tc_mma(d_tmem, dah + off, dbl + off, idesc, 1u);
+            tc_mma(d_tmem, dal + off, dbh + off, idesc, 1u);
+          }
+          tc_commit(empty0 + 8 * stage);  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull0 + 8 * a);        // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;  // == warp % 4: TMEM lanes [32*ew, 32*ew + 32)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int mt = tile / p.NT, nt = tile - mt * p.NT;
+      const int2 t = p.tiles[mt];
+      mbar_wait(tfull0 + 8 * a, aph);
+      tc_fence_after();
+      const int rl = ew * 32 + lane;
+      const bool valid = rl < t.y;
+      const int64_t r = (int64_t)t.x + rl;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN + ch * 32), v);
+        if (valid) epilogue32(p.e, r, nt * BN + ch * 32, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * a);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+__global__ void k_split_planes(const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int64_t r = i / C;
+  const int c = (int)(i - r * C);
+  const float v = x[r * ld + c] * scale;
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_encode_tried = false;
+
+EncodeTiledFn get_encode() {
+  if (!g_encode_tried) {
+    g_encode_tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode = (EncodeTiledFn)fn;
+  }
+  return g_encode;
+}
+
+// 2-D fp16 row-major [rows, cols] tensor, box [box_rows x 64 cols], 128B swizzle, zero OOB fill
+int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  SSB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSB_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+}  // namespace
+
+bool tc_available() { return get_encode() != nullptr; }
+
+int make_weight_maps(ConvTC* w) {
+  SSB_CHECK(w->Cin % BK == 0 && w->N % BN == 0, "tensor-core path needs Cin % 64 == 0 and N % 128 == 0");
+  if (make_map(&w->tm_hi, w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, BN)) return -1;
+  if (make_map(&w->tm_lo, w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, BN)) return -1;
+  w->ok = true;
+  return 0;
+}
+
+int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
+  if (ctx.dry || p.ntiles == 0) return 0;
+  const ConvTC& w = *p.w;
+  SSB_CHECK(w.ok, "conv_gemm_tc: weights not packed for the tensor-core path");
+  static bool configured = false;
+  static int num_sms = 148;
+  if (!configured) {
+    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  CUtensorMap ta_hi, ta_lo;
+  if (make_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (make_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  TCParams tp;
+  tp.tiles = p.tiles; tp.ntiles = p.ntiles; tp.NT = w.N / BN; tp.taps = w.taps; tp.kchunks = w.Cin / BK;
+  tp.dil = w.dil; tp.center = w.center; tp.N = w.N; tp.e = p.e;
+  if (!tp.e.bias) tp.e.bias = w.bias;
+  const int total = tp.ntiles * tp.NT;
+  const int grid = total < num_sms ? total : num_sms;
+  conv_gemm_tc_kernel<<<grid, 256, SMEM_BYTES, ctx.stream>>>(ta_hi, ta_lo, w.tm_hi, w.tm_lo, tp);
+  SSB_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int split_planes(Ctx& ctx, const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {
+  if (ctx.dry || rows == 0) return 0;
+  const int64_t n = rows * C;
+  k_split_planes<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(x, ld, rows, C, scale, hi, lo);
+  SSB_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+}  // namespace ssb

@@ -1,0 +1,65 @@
+// tcgen05 / TMA implicit-GEMM conv1d for the dense contractions of the denoisers.
+//
+// Precision: every fp32 operand is carried as TWO fp16 planes (hi = fp16(x), lo = fp16(x - hi));
+// each K step issues three tcgen05.mma (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator, so the
+// contraction keeps ~22 mantissa bits (single-pass bf16/fp16/TF32 cannot meet the
+// mel L-inf < 1e-3 bar at T=100; a 3-pass split can).  Effective tensor peak = 1/3 of the fp16 peak.
+//
+// Layout: A = activation planes [rows, C] fp16 row-major (guard-banded rows, see common.cuh), loaded by
+// TMA as [128 rows x 64 ch] boxes with 128B swizzle at row offset (tap - center) * dilation;
+// B = weights [taps*N, Cin] fp16 (K-major), boxes [128 n x 64 ch].  D = 128 x 128 fp32 in TMEM,
+// double buffered so the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_gemm.cuh"
+
+namespace ssb {
+
+struct ConvTC {            // packed weights for the tensor-core path
+  __half* W_hi = nullptr;  // [taps][N][Cin]
+  __half* W_lo = nullptr;
+  CUtensorMap tm_hi, tm_lo;
+  int taps = 1, Cin = 0, N = 0, dil = 1, center = 0;
+  const float* bias = nullptr;  // [N] (packed column order)
+  bool ok = false;
+};
+
+struct EpiTC {
+  int mode = EPI_GENERIC;        // EPI_GENERIC: out = acc + bias ; EPI_GATE ; EPI_RES_SKIP
+  const float* bias = nullptr;
+  const float* add = nullptr;    // GATE: [rows, ld_add] fp32 added before the gate (hoisted conditioner projection)
+  int ld_add = 0;
+  float* out = nullptr;          // GENERIC / RES_SKIP residual path: fp32 [rows, ldo]
+  int ldo = 0;
+  __half* oh = nullptr;          // GATE: z planes [rows, C];  RES_SKIP: y = x_new + vec2 planes [rows, C] (may be null)
+  __half* ol = nullptr;
+  int ldh = 0;
+  const float* res = nullptr;    // RES_SKIP: x [rows, ld_res]
+  int ld_res = 0;
+  float beta = 1.0f;
+  const float* vec2 = nullptr;   // RES_SKIP: step bias of the next layer [C]
+  float* skip = nullptr;         // RES_SKIP: [rows, ld_skip]
+  int ld_skip = 0;
+  int C = 0;
+  int skip_init = 0;
+};
+
+struct GemmTC {
+  const __half* A_hi = nullptr;  // [rows_total, Cin]
+  const __half* A_lo = nullptr;
+  int64_t rows_total = 0;
+  const ConvTC* w = nullptr;
+  const int2* tiles = nullptr;
+  int ntiles = 0;
+  EpiTC e;
+};
+
+bool tc_available();  // driver entry point for cuTensorMapEncodeTiled resolved
+int make_weight_maps(ConvTC* w);
+int conv_gemm_tc(Ctx& ctx, const GemmTC& p);
+// x fp32 [rows, ld] -> hi/lo planes [rows, C] (all rows incl. guards; guards stay zero)
+int split_planes(Ctx& ctx, const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo);
+
+}  // namespace ssb

@@ -9,6 +9,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "conv_gemm.cuh"
+#include "conv_gemm_tc.cuh"
 #include "ops.cuh"
 
 namespace ssb {
@@ -62,6 +63,7 @@ struct DenoiserLayer {
   Conv dil;    // k3 dilated, gate-interleaved columns, N = 2C
   Conv outp;   // 1x1, N = 2C ([res | skip])
   Conv dproj;  // diffusion_projection C -> C (used only to build the step-bias table)
+  ConvTC dil_tc, outp_tc;  // tensor-core packing of dil / outp (ok == false when not eligible)
 };
 struct Denoiser {
   int C = 0, L = 0, in_dims = 0, out_dims = 0, cycle = 4;
@@ -109,6 +111,7 @@ struct Model {
   Denoiser melnet;
   Conv mel_out, ln_proj;
   float log_eps = 0.f;
+  bool use_tc = true;  // tcgen05 path for the denoiser layer GEMMs (ssb_model_set_tensor_cores)
 };
 
 struct VocStage {
@@ -130,6 +133,7 @@ struct Vocoder {
 // ---- packing helpers (pack.cu) -------------------------------------------------------------------
 int pack_conv(DevicePool& pool, const HostTensor* w, const HostTensor* b, int dil, PackMode mode, Conv* out,
               const HostTensor* g = nullptr /* weight-norm g: w is v */);
+int pack_conv_tc(DevicePool& pool, const HostTensor* w, int dil, PackMode mode, const float* packed_bias, ConvTC* out);
 int pack_linear(DevicePool& pool, const HostTensor* w, const HostTensor* b, Conv* out, int row0 = 0, int nrows = -1);
 int pack_conv_transpose(DevicePool& pool, const HostTensor* v, const HostTensor* g, const HostTensor* b, int u, Conv* out);
 int build_model(TensorMap& tm, const ssb_hparams& hp, Model* m);

@@ -357,7 +357,7 @@ __global__ void k_f0_p_sample(const int4* utt, F0StepArgs a) {
   a.uv[r] = (g1 + p1) > (g0 + p0) ? 1 : 0;  // argmax, ties -> 0
 }
 __global__ void k_ddiff_input(const int4* utt, const float* z, const int32_t* uv, const float* w, const float* bb,
-                              const float* Euv, const float* d0, float* x, float* y, int C) {
+                              const float* Euv, const float* d0, float* x, float* y, int C, __half* yh, __half* yl) {
   ROW_SETUP();
   const int h = C / 2;
   const float f = z[r];
@@ -365,7 +365,13 @@ __global__ void k_ddiff_input(const int4* utt, const float* z, const int32_t* uv
   for (int c = threadIdx.x; c < C; c += 32) {
     const float v = c < h ? (f * w[c] + bb[c]) : Euv[cls * h + (c - h)];
     x[r * C + c] = v;
-    y[r * C + c] = v + d0[c];
+    const float yy = v + d0[c];
+    if (y) y[r * C + c] = yy;
+    if (yh) {
+      const __half h = __float2half_rn(yy);
+      yh[r * C + c] = h;
+      yl[r * C + c] = __float2half_rn(yy - __half2float(h));
+    }
   }
 }
 
@@ -708,8 +714,8 @@ int f0_init(Ctx& ctx, const SeqDev& s, float* z, int32_t* uv, const float* gnois
   return 0;
 }
 int ddiff_input(Ctx& ctx, const SeqDev& s, const float* z, const int32_t* uv, const float* w, const float* b,
-                const float* Euv, const float* d0, float* x, float* y, int C) {
-  LAUNCH_ROWS(k_ddiff_input, s, z, uv, w, b, Euv, d0, x, y, C);
+                const float* Euv, const float* d0, float* x, float* y, int C, __half* yh, __half* yl) {
+  LAUNCH_ROWS(k_ddiff_input, s, z, uv, w, b, Euv, d0, x, y, C, yh, yl);
   return 0;
 }
 int midi_clip_band(Ctx& ctx, const SeqDev& s, const int32_t* midi, float* lo, float* hi) {

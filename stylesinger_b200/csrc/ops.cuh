@@ -107,7 +107,7 @@ int f0_p_sample(Ctx&, const SeqDev&, const F0StepArgs&);
 int f0_init(Ctx&, const SeqDev&, float* z, int32_t* uv, const float* gnoise, uint64_t seed, uint64_t stream_id);
 // DDiffNet input: x[r, c<C/2] = f0*w+b ; x[r, c>=C/2] = E_uv[uv]; y = x + d0
 int ddiff_input(Ctx&, const SeqDev&, const float* z, const int32_t* uv, const float* w, const float* b, const float* Euv,
-                const float* d0, float* x, float* y, int C);
+                const float* d0, float* x, float* y, int C, __half* yh = nullptr, __half* yl = nullptr);
 
 // ---- pitch glue (a15) -----------------------------------------------------------------------------------
 int midi_clip_band(Ctx&, const SeqDev&, const int32_t* midi, float* lo, float* hi);

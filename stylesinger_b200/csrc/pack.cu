@@ -97,6 +97,35 @@ int pack_conv(DevicePool& pool, const HostTensor* w, const HostTensor* b, int di
   return pack_from_host(pool, src, N, Cin, k, b ? b->data : nullptr, dil, mode, out);
 }
 
+// Tensor-core packing: W[tap][n'][c] as fp16 hi/lo planes (n' = permuted output column), + TMA maps.
+int pack_conv_tc(DevicePool& pool, const HostTensor* w, int dil, PackMode mode, const float* packed_bias, ConvTC* out) {
+  if (!w) return -1;
+  const int N = (int)w->shape[0], Cin = (int)w->shape[1], k = w->shape.size() == 3 ? (int)w->shape[2] : 1;
+  if (Cin % 64 != 0 || N % 128 != 0 || !tc_available()) return 0;  // not eligible: out->ok stays false
+  std::vector<__half> hi((size_t)k * N * Cin), lo((size_t)k * N * Cin);
+  for (int n = 0; n < N; ++n) {
+    const int pn = perm_col(n, N, mode);
+    for (int c = 0; c < Cin; ++c)
+      for (int j = 0; j < k; ++j) {
+        const float v = w->data[((size_t)n * Cin + c) * k + j];
+        const __half h = __float2half_rn(v);
+        const size_t o = ((size_t)j * N + pn) * Cin + c;
+        hi[o] = h;
+        lo[o] = __float2half_rn(v - __half2float(h));
+      }
+  }
+  void *dh = nullptr, *dl = nullptr;
+  SSB_CUDA(cudaMalloc(&dh, hi.size() * sizeof(__half)));
+  pool.ptrs.push_back(dh);
+  SSB_CUDA(cudaMalloc(&dl, lo.size() * sizeof(__half)));
+  pool.ptrs.push_back(dl);
+  SSB_CUDA(cudaMemcpy(dh, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  SSB_CUDA(cudaMemcpy(dl, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  out->W_hi = (__half*)dh; out->W_lo = (__half*)dl;
+  out->taps = k; out->Cin = Cin; out->N = N; out->dil = dil; out->center = (k - 1) / 2; out->bias = packed_bias;
+  return make_weight_maps(out);
+}
+
 int pack_linear(DevicePool& pool, const HostTensor* w, const HostTensor* b, Conv* out, int row0, int nrows) {
   if (!w) return -1;
   const int Ntot = (int)w->shape[0], Cin = (int)w->shape[1];
@@ -191,6 +220,8 @@ static int build_denoiser(TensorMap& tm, DevicePool& pool, const std::string& p,
     if (pack_conv(pool, tm.get(q + "dilated_conv.weight"), tm.get(q + "dilated_conv.bias"), dil, PACK_GATE_SIG_TANH, &d->layers[i].dil)) return -1;
     if (pack_conv(pool, tm.get(q + "output_projection.weight"), tm.get(q + "output_projection.bias"), 1, PACK_PLAIN, &d->layers[i].outp)) return -1;
     if (pack_linear(pool, tm.get(q + "diffusion_projection.weight"), tm.get(q + "diffusion_projection.bias"), &d->layers[i].dproj)) return -1;
+    if (pack_conv_tc(pool, tm.get(q + "dilated_conv.weight"), dil, PACK_GATE_SIG_TANH, d->layers[i].dil.bias, &d->layers[i].dil_tc)) return -1;
+    if (pack_conv_tc(pool, tm.get(q + "output_projection.weight"), 1, PACK_PLAIN, d->layers[i].outp.bias, &d->layers[i].outp_tc)) return -1;
     const HostTensor* cw = tm.get(q + "conditioner_projection.weight");
     const HostTensor* cb = tm.get(q + "conditioner_projection.bias");
     if (!cw || !cb) return -1;

@@ -288,50 +288,85 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
 
 // ------------------------------------------------------------------------------------------------
 // a13/a18: the denoiser residual stack for one diffusion step.
-// x [rows,C] (residual stream, overwritten), y = x + d[t][0] [rows,C] (overwritten), condall [rows, L*2C]
-// -> head [rows, out_dims(pad 4)]
-int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, float* x, float* y, const float* condall,
-                   float* zg, float* skip, float* sbuf, float* head, int ld_head) {
+// On entry b.x holds the residual stream and (b.y | b.yh,b.yl) holds x + d[t][0]; both are overwritten.
+// SIMT path: fp32 conv_gemm.  Tensor-core path (b.tc): tcgen05 GEMMs on fp16 hi/lo planes.
+int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBufs& b) {
   const int C = d.C, L = d.L;
   SSB_CHECK(d.dtab != nullptr && t >= 0 && t < d.T, "denoiser: schedule not set (ssb_model_set_schedule) or bad t");
   const float* dt = d.dtab + (size_t)t * L * C;
   for (int l = 0; l < L; ++l) {
+    if (b.tc) {
+      {
+        GemmTC g;
+        g.A_hi = b.yh; g.A_lo = b.yl; g.rows_total = s.rows; g.w = &d.layers[l].dil_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+        g.e.mode = EPI_GATE; g.e.add = b.condall + (size_t)l * 2 * C; g.e.ld_add = L * 2 * C;
+        g.e.oh = b.zh; g.e.ol = b.zl; g.e.ldh = C;
+        RUN(conv_gemm_tc(c, g));
+      }
+      {
+        GemmTC g;
+        g.A_hi = b.zh; g.A_lo = b.zl; g.rows_total = s.rows; g.w = &d.layers[l].outp_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+        g.e.mode = EPI_RES_SKIP; g.e.C = C; g.e.res = b.x; g.e.ld_res = C; g.e.beta = 0.70710678118654752440f;
+        g.e.out = b.x; g.e.ldo = C;
+        if (l + 1 < L) { g.e.oh = b.yh; g.e.ol = b.yl; g.e.ldh = C; g.e.vec2 = dt + (size_t)(l + 1) * C; }
+        g.e.skip = b.skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
+        RUN(conv_gemm_tc(c, g));
+      }
+      continue;
+    }
     {
-      ConvGemm g = make_gemm(d.layers[l].dil, s, y, C);
-      g.e.mode = EPI_GATE; g.e.add = condall + (size_t)l * 2 * C; g.e.ld_add = L * 2 * C; g.e.out = zg; g.e.ldo = C;
+      ConvGemm g = make_gemm(d.layers[l].dil, s, b.y, C);
+      g.e.mode = EPI_GATE; g.e.add = b.condall + (size_t)l * 2 * C; g.e.ld_add = L * 2 * C; g.e.out = b.zg; g.e.ldo = C;
       RUN(conv_gemm(c, g));
     }
     {
-      ConvGemm g = make_gemm(d.layers[l].outp, s, zg, C);
-      g.e.mode = EPI_RES_SKIP; g.e.C = C; g.e.res = x; g.e.ld_res = C; g.e.beta = 0.70710678118654752440f;
-      g.e.out = x; g.e.ldo = C;
-      if (l + 1 < L) { g.e.out2 = y; g.e.ldo2 = C; g.e.vec2 = dt + (size_t)(l + 1) * C; }
-      g.e.skip = skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
+      ConvGemm g = make_gemm(d.layers[l].outp, s, b.zg, C);
+      g.e.mode = EPI_RES_SKIP; g.e.C = C; g.e.res = b.x; g.e.ld_res = C; g.e.beta = 0.70710678118654752440f;
+      g.e.out = b.x; g.e.ldo = C;
+      if (l + 1 < L) { g.e.out2 = b.y; g.e.ldo2 = C; g.e.vec2 = dt + (size_t)(l + 1) * C; }
+      g.e.skip = b.skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
       RUN(conv_gemm(c, g));
     }
   }
   {
-    ConvGemm g = make_gemm(d.skip_proj, s, skip, C);
+    ConvGemm g = make_gemm(d.skip_proj, s, b.skip, C);
     g.a_scale = 1.0f / sqrtf((float)L);
-    g.e.act = ACT_RELU; g.e.out = sbuf; g.e.ldo = C;
+    g.e.act = ACT_RELU; g.e.out = b.sbuf; g.e.ldo = C;
     RUN(conv_gemm(c, g));
   }
   {
-    ConvGemm g = make_gemm(d.out_proj, s, sbuf, C);
-    g.e.out = head; g.e.ldo = ld_head;
+    ConvGemm g = make_gemm(d.out_proj, s, b.sbuf, C);
+    g.e.out = b.head; g.e.ldo = b.ld_head;
     RUN(conv_gemm(c, g));
   }
   return 0;
 }
 
-struct DenoiserBufs {
-  float *x, *y, *zg, *skip, *sbuf, *head, *condall;
-  int ld_head;
-};
-static int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, DenoiserBufs* b) {
+static __half* alloc_half_rows(Ctx& c, const SeqDev& s, int C) {
+  __half* p = c.alloc<__half>((size_t)s.rows * C);
+  if (!c.dry && p && !c.failed) cudaMemsetAsync(p, 0, (size_t)s.rows * C * sizeof(__half), c.stream);
+  return p;
+}
+bool denoiser_tc_ok(const Model& m, const Denoiser& d) {
+  if (!m.use_tc) return false;
+  for (auto& l : d.layers)
+    if (!l.dil_tc.ok || !l.outp_tc.ok) return false;
+  return true;
+}
+int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b) {
+  b->tc = tc;
   b->x = alloc_rows(c, s, d.C);
-  b->y = alloc_rows(c, s, d.C);
-  b->zg = alloc_rows(c, s, d.C);
+  b->y = b->zg = nullptr;
+  b->yh = b->yl = b->zh = b->zl = nullptr;
+  if (tc) {
+    b->yh = alloc_half_rows(c, s, d.C);
+    b->yl = alloc_half_rows(c, s, d.C);
+    b->zh = alloc_half_rows(c, s, d.C);
+    b->zl = alloc_half_rows(c, s, d.C);
+  } else {
+    b->y = alloc_rows(c, s, d.C);
+    b->zg = alloc_rows(c, s, d.C);
+  }
   b->skip = alloc_rows(c, s, d.C);
   b->sbuf = alloc_rows(c, s, d.C);
   b->ld_head = (d.out_dims + 3) & ~3;
@@ -340,19 +375,21 @@ static int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, DenoiserBu
   WS_OK(c);
   return 0;
 }
-static int hoist_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, float* condall) {
+int hoist_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, float* condall) {
   ConvGemm g = make_gemm(d.cond_all, s, cond_g, 256);
   g.e.out = condall; g.e.ldo = d.L * 2 * d.C;
   return conv_gemm(c, g);
 }
 
 // a18 entry for one evaluation (mel): x80 [rows,80] guarded -> head
-static int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const float* x80, DenoiserBufs& b) {
+int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const float* x80, DenoiserBufs& b) {
   ConvGemm g = make_gemm(d.in_proj, s, x80, 80);
-  g.e.act = ACT_RELU; g.e.out = b.x; g.e.ldo = d.C; g.e.out2 = b.y; g.e.ldo2 = d.C;
+  g.e.act = ACT_RELU; g.e.out = b.x; g.e.ldo = d.C;
   g.e.vec2 = d.dtab + (size_t)t * d.L * d.C;
+  if (b.tc) { g.e.out2_h = b.yh; g.e.out2_l = b.yl; g.e.ldh = d.C; }
+  else { g.e.out2 = b.y; g.e.ldo2 = d.C; }
   RUN(conv_gemm(c, g));
-  return denoiser_stack(c, d, s, t, b.x, b.y, b.condall, b.zg, b.skip, b.sbuf, b.head, b.ld_head);
+  return denoiser_stack(c, d, s, t, b);
 }
 
 // a18+a19: DiffusionDecoder.forward(infer=True) (shallow_diffusion_tts.py:284-307)
@@ -362,7 +399,7 @@ int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond
   SSB_CHECK(d.T > 0, "mel schedule not set: call ssb_model_set_schedule(which=0)");
   const size_t mk = c.mark();
   DenoiserBufs b;
-  RUN(alloc_denoiser(c, d, s, &b));
+  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
   float* xm = alloc_rows(c, s, 80);
   WS_OK(c);
   RUN(hoist_cond(c, d, s, cond_g, b.condall));
@@ -387,7 +424,7 @@ int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const f
   SSB_CHECK(d.T > 0, "f0 schedule not set: call ssb_model_set_schedule(which=1)");
   const size_t mk = c.mark();
   DenoiserBufs b;
-  RUN(alloc_denoiser(c, d, s, &b));
+  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
   RUN(hoist_cond(c, d, s, cond_g, b.condall));
   const int T = d.T;
   const size_t per = (size_t)s.total;
@@ -395,8 +432,8 @@ int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const f
   RUN(f0_init(c, s, z, uv, gnoise, seed, sbase));
   for (int t = T - 1; t >= 0; --t) {
     const float* dt = d.dtab + (size_t)t * d.L * d.C;
-    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.x, b.y, d.C));
-    RUN(denoiser_stack(c, d, s, t, b.x, b.y, b.condall, b.zg, b.skip, b.sbuf, b.head, b.ld_head));
+    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.x, b.y, d.C, b.yh, b.yl));
+    RUN(denoiser_stack(c, d, s, t, b));
     F0StepArgs a;
     a.z = z; a.uv = uv; a.out3 = b.head; a.ld3 = b.ld_head; a.lo = lo; a.hi = hi;
     a.gnoise = gnoise ? gnoise + per * (size_t)(T - t) : nullptr;

@@ -10,8 +10,17 @@ int run_duration_predictor(Ctx& c, const Model& m, const SeqDev& sp, const float
                            float* logdur, int32_t* dur);
 int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const float* dec0, const float* ref_g,
               const float* reff0_g, float* style, int32_t* codes, float* rq_in_out);
-int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, float* x, float* y, const float* condall,
-                   float* zg, float* skip, float* sbuf, float* head, int ld_head);
+struct DenoiserBufs {
+  float *x, *y, *zg, *skip, *sbuf, *head, *condall;
+  __half *yh, *yl, *zh, *zl;  // tensor-core path: fp16 hi/lo planes of y = x + step bias and of the gate output
+  int ld_head;
+  bool tc;
+};
+bool denoiser_tc_ok(const Model& m, const Denoiser& d);
+int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b);
+int hoist_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, float* condall);
+int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const float* x80, DenoiserBufs& b);
+int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBufs& b);
 int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
                       const float* noise, uint64_t seed, float* mel_tight);
 int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const float* cond_g, const float* lo,

@@ -157,6 +157,10 @@ class AcousticModel:
             lib.ssb_model_free(h)
             self._h = None
 
+    def set_tensor_cores(self, enable=True):
+        """tcgen05 (fp16 hi/lo split, 3 MMAs) vs fp32 FFMA for the denoiser layer GEMMs. Returns the mode in effect."""
+        return bool(lib.ssb_model_set_tensor_cores(self._h, 1 if enable else 0))
+
     # -- schedules -------------------------------------------------------------------------------
     def set_timesteps(self, T=None, f0_T=None):
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -370,6 +374,20 @@ def op_conv1d(x, offsets, w, b, dilation=1, act=0):
     check(lib.ssb_op_conv1d(_ptr(x), off.ctypes.data, len(off) - 1, Cin, C.c_void_p(wc.data_ptr()),
                             None if bc is None else C.c_void_p(bc.data_ptr()), N, k, dilation, act, _ptr(out), stream),
           "ssb_op_conv1d")
+    return out
+
+
+def op_conv1d_tc(x, offsets, w, b, dilation=1):
+    _require_cuda()
+    off = np.ascontiguousarray(offsets, np.int32)
+    N, Cin, k = w.shape
+    wc = w.detach().cpu().float().contiguous()
+    bc = None if b is None else b.detach().cpu().float().contiguous()
+    out = torch.empty((x.shape[0], N), dtype=torch.float32, device=x.device)
+    stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    check(lib.ssb_op_conv1d_tc(_ptr(x), off.ctypes.data, len(off) - 1, Cin, C.c_void_p(wc.data_ptr()),
+                               None if bc is None else C.c_void_p(bc.data_ptr()), N, k, dilation, _ptr(out), stream),
+          "ssb_op_conv1d_tc")
     return out
 
 

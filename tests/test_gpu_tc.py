@@ -1,0 +1,83 @@
+"""tcgen05 path (fp16 hi/lo split operands, 3 MMAs per product, fp32 TMEM accumulators) against torch fp32
+and against the reference-generated goldens; and SIMT-vs-tensor-core agreement of the samplers."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import stylesinger_oracle as O
+from tests.common import acoustic_engine, acoustic_sd, golden, hp_for
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _maxabs(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+
+
+@pytest.mark.parametrize("cin,n,k,dil", [(64, 128, 1, 1), (256, 512, 1, 1), (256, 512, 3, 8), (192, 384, 3, 2),
+                                         (192, 384, 1, 1), (256, 256, 3, 1)])
+def test_conv1d_tc_matches_torch(cin, n, k, dil):
+    from stylesinger_b200.engine import op_conv1d_tc
+    g = torch.Generator().manual_seed(cin + n + k)
+    lens = [5, 131, 64, 300, 128]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    x = torch.randn(int(offs[-1]), cin, generator=g) * 2.0
+    w = torch.randn(n, cin, k, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(n, generator=g)
+    y = op_conv1d_tc(x.to(DEV), offs, w, b, dilation=dil).cpu()
+    worst = 0.0
+    for i in range(len(lens)):
+        xi = x[offs[i]:offs[i + 1]].t()[None].double()
+        ref = F.conv1d(xi, w.double(), b.double(), padding=dil * (k - 1) // 2, dilation=dil)[0].t()
+        worst = max(worst, _maxabs(y[offs[i]:offs[i + 1]], ref))
+    print(f"tc conv {cin}->{n} k{k} d{dil}: max err {worst:.3e}")
+    assert worst < 2e-5
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_denoisers_match_reference_golden(tc):
+    g, meta = golden("ref_small_T4")
+    m = acoustic_engine(meta["T"])
+    assert m.set_tensor_cores(tc) == tc
+    try:
+        Fr = g["dn_spec"].shape[1]
+        offs = np.array([0, Fr], np.int32)
+        cond = torch.from_numpy(g["dn_cond"].T.copy()).to(DEV)
+        e = m.denoiser_eval(0, torch.from_numpy(g["dn_spec"].T.copy()).to(DEV), None, meta["T"] - 1, cond, offs)
+        f0 = torch.from_numpy(g["dd_f0"]).to(DEV)
+        uv = torch.from_numpy(g["dd_uv"].astype(np.int32)).to(DEV)
+        e2 = m.denoiser_eval(1, f0, uv, 1, cond, offs)
+        e3 = m.denoiser_eval(2, f0, uv, 0, cond, offs)
+        errs = (_maxabs(e.cpu().numpy().T, g["dn_out"]), _maxabs(e2.cpu().numpy().T, g["dd_out"]),
+                _maxabs(e3.cpu().numpy().T, g["dd_out_inp"]))
+        print("tc" if tc else "simt", "denoiser errs", errs)
+        assert max(errs) < 5e-5
+    finally:
+        m.set_tensor_cores(True)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_mel_diffusion_T100_vs_oracle(tc):
+    T, Fr = 100, 80
+    hp = hp_for(T)
+    gen = torch.Generator().manual_seed(77)
+    cond = torch.randn(1, Fr, 256, generator=gen)
+    coarse = (-3 + 0.8 * torch.randn(1, Fr, 80, generator=gen)).clamp(-6, 0.5)
+    ns = O.NoiseSource(123)
+    ns.record = []
+    with torch.no_grad():
+        ref = O.mel_diffusion_sample(cond, coarse, acoustic_sd(), hp, ns)
+    noise = torch.stack([n[0, 0].t().contiguous() for n in ns.record]).contiguous().to(DEV)
+    m = acoustic_engine(T, 4)
+    m.set_tensor_cores(tc)
+    try:
+        mel = m.mel_diffusion(cond[0].to(DEV).contiguous(), coarse[0].to(DEV).contiguous(), np.array([0, Fr], np.int32), noise)
+        err = _maxabs(mel, ref[0])
+        print(("tc" if tc else "simt"), "mel L-inf after T=100:", err)
+        assert err < 1e-3
+    finally:
+        m.set_tensor_cores(True)
