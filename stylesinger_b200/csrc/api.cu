@@ -239,7 +239,7 @@ int denoiser_eval_api(Ctx& c, const Model& m, int which, const SeqDev& s, const 
   DenoiserBufs b;
   RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
   RUN(pack_rows(c, s, cond_tight, 256, cond, 256, 256));
-  RUN(hoist_cond(c, d, s, cond, b.condall));
+  RUN(prepare_cond(c, d, s, cond, b));
   if (which == 0) {
     float* x80 = alloc_rows(c, s, 80);
     WS_OK(c);

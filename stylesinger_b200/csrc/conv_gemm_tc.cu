@@ -1,11 +1,13 @@
 // tcgen05 + TMA + TMEM implicit-GEMM conv1d (see conv_gemm_tc.cuh).  sm_100a only.
 //
 // CTA = 256 threads, persistent over (M-tile, N-tile) pairs:
-//   warp 0 (1 lane)  TMA producer: per K block loads A_hi, A_lo [128x64] and W_hi, W_lo [128x64] (128B swizzle)
-//   warp 1 (1 lane)  MMA issuer:   4 K-steps x 3 products of tcgen05.mma.kind::f16 (M128 N128 K16), fp32 in TMEM
-//   warp 2           TMEM allocator (256 columns = 2 accumulator buffers)
-//   warps 4-7        epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
-// smem ring: 3 stages x 64 KB; mbarriers: full/empty per stage, tmem_full/tmem_empty per accumulator buffer.
+//   warp 0 (1 lane)  TMA producer: per K block loads A_hi, A_lo [128x64] and W_hi, W_lo [BNx64] (128B swizzle)
+//   warp 1 (1 lane)  MMA issuer:   4 K-steps x 3 products of tcgen05.mma.kind::f16 (M128 N=BN K16), fp32 in TMEM
+//   warp 2           TMEM allocator (2 x BN columns = 2 accumulator buffers)
+//   warps 4-7        epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global,
+//                    with the epilogue's own global operands (residual / skip) prefetched one chunk ahead
+// smem ring: BN=128: 3 stages x 64 KB, BN=64: 4 stages x 48 KB; mbarriers: full/empty per stage,
+// tmem_full/tmem_empty per accumulator buffer.  BN=64 is picked for small problems (more CTAs in flight).
 #include <cuda_fp16.h>
 
 #include "conv_gemm_tc.cuh"
@@ -14,15 +16,21 @@ namespace ssb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 2;        // 16 KB (A and B tiles have the same size)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr int BM = 128, BK = 64;
+constexpr int A_TILE = BM * BK * 2;  // 16 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE = BN * BK * 2;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
 
 struct TCParams {
   const int2* tiles;
-  int ntiles, NT, taps, kchunks, dil, center, N;
+  int ntiles, NT, taps, kchunks, kchunks2, dil, center, N;
   EpiTC e;
 };
 
@@ -92,7 +100,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* z) {
-  // 16 consecutive values -> two 32-byte stores per plane
+  // 16 consecutive values -> two 16-byte stores per plane
   __align__(16) __half h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -105,30 +113,41 @@ __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const floa
   *reinterpret_cast<uint4*>(lo + 8) = *reinterpret_cast<const uint4*>(&l[8]);
 }
 
+// Global operands of the epilogue for 32 columns [n, n+32) of row r, fetched ahead of use.
+struct Pre {
+  float4 a[8];
+};
+__device__ __forceinline__ void prefetch32(const EpiTC& e, int64_t r, int n, bool valid, Pre& p) {
+  if (e.mode != EPI_RES_SKIP || !valid) return;
+  if (n < e.C) {
+    const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) p.a[q] = rp[q];
+  } else if (!e.skip_init) {
+    const float4* sp = reinterpret_cast<const float4*>(e.skip + r * e.ld_skip + (n - e.C));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) p.a[q] = sp[q];
+  }
+}
+
 // fused epilogue for 32 consecutive columns [n, n+32) of row r
-__device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, const uint32_t (&raw)[32]) {
+__device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, const uint32_t (&raw)[32], const Pre& pre) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n + j) : 0.0f);
   if (e.mode == EPI_GATE) {
-    const float4* ap = reinterpret_cast<const float4*>(e.add + r * e.ld_add + n);
     float z[16];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 a = __ldg(ap + q);
-      z[2 * q] = sigmoidf_(v[4 * q] + a.x) * tanhf(v[4 * q + 1] + a.y);
-      z[2 * q + 1] = sigmoidf_(v[4 * q + 2] + a.z) * tanhf(v[4 * q + 3] + a.w);
-    }
+    for (int q = 0; q < 16; ++q) z[q] = sigmoidf_(v[2 * q]) * tanhf(v[2 * q + 1]);
     split_store16(e.oh + r * e.ldh + (n >> 1), e.ol + r * e.ldh + (n >> 1), z);
     return;
   }
   if (e.mode == EPI_RES_SKIP) {
     if (n < e.C) {
-      const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
       float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 x0 = rp[q];
+        const float4 x0 = pre.a[q];
         v[4 * q] = (v[4 * q] + x0.x) * e.beta;
         v[4 * q + 1] = (v[4 * q + 1] + x0.y) * e.beta;
         v[4 * q + 2] = (v[4 * q + 2] + x0.z) * e.beta;
@@ -147,7 +166,7 @@ __device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, con
       for (int q = 0; q < 8; ++q) {
         float4 s = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         if (!e.skip_init) {
-          const float4 o = sp[q];
+          const float4 o = pre.a[q];
           s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
         }
         sp[q] = s;
@@ -160,13 +179,18 @@ __device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, con
   for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+template <int BN>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
+                    const __grid_constant__ CUtensorMap tmB2_hi, const __grid_constant__ CUtensorMap tmB2_lo,
                     const TCParams p) {
+  using K = Cfg<BN>;
+  constexpr int STAGES = K::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * K::STAGE);
   // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base address
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const uint32_t sbase = smem_u32(smem);
@@ -185,7 +209,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -194,7 +218,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const int total = p.ntiles * p.NT;
-  const int nk = p.taps * p.kchunks;
+  const int nk1 = p.taps * p.kchunks;
+  const int nk = nk1 + p.kchunks2;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -204,25 +229,33 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int mt = tile / p.NT, nt = tile - mt * p.NT;
         const int row0 = p.tiles[mt].x;
         for (int kb = 0; kb < nk; ++kb) {
-          const int tap = kb / p.kchunks;
-          const int c0 = (kb - tap * p.kchunks) * BK;
-          const int arow = row0 + (tap - p.center) * p.dil;
-          const int brow = tap * p.N + nt * BN;
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t fb = full0 + 8 * stage;
-          mbar_expect_tx(fb, STAGE_BYTES);
-          const uint32_t sa = sbase + stage * STAGE_BYTES;
-          tma_load_2d(sa, &tmA_hi, fb, c0, arow);
-          tma_load_2d(sa + TILE_BYTES, &tmA_lo, fb, c0, arow);
-          tma_load_2d(sa + 2 * TILE_BYTES, &tmB_hi, fb, c0, brow);
-          tma_load_2d(sa + 3 * TILE_BYTES, &tmB_lo, fb, c0, brow);
+          mbar_expect_tx(fb, K::STAGE);
+          const uint32_t sa = sbase + stage * K::STAGE;
+          if (kb < nk1) {
+            const int tap = kb / p.kchunks;
+            const int c0 = (kb - tap * p.kchunks) * BK;
+            const int arow = row0 + (tap - p.center) * p.dil;
+            const int brow = tap * p.N + nt * BN;
+            tma_load_2d(sa, &tmA_hi, fb, c0, arow);
+            tma_load_2d(sa + A_TILE, &tmA_lo, fb, c0, arow);
+            tma_load_2d(sa + 2 * A_TILE, &tmB_hi, fb, c0, brow);
+            tma_load_2d(sa + 2 * A_TILE + K::B_TILE, &tmB_lo, fb, c0, brow);
+          } else {
+            const int c0 = (kb - nk1) * BK;
+            tma_load_2d(sa, &tmA2_hi, fb, c0, row0);
+            tma_load_2d(sa + A_TILE, &tmA2_lo, fb, c0, row0);
+            tma_load_2d(sa + 2 * A_TILE, &tmB2_hi, fb, c0, nt * BN);
+            tma_load_2d(sa + 2 * A_TILE + K::B_TILE, &tmB2_lo, fb, c0, nt * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=F16, both K-major, N=128, M=128
+      // instruction descriptor: D=F32, A=B=F16, both K-major, N=BN, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -236,9 +269,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = sbase + stage * STAGE_BYTES;
-          const uint64_t dah = make_sdesc(sa), dal = make_sdesc(sa + TILE_BYTES);
-          const uint64_t dbh = make_sdesc(sa + 2 * TILE_BYTES), dbl = make_sdesc(sa + 3 * TILE_BYTES);
+          const uint32_t sa = sbase + stage * K::STAGE;
+          const uint64_t dah = make_sdesc(sa), dal = make_sdesc(sa + A_TILE);
+          const uint64_t dbh = make_sdesc(sa + 2 * A_TILE), dbl = make_sdesc(sa + 2 * A_TILE + K::B_TILE);
 #pragma unroll
           for (int ks = 0; ks < BK / 16; ++ks) {
             const uint64_t off = (uint64_t)((ks * 32) >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle atom
@@ -254,22 +287,27 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;  // == warp % 4: TMEM lanes [32*ew, 32*ew + 32)
+    constexpr int NCH = BN / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int mt = tile / p.NT, nt = tile - mt * p.NT;
       const int2 t = p.tiles[mt];
-      mbar_wait(tfull0 + 8 * a, aph);
-      tc_fence_after();
       const int rl = ew * 32 + lane;
       const bool valid = rl < t.y;
       const int64_t r = (int64_t)t.x + rl;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      Pre cur, nxt;
+      prefetch32(p.e, r, nt * BN, valid, cur);  // issued before the accumulator is ready: overlaps the MMAs
+      mbar_wait(tfull0 + 8 * a, aph);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        if (ch + 1 < NCH) prefetch32(p.e, r, nt * BN + (ch + 1) * 32, valid, nxt);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN + ch * 32), v);
-        if (valid) epilogue32(p.e, r, nt * BN + ch * 32, v);
+        if (valid) epilogue32(p.e, r, nt * BN + ch * 32, v, cur);
+        cur = nxt;
       }
       tc_fence_before();
       __syncwarp();
@@ -280,7 +318,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS) : "memory");
   }
 }
 
@@ -328,14 +366,40 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint
   return 0;
 }
 
+template <int BN>
+int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
+  const ConvTC& w = *p.w;
+  const ConvTC& w2 = p.w2 ? *p.w2 : *p.w;
+  const int bi = BN == 128 ? 0 : 1;
+  CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo;
+  if (make_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (make_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (p.w2) {
+    if (make_map(&ta2_hi, p.A2_hi, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+    if (make_map(&ta2_lo, p.A2_lo, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+  } else {
+    ta2_hi = ta_hi;
+    ta2_lo = ta_lo;
+  }
+  const int total = tp.ntiles * tp.NT;
+  const int grid = total < num_sms ? total : num_sms;
+  conv_gemm_tc_kernel<BN><<<grid, 256, Cfg<BN>::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm_hi[bi], w.tm_lo[bi], ta2_hi, ta2_lo,
+                                                                    w2.tm_hi[bi], w2.tm_lo[bi], tp);
+  SSB_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
 }  // namespace
 
 bool tc_available() { return get_encode() != nullptr; }
 
 int make_weight_maps(ConvTC* w) {
-  SSB_CHECK(w->Cin % BK == 0 && w->N % BN == 0, "tensor-core path needs Cin % 64 == 0 and N % 128 == 0");
-  if (make_map(&w->tm_hi, w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, BN)) return -1;
-  if (make_map(&w->tm_lo, w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, BN)) return -1;
+  SSB_CHECK(w->Cin % BK == 0 && w->N % 128 == 0, "tensor-core path needs Cin % 64 == 0 and N % 128 == 0");
+  if (make_map(&w->tm_hi[0], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 128)) return -1;
+  if (make_map(&w->tm_lo[0], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 128)) return -1;
+  if (make_map(&w->tm_hi[1], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 64)) return -1;
+  if (make_map(&w->tm_lo[1], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 64)) return -1;
   w->ok = true;
   return 0;
 }
@@ -343,29 +407,30 @@ int make_weight_maps(ConvTC* w) {
 int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   if (ctx.dry || p.ntiles == 0) return 0;
   const ConvTC& w = *p.w;
-  SSB_CHECK(w.ok, "conv_gemm_tc: weights not packed for the tensor-core path");
+  SSB_CHECK(w.ok && (!p.w2 || (p.w2->ok && p.w2->N == w.N && p.w2->taps == 1)), "conv_gemm_tc: weights not packed for the tensor-core path");
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
-    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  CUtensorMap ta_hi, ta_lo;
-  if (make_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
-  if (make_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
   TCParams tp;
-  tp.tiles = p.tiles; tp.ntiles = p.ntiles; tp.NT = w.N / BN; tp.taps = w.taps; tp.kchunks = w.Cin / BK;
+  tp.tiles = p.tiles; tp.ntiles = p.ntiles; tp.taps = w.taps; tp.kchunks = w.Cin / BK;
+  tp.kchunks2 = p.w2 ? p.w2->Cin / BK : 0;
   tp.dil = w.dil; tp.center = w.center; tp.N = w.N; tp.e = p.e;
   if (!tp.e.bias) tp.e.bias = w.bias;
-  const int total = tp.ntiles * tp.NT;
-  const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_tc_kernel<<<grid, 256, SMEM_BYTES, ctx.stream>>>(ta_hi, ta_lo, w.tm_hi, w.tm_lo, tp);
-  SSB_CUDA(cudaGetLastError());
-  ++g_launches;
-  return 0;
+  // small problems: 64-wide N tiles keep more SMs busy and shorten each tile's dependent chain
+  const bool small = (int64_t)p.ntiles * (w.N / 128) < (int64_t)num_sms * 2;
+  if (small) {
+    tp.NT = w.N / 64;
+    return launch<64>(ctx, p, tp, num_sms);
+  }
+  tp.NT = w.N / 128;
+  return launch<128>(ctx, p, tp, num_sms);
 }
 
 int split_planes(Ctx& ctx, const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {

@@ -7,8 +7,11 @@
 //
 // Layout: A = activation planes [rows, C] fp16 row-major (guard-banded rows, see common.cuh), loaded by
 // TMA as [128 rows x 64 ch] boxes with 128B swizzle at row offset (tap - center) * dilation;
-// B = weights [taps*N, Cin] fp16 (K-major), boxes [128 n x 64 ch].  D = 128 x 128 fp32 in TMEM,
+// B = weights [taps*N, Cin] fp16 (K-major), boxes [BN n x 64 ch].  D = 128 x BN fp32 in TMEM,
 // double buffered so the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs).
+// An optional SECOND operand pair (A2, W2: 1 tap, no shift) extends the K loop: the DiffNet layer
+// GEMM contracts [3 taps x C of y | 256 of cond] in one accumulator, so the conditioner projection
+// needs neither a hoisted [rows, L*2C] fp32 buffer nor an epilogue read.
 #pragma once
 #include <cuda.h>
 
@@ -20,7 +23,7 @@ namespace ssb {
 struct ConvTC {            // packed weights for the tensor-core path
   __half* W_hi = nullptr;  // [taps][N][Cin]
   __half* W_lo = nullptr;
-  CUtensorMap tm_hi, tm_lo;
+  CUtensorMap tm_hi[2], tm_lo[2];  // [0]: box 128 rows (BN=128), [1]: box 64 rows (BN=64)
   int taps = 1, Cin = 0, N = 0, dil = 1, center = 0;
   const float* bias = nullptr;  // [N] (packed column order)
   bool ok = false;
@@ -29,8 +32,6 @@ struct ConvTC {            // packed weights for the tensor-core path
 struct EpiTC {
   int mode = EPI_GENERIC;        // EPI_GENERIC: out = acc + bias ; EPI_GATE ; EPI_RES_SKIP
   const float* bias = nullptr;
-  const float* add = nullptr;    // GATE: [rows, ld_add] fp32 added before the gate (hoisted conditioner projection)
-  int ld_add = 0;
   float* out = nullptr;          // GENERIC / RES_SKIP residual path: fp32 [rows, ldo]
   int ldo = 0;
   __half* oh = nullptr;          // GATE: z planes [rows, C];  RES_SKIP: y = x_new + vec2 planes [rows, C] (may be null)
@@ -51,6 +52,9 @@ struct GemmTC {
   const __half* A_lo = nullptr;
   int64_t rows_total = 0;
   const ConvTC* w = nullptr;
+  const __half* A2_hi = nullptr; // optional second operand [rows_total, w2->Cin], contracted with w2 (1 tap)
+  const __half* A2_lo = nullptr;
+  const ConvTC* w2 = nullptr;
   const int2* tiles = nullptr;
   int ntiles = 0;
   EpiTC e;

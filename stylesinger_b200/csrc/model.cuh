@@ -64,6 +64,8 @@ struct DenoiserLayer {
   Conv outp;   // 1x1, N = 2C ([res | skip])
   Conv dproj;  // diffusion_projection C -> C (used only to build the step-bias table)
   ConvTC dil_tc, outp_tc;  // tensor-core packing of dil / outp (ok == false when not eligible)
+  ConvTC cond_tc;          // conditioner_projection (256 -> 2C, gate-interleaved) as the 2nd K segment of dil_tc
+  float* bias_gate_tc = nullptr;  // dil bias + conditioner bias (packed column order)
 };
 struct Denoiser {
   int C = 0, L = 0, in_dims = 0, out_dims = 0, cycle = 4;

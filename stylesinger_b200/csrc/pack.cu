@@ -230,6 +230,14 @@ static int build_denoiser(TensorMap& tm, DevicePool& pool, const std::string& p,
       for (int c = 0; c < H; ++c) Wc[(size_t)c * L * N2 + pn] = cw->data[(size_t)n * H + c];
       Bc[pn] = cb->data[n];
     }
+    {  // tensor-core path: conditioner projection folded into the layer GEMM as a second K segment
+      const HostTensor* db = tm.get(q + "dilated_conv.bias");
+      if (!db) return -1;
+      std::vector<float> bs((size_t)N2);
+      for (int n = 0; n < N2; ++n) bs[perm_col(n, N2, PACK_GATE_SIG_TANH)] = db->data[n] + cb->data[n];
+      d->layers[i].bias_gate_tc = pool.upload(bs);
+      if (pack_conv_tc(pool, cw, 1, PACK_GATE_SIG_TANH, d->layers[i].bias_gate_tc, &d->layers[i].cond_tc)) return -1;
+    }
   }
   d->cond_all.W = pool.upload(Wc);
   d->cond_all.bias = pool.upload(Bc);

@@ -299,7 +299,8 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
       {
         GemmTC g;
         g.A_hi = b.yh; g.A_lo = b.yl; g.rows_total = s.rows; g.w = &d.layers[l].dil_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
-        g.e.mode = EPI_GATE; g.e.add = b.condall + (size_t)l * 2 * C; g.e.ld_add = L * 2 * C;
+        g.A2_hi = b.ch; g.A2_lo = b.cl; g.w2 = &d.layers[l].cond_tc;  // K = 3*C (taps of y) + 256 (cond)
+        g.e.mode = EPI_GATE; g.e.bias = d.layers[l].bias_gate_tc;
         g.e.oh = b.zh; g.e.ol = b.zl; g.e.ldh = C;
         RUN(conv_gemm_tc(c, g));
       }
@@ -350,34 +351,40 @@ static __half* alloc_half_rows(Ctx& c, const SeqDev& s, int C) {
 bool denoiser_tc_ok(const Model& m, const Denoiser& d) {
   if (!m.use_tc) return false;
   for (auto& l : d.layers)
-    if (!l.dil_tc.ok || !l.outp_tc.ok) return false;
+    if (!l.dil_tc.ok || !l.outp_tc.ok || !l.cond_tc.ok) return false;
   return true;
 }
 int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b) {
   b->tc = tc;
   b->x = alloc_rows(c, s, d.C);
   b->y = b->zg = nullptr;
-  b->yh = b->yl = b->zh = b->zl = nullptr;
+  b->yh = b->yl = b->zh = b->zl = b->ch = b->cl = nullptr;
+  b->condall = nullptr;
   if (tc) {
     b->yh = alloc_half_rows(c, s, d.C);
     b->yl = alloc_half_rows(c, s, d.C);
     b->zh = alloc_half_rows(c, s, d.C);
     b->zl = alloc_half_rows(c, s, d.C);
+    b->ch = alloc_half_rows(c, s, 256);
+    b->cl = alloc_half_rows(c, s, 256);
   } else {
     b->y = alloc_rows(c, s, d.C);
     b->zg = alloc_rows(c, s, d.C);
+    b->condall = alloc_rows(c, s, d.L * 2 * d.C, false);
   }
   b->skip = alloc_rows(c, s, d.C);
   b->sbuf = alloc_rows(c, s, d.C);
   b->ld_head = (d.out_dims + 3) & ~3;
   b->head = alloc_rows(c, s, b->ld_head);
-  b->condall = alloc_rows(c, s, d.L * 2 * d.C, false);
   WS_OK(c);
   return 0;
 }
-int hoist_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, float* condall) {
+// Conditioner: tensor-core path -> fp16 hi/lo planes of cond (contracted inside every layer GEMM);
+// SIMT path -> the step-invariant projection of all L layers hoisted into one [rows, L*2C] buffer.
+int prepare_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, DenoiserBufs& b) {
+  if (b.tc) return split_planes(c, cond_g, 256, s.rows, 256, 1.0f, b.ch, b.cl);
   ConvGemm g = make_gemm(d.cond_all, s, cond_g, 256);
-  g.e.out = condall; g.e.ldo = d.L * 2 * d.C;
+  g.e.out = b.condall; g.e.ldo = d.L * 2 * d.C;
   return conv_gemm(c, g);
 }
 
@@ -402,7 +409,7 @@ int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond
   RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
   float* xm = alloc_rows(c, s, 80);
   WS_OK(c);
-  RUN(hoist_cond(c, d, s, cond_g, b.condall));
+  RUN(prepare_cond(c, d, s, cond_g, b));
   const int T = d.T;
   const size_t per = (size_t)s.total * 80;
   const float sa = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 5], s1a = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 6];
@@ -425,7 +432,7 @@ int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const f
   const size_t mk = c.mark();
   DenoiserBufs b;
   RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
-  RUN(hoist_cond(c, d, s, cond_g, b.condall));
+  RUN(prepare_cond(c, d, s, cond_g, b));
   const int T = d.T;
   const size_t per = (size_t)s.total;
   const uint64_t sbase = 2000 + (uint64_t)which * 100000;

@@ -13,12 +13,13 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
 struct DenoiserBufs {
   float *x, *y, *zg, *skip, *sbuf, *head, *condall;
   __half *yh, *yl, *zh, *zl;  // tensor-core path: fp16 hi/lo planes of y = x + step bias and of the gate output
+  __half *ch, *cl;            // tensor-core path: fp16 hi/lo planes of the conditioner [rows,256]
   int ld_head;
   bool tc;
 };
 bool denoiser_tc_ok(const Model& m, const Denoiser& d);
 int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b);
-int hoist_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, float* condall);
+int prepare_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, DenoiserBufs& b);
 int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const float* x80, DenoiserBufs& b);
 int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBufs& b);
 int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
