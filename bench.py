@@ -74,19 +74,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def lpt_assign(lengths, world):
-    """Longest-processing-time-first assignment of utterances to ranks."""
-    order = np.argsort(-np.asarray(lengths))
-    loads, bins = [0.0] * world, [[] for _ in range(world)]
-    for i in order:
-        r = int(np.argmin(loads))
-        bins[r].append(int(i))
-        loads[r] += float(lengths[i])
-    return bins
-
-
 def make_workload(name, rank, world):
     from stylesinger_b200 import synth
+    from stylesinger_b200.dist import lpt_assign
     if name == "utt10s":
         return [synth.make_utterance(10.0, utt_idx=rank)], "single 10 s utterance per GPU (BASELINE.json configs[1])"
     n_per = {"batch64": 64, "batch8": 8}[name]
@@ -121,10 +111,17 @@ def cpu_reference_pass(seconds, T, threads):
     return int(u["mel2ph"].shape[0]), time.perf_counter() - t0
 
 
+def cpu_threads():
+    """Threads for the CPU arm.  The reference's PyTorch CPU path gets SLOWER beyond ~16 threads on the GPU
+    box's 128 logical cores (probe, 94 frames x 20 steps: 8 thr 0.74 s, 16 thr 0.70 s, 32 thr 1.50 s, 64 thr 3.59 s;
+    128 thr did not finish in 15 min), so "all the threads it can use" is capped where it is fastest."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     sample_s = args.cpu_sample_seconds
     cpu_reference_pass(0.3, 2, threads)  # warm-up (thread pools, allocator)
     for _ in range(max(args.warmup - 1, 0)):
@@ -140,7 +137,7 @@ def run_reference(args, rank, world):
             "data": "synthetic", "impl": "reference",
             "config": {"workload": f"CPU oracle port of the reference (reference is Python, cannot travel): one "
                                    f"{sample_s:g} s utterance, T={args.T} (mel + 2 F0 loops) + HiFi-GAN-NSF, per step"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "host_logical_cores": os.cpu_count(), "kind": "port",
                              "sample": f"{sample_s:g} s utterance ({frames} frames), full ph->wav, T={args.T}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -229,10 +226,10 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = cpu_threads()
             cpu_reference_pass(0.3, 2, threads)
             f, dt = cpu_reference_pass(args.cpu_sample_seconds, T, threads)
-            cpu = {"value": f / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            cpu = {"value": f / dt, "unit": UNIT, "cores": threads, "host_logical_cores": os.cpu_count(), "kind": "port",
                    "sample": f"{args.cpu_sample_seconds:g} s utterance ({f} frames), full ph->wav, T={T}, 1 pass ({dt:.1f} s)"}
         val = total_frames / (ms / 1000.0)
         audio_s = total_frames * 256 / 48000.0

@@ -1,0 +1,73 @@
+"""N>1 host logic on CPU (gloo, world_size 2): LPT sharding + scatter of the ragged inputs + gather of the outputs."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from stylesinger_b200 import synth
+    from stylesinger_b200.dist import gather_waveforms, scatter_utterances
+    n = 5
+    utts = [synth.make_utterance(0.3 + 0.2 * i, utt_idx=i, ref_frames=20 + i) for i in range(n)] if rank == 0 else None
+    pb, idx = scatter_utterances(utts, src=0)
+    # every rank checks its shard against a local regeneration of the same utterances
+    for j, i in enumerate(idx):
+        u = synth.make_utterance(0.3 + 0.2 * i, utt_idx=i, ref_frames=20 + i)
+        a, b = pb.ph_offsets[j], pb.ph_offsets[j + 1]
+        assert torch.equal(pb.t["txt_tokens"][a:b].long(), u["txt_tokens"])
+        fa, fb = pb.frame_offsets[j], pb.frame_offsets[j + 1]
+        assert torch.equal(pb.t["mel2ph"][fa:fb].long(), u["mel2ph"])
+        ra, rb = pb.ref_offsets[j], pb.ref_offsets[j + 1]
+        assert torch.equal(pb.t["ref_mels"][ra:rb], u["ref_mels"])
+        assert torch.equal(pb.t["spk_embed"][j], u["spk_embed"])
+    # fake "waveforms": utterance index encoded in the samples
+    wavs = [np.full(int(pb.frame_offsets[j + 1] - pb.frame_offsets[j]) * 4, float(i), np.float32) for j, i in enumerate(idx)]
+    out = gather_waveforms(wavs, idx, n, dst=0)
+    if rank == 0:
+        ok = all(o is not None and np.all(o == float(i)) for i, o in enumerate(out))
+        lens = [len(o) for o in out]
+        q.put((ok, lens, sorted(idx)))
+    else:
+        q.put((True, None, sorted(idx)))
+    dist.destroy_process_group()
+
+
+def test_scatter_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[0] for r in res)
+    all_idx = sorted(sum((r[2] for r in res), []))
+    assert all_idx == [0, 1, 2, 3, 4]  # every utterance owned exactly once
+
+
+def test_lpt_balances_frames():
+    from stylesinger_b200 import synth
+    from stylesinger_b200.dist import lpt_assign
+    secs = synth.batch_seconds(512, seed=1234)
+    bins = lpt_assign(secs, 8)
+    loads = [sum(secs[i] for i in b) for b in bins]
+    assert sorted(sum(bins, [])) == list(range(512))
+    assert max(loads) / min(loads) < 1.01
