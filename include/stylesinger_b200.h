@@ -186,6 +186,10 @@ int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* 
  * (3 MMAs per product, fp32 accumulate; default when available), 0 = fp32 FFMA.  Returns the mode in effect. */
 int ssb_model_set_tensor_cores(ssb_model_t* m, int32_t enable);
 
+/* 1 (default): small batches run the whole T-step mel sampler in ONE persistent cooperative kernel launch
+ * (csrc/sampler_tc.cu); 0: one launch per GEMM (BASELINE.json configs[4] compares the two). */
+int ssb_model_set_persistent(ssb_model_t* m, int32_t enable);
+
 /* Unit-test granularity: ssb_op_conv1d through the tcgen05 path (Cin % 64 == 0, N % 128 == 0, no activation). */
 int ssb_op_conv1d_tc(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
                      const float* b_host, int32_t N, int32_t k, int32_t dilation, float* out, void* stream);

@@ -92,6 +92,7 @@ struct SeqDev {
   int64_t total = 0;            // tight rows
   int maxlen = 0;
   int rate = 1;
+  const int* tile_tight = nullptr;  // per tile: tight (packed) index of its first row
 };
 
 // ---------------------------------------------------------------------------------------------

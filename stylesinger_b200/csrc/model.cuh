@@ -82,6 +82,11 @@ struct Denoiser {
   float* gtab = nullptr;        // [T][8]
   float* mtab = nullptr;        // [T][8] (ddiff only)
   std::vector<float> gtab_h;
+  // persistent-sampler extras (mel net): every GEMM of a diffusion step on the tcgen05 path
+  ConvTC in_tc;    // input_projection, K padded 80 -> 128
+  ConvTC skip_tc;  // skip_projection with the 1/sqrt(L) skip scale folded into the weights
+  ConvTC out_tc;   // output_projection, N padded 80 -> 128
+  float* out_bias_pad = nullptr;
 };
 
 struct AlignLayer {
@@ -113,6 +118,7 @@ struct Model {
   Denoiser melnet;
   Conv mel_out, ln_proj;
   float log_eps = 0.f;
+  bool persistent = true;  // single-launch persistent sampler for small batches (ssb_model_set_persistent)
   bool use_tc = true;  // tcgen05 path for the denoiser layer GEMMs (ssb_model_set_tensor_cores)
 };
 

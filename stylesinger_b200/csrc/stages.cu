@@ -1,4 +1,7 @@
 // Stage drivers: compose the kernels into the reference's modules (one function per SURVEY.md §8a group).
+#include <string.h>
+
+#include "sampler_tc.cuh"
 #include "stages.cuh"
 
 namespace ssb {
@@ -15,12 +18,15 @@ int upload_layout(Ctx& c, const Seq& s, int rate, SeqDev* out) {
   const int nt = s.ntiles(rate);
   int2* tiles = c.alloc<int2>((size_t)nt + 1);
   int4* utt = c.alloc<int4>((size_t)s.B + 1);
+  int* ttight = c.alloc<int>((size_t)nt + 1);
+  out->tile_tight = ttight;
   out->tiles = tiles; out->ntiles = nt; out->utt = utt; out->B = s.B; out->rows = s.rows(rate);
   out->total = s.total * rate; out->maxlen = s.maxlen * rate; out->rate = rate;
   if (c.dry) return 0;
   SSB_CHECK(!c.failed && tiles && utt, "workspace too small (layout tables)");
   std::vector<int2> ht((size_t)nt + 1);
   std::vector<int4> hu((size_t)s.B + 1);
+  std::vector<int> htt((size_t)nt + 1);
   int k = 0;
   int64_t tight = 0;
   for (int b = 0; b < s.B; ++b) {
@@ -28,8 +34,12 @@ int upload_layout(Ctx& c, const Seq& s, int rate, SeqDev* out) {
     const int rs = s.rs[b] * rate;
     hu[b] = make_int4(rs, len, (int)tight, 0);
     tight += len;
-    for (int t0 = 0; t0 < len; t0 += TILE_M) ht[k++] = make_int2(rs + t0, (len - t0) < TILE_M ? (len - t0) : TILE_M);
+    for (int t0 = 0; t0 < len; t0 += TILE_M) {
+      htt[k] = (int)(tight - len) + t0;
+      ht[k++] = make_int2(rs + t0, (len - t0) < TILE_M ? (len - t0) : TILE_M);
+    }
   }
+  SSB_CUDA(cudaMemcpyAsync(ttight, htt.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, c.stream));
   SSB_CUDA(cudaMemcpyAsync(tiles, ht.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice, c.stream));
   SSB_CUDA(cudaMemcpyAsync(utt, hu.data(), sizeof(int4) * s.B, cudaMemcpyHostToDevice, c.stream));
   // pageable-source async copies are staged before returning, so the host vectors may die here
@@ -46,6 +56,8 @@ static int32_t* alloc_rows_i32(Ctx& c, const SeqDev& s, int C = 1) {
   if (!c.dry && p && !c.failed) cudaMemsetAsync(p, 0, (size_t)s.rows * C * sizeof(int32_t), c.stream);
   return p;
 }
+
+static __half* alloc_half_rows(Ctx& c, const SeqDev& s, int C);
 
 #define RUN(x)                 \
   do {                         \
@@ -399,11 +411,106 @@ int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const f
   return denoiser_stack(c, d, s, t, b);
 }
 
+// a18+a19, single launch: all T reverse steps in the persistent tcgen05 kernel (sampler_tc.cu).
+static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
+                                        const float* noise, uint64_t seed, float* mel_tight) {
+  const Denoiser& d = m.melnet;
+  const int C = d.C, L = d.L, T = d.T;
+  const size_t mk = c.mark();
+  float* xm = alloc_rows(c, s, 80);
+  float* x = alloc_rows(c, s, C);
+  float* skip = alloc_rows(c, s, C);
+  __half* pl[12];
+  const int pcols[6] = {128, C, C, 256, C, C};  // x80, y, z, cond, skip, s
+  for (int i = 0; i < 6; ++i) {
+    pl[2 * i] = alloc_half_rows(c, s, pcols[i]);
+    pl[2 * i + 1] = alloc_half_rows(c, s, pcols[i]);
+  }
+  const int nmaps = 12 + 2 + 6 * L + 4;
+  const int nph = T * (2 * L + 3);
+  CUtensorMap* maps_dev = c.alloc<CUtensorMap>((size_t)nmaps);
+  SPhase* ph_dev = c.alloc<SPhase>((size_t)nph);
+  unsigned* ctr = c.alloc<unsigned>(4);
+  WS_OK(c);
+  const size_t per = (size_t)s.total * 80;
+  const float sa = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 5], s1a = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 6];
+  RUN(mel_q_sample(c, s, coarse_g, 80, noise, m.spec_min, m.spec_max, sa, s1a, xm, 80, seed, 1000));
+  RUN(x80_planes(c, xm, s.rows, pl[0], pl[1]));
+  RUN(split_planes(c, cond_g, 256, s.rows, 256, 1.0f, pl[6], pl[7]));
+  if (!c.dry) {
+    std::vector<CUtensorMap> maps((size_t)nmaps);
+    for (int i = 0; i < 6; ++i) {
+      if (make_act_map(&maps[2 * i], pl[2 * i], s.rows, pcols[i])) return -1;
+      if (make_act_map(&maps[2 * i + 1], pl[2 * i + 1], s.rows, pcols[i])) return -1;
+    }
+    auto put = [&](int idx, const ConvTC& w) { maps[idx] = w.tm_hi[1]; maps[idx + 1] = w.tm_lo[1]; };
+    const int W_IN = 12, W_L0 = 14, W_SKIP = 14 + 6 * L, W_OUT = W_SKIP + 2;
+    put(W_IN, d.in_tc);
+    for (int l = 0; l < L; ++l) {
+      put(W_L0 + 6 * l, d.layers[l].dil_tc);
+      put(W_L0 + 6 * l + 2, d.layers[l].cond_tc);
+      put(W_L0 + 6 * l + 4, d.layers[l].outp_tc);
+    }
+    put(W_SKIP, d.skip_tc);
+    put(W_OUT, d.out_tc);
+    std::vector<SPhase> ph((size_t)nph);
+    size_t k = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      const float* dt = d.dtab + (size_t)t * L * C;
+      SPhase z;
+      memset(&z, 0, sizeof(z));
+      z.a2 = -1; z.taps = 1; z.dil = 1; z.beta = 1.0f;
+      {  // input_projection + ReLU ; y = x + step bias of layer 0
+        SPhase q = z;
+        q.a1 = 0; q.w1 = W_IN; q.kchunks = 2; q.N = C; q.NT = C / 64; q.mode = SP_INPROJ; q.bias = d.in_proj.bias;
+        q.out = x; q.ldo = C; q.oh = pl[2]; q.ol = pl[3]; q.ldh = C; q.vec2 = dt;
+        ph[k++] = q;
+      }
+      for (int l = 0; l < L; ++l) {
+        SPhase a = z;  // dilated conv (3 taps of y) + conditioner (cond) -> gate -> z planes
+        a.a1 = 2; a.a2 = 6; a.w1 = W_L0 + 6 * l; a.w2 = W_L0 + 6 * l + 2; a.taps = 3; a.kchunks = C / 64; a.kchunks2 = 4;
+        a.dil = d.layers[l].dil_tc.dil; a.center = 1; a.N = 2 * C; a.NT = 2 * C / 64; a.mode = SP_GATE;
+        a.bias = d.layers[l].bias_gate_tc; a.oh = pl[4]; a.ol = pl[5]; a.ldh = C;
+        ph[k++] = a;
+        SPhase b = z;  // 1x1 output projection -> residual stream, next layer's input planes, skip sum
+        b.a1 = 4; b.w1 = W_L0 + 6 * l + 4; b.kchunks = C / 64; b.N = 2 * C; b.NT = 2 * C / 64; b.mode = SP_RES_SKIP;
+        b.bias = d.layers[l].outp.bias; b.res = x; b.ld_res = C; b.out = x; b.ldo = C; b.beta = 0.70710678118654752440f;
+        if (l + 1 < L) { b.oh = pl[2]; b.ol = pl[3]; b.ldh = C; b.vec2 = dt + (size_t)(l + 1) * C; }
+        b.skip = skip; b.ld_skip = C; b.C = C; b.skip_init = (l == 0);
+        if (l == L - 1) { b.sh = pl[8]; b.sl = pl[9]; }
+        ph[k++] = b;
+      }
+      {  // skip_projection (1/sqrt(L) folded into the weights) + ReLU -> s planes
+        SPhase q = z;
+        q.a1 = 8; q.w1 = W_SKIP; q.kchunks = C / 64; q.N = C; q.NT = C / 64; q.mode = SP_SKIPPROJ; q.bias = d.skip_proj.bias;
+        q.oh = pl[10]; q.ol = pl[11]; q.ldh = C;
+        ph[k++] = q;
+      }
+      {  // output_projection -> eps ; fused DDPM posterior step on x_t
+        SPhase q = z;
+        q.a1 = 10; q.w1 = W_OUT; q.kchunks = C / 64; q.N = 128; q.NT = 2; q.mode = SP_MEL_SAMPLE; q.bias = d.out_bias_pad;
+        q.out = xm; q.ldo = 80; q.oh = pl[0]; q.ol = pl[1]; q.ldh = 128; q.tab = d.gtab + (size_t)t * 8;
+        q.noise = noise ? noise + per * (size_t)(T - t) : nullptr; q.seed = seed; q.stream_id = 1001 + (uint64_t)t; q.n_valid = 80;
+        ph[k++] = q;
+      }
+    }
+    SSB_CUDA(cudaMemcpyAsync(maps_dev, maps.data(), sizeof(CUtensorMap) * nmaps, cudaMemcpyHostToDevice, c.stream));
+    SSB_CUDA(cudaMemcpyAsync(ph_dev, ph.data(), sizeof(SPhase) * nph, cudaMemcpyHostToDevice, c.stream));
+    RUN(launch_sampler_tc(c, maps_dev, ph_dev, nph, s.tiles, s.tile_tight, s.ntiles, 2 * C / 64, ctr));
+  }
+  RUN(mel_denorm(c, s, xm, 80, m.spec_min, m.spec_max, nullptr, mel_tight, 80));
+  c.release(mk);
+  return 0;
+}
+
 // a18+a19: DiffusionDecoder.forward(infer=True) (shallow_diffusion_tts.py:284-307)
 int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
                       const float* noise /*tight [(T+1), total, 80] or null*/, uint64_t seed, float* mel_tight) {
   const Denoiser& d = m.melnet;
   SSB_CHECK(d.T > 0, "mel schedule not set: call ssb_model_set_schedule(which=0)");
+  if (m.persistent && denoiser_tc_ok(m, d) && d.in_tc.ok && d.skip_tc.ok && d.out_tc.ok && s.ntiles <= 48 &&
+      sampler_tc_max_ctas() > 0)
+    return run_mel_diffusion_persistent(c, m, s, cond_g, coarse_g, noise, seed, mel_tight);
   const size_t mk = c.mark();
   DenoiserBufs b;
   RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));

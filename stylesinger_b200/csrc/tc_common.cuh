@@ -1,0 +1,94 @@
+// Shared device-side helpers of the tcgen05 kernels: mbarrier / TMA / tcgen05 PTX wrappers, the UMMA
+// shared-memory descriptor for K-major 128B-swizzled tiles, TMEM loads and the fp16 hi/lo plane split.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace ssb {
+namespace tc {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s watchdog: fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// K-major, 128B-swizzled tile (rows of 128 bytes, 8-row atoms of 1024 bytes): shared-memory matrix descriptor
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address
+  d |= (uint64_t)(1024u >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* z) {
+  // 16 consecutive values -> two 16-byte stores per plane
+  __align__(16) __half h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    h[j] = __float2half_rn(z[j]);
+    l[j] = __float2half_rn(z[j] - __half2float(h[j]));
+  }
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(&h[0]);
+  *reinterpret_cast<uint4*>(hi + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+  *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(&l[0]);
+  *reinterpret_cast<uint4*>(lo + 8) = *reinterpret_cast<const uint4*>(&l[8]);
+}
+
+
+}  // namespace tc
+}  // namespace ssb

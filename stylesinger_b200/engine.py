@@ -161,6 +161,10 @@ class AcousticModel:
         """tcgen05 (fp16 hi/lo split, 3 MMAs) vs fp32 FFMA for the denoiser layer GEMMs. Returns the mode in effect."""
         return bool(lib.ssb_model_set_tensor_cores(self._h, 1 if enable else 0))
 
+    def set_persistent(self, enable=True):
+        """Single-launch persistent sampler kernel for small batches (True) vs one launch per GEMM (False)."""
+        return bool(lib.ssb_model_set_persistent(self._h, 1 if enable else 0))
+
     # -- schedules -------------------------------------------------------------------------------
     def set_timesteps(self, T=None, f0_T=None):
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -30,9 +30,9 @@ def timed(fn, n=2):
     return a.elapsed_time(b) / n, (time.perf_counter() - t0) * 1000 / n, (lib.ssb_launch_count() - l0) // n, r
 
 res = {}
-for tc in (True, False):
-    m.set_tensor_cores(tc)
-    tag = "tc" if tc else "simt"
+for tag in ("persist", "tc", "simt"):
+    m.set_tensor_cores(tag != "simt")
+    m.set_persistent(tag == "persist")
     ms, wall, nl, out = timed(lambda: m.forward(pb, seed=1, skip_mel_diffusion=True, want=("coarse_mel", "diff_cond", "f0_denorm")))
     res[f"{tag}.acoustic_wo_mel(enc+style+2xF0+dec)"] = (round(ms, 2), round(wall, 2), nl)
     cond, coarse = out["diff_cond"], out["coarse_mel"]
@@ -41,7 +41,7 @@ for tc in (True, False):
     lo = torch.full((F_,), -1.0, device=dev); hi = torch.full((F_,), 1.0, device=dev)
     ms, wall, nl, _ = timed(lambda: m.f0_diffusion(0, cond, lo, hi, pb.frame_offsets, seed=3))
     res[f"{tag}.one_f0_diffusion"] = (round(ms, 2), round(wall, 2), nl)
-m.set_tensor_cores(True)
+m.set_tensor_cores(True); m.set_persistent(True)
 melc = mel.clamp(-6, 1.5).contiguous(); f0 = out["f0_denorm"]
 ms, wall, nl, _ = timed(lambda: v.generate(melc, f0, pb.frame_offsets, seed=4))
 res["vocoder"] = (round(ms, 2), round(wall, 2), nl)
