@@ -317,7 +317,7 @@ int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
 }  // namespace
 
 bool tc_available() { return get_encode() != nullptr; }
-int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols) { return make_map(m, ptr, (uint64_t)rows, (uint64_t)cols, BM); }
+int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols, int box_rows) { return make_map(m, ptr, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows); }
 
 int make_weight_maps(ConvTC* w) {
   SSB_CHECK(w->Cin % BK == 0 && w->N % 128 == 0, "tensor-core path needs Cin % 64 == 0 and N % 128 == 0");

@@ -63,7 +63,7 @@ struct GemmTC {
 bool tc_available();  // driver entry point for cuTensorMapEncodeTiled resolved
 int make_weight_maps(ConvTC* w);
 // TMA descriptor of an activation plane [rows, cols] fp16 (box 128 rows x 64 cols, 128B swizzle)
-int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols);
+int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols, int box_rows = 128);
 int conv_gemm_tc(Ctx& ctx, const GemmTC& p);
 // x fp32 [rows, ld] -> hi/lo planes [rows, C] (all rows incl. guards; guards stay zero)
 int split_planes(Ctx& ctx, const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo);

@@ -85,7 +85,7 @@ struct Denoiser {
   // persistent-sampler extras (mel net): every GEMM of a diffusion step on the tcgen05 path
   ConvTC in_tc;    // input_projection, K padded 80 -> 128
   ConvTC skip_tc;  // skip_projection with the 1/sqrt(L) skip scale folded into the weights
-  ConvTC out_tc;   // output_projection, N padded 80 -> 128
+  ConvTC out_tc;   // output_projection, N padded 80 -> 256 (4 N-tiles of 64: one cluster)
   float* out_bias_pad = nullptr;
 };
 

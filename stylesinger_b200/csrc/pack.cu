@@ -251,7 +251,7 @@ static int build_denoiser(TensorMap& tm, DevicePool& pool, const std::string& p,
     const HostTensor* ow = tm.get(p + "output_projection.weight");
     const HostTensor* ob = tm.get(p + "output_projection.bias");
     if (!iw || !sw || !ow || !ob) return -1;
-    std::vector<float> wi((size_t)C * 128, 0.f), ws((size_t)C * C), wo((size_t)128 * C, 0.f), bo(128, 0.f);
+    std::vector<float> wi((size_t)C * 128, 0.f), ws((size_t)C * C), wo((size_t)256 * C, 0.f), bo(256, 0.f);  // N padded to 4 x 64
     for (int n = 0; n < C; ++n)
       for (int c = 0; c < in_dims; ++c) wi[(size_t)n * 128 + c] = iw->data[(size_t)n * in_dims + c];
     const float sc = 1.0f / sqrtf((float)L);
@@ -264,7 +264,7 @@ static int build_denoiser(TensorMap& tm, DevicePool& pool, const std::string& p,
     HostTensor ti, ts, to;
     ti.data = wi.data(); ti.shape = {C, 128, 1};
     ts.data = ws.data(); ts.shape = {C, C, 1};
-    to.data = wo.data(); to.shape = {128, C, 1};
+    to.data = wo.data(); to.shape = {256, C, 1};
     if (pack_conv_tc(pool, &ti, 1, PACK_PLAIN, d->in_proj.bias, &d->in_tc)) return -1;
     if (pack_conv_tc(pool, &ts, 1, PACK_PLAIN, d->skip_proj.bias, &d->skip_tc)) return -1;
     if (pack_conv_tc(pool, &to, 1, PACK_PLAIN, d->out_bias_pad, &d->out_tc)) return -1;

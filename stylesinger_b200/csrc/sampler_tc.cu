@@ -12,6 +12,7 @@
 // the previous one through +-dilation halos).  Tensor maps (activations + every layer's weights) live in a
 // device array; mbarrier phases, the smem ring and the TMEM allocation persist across all 43*T phases.
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include "philox.cuh"
 #include "sampler_tc.cuh"
@@ -32,6 +33,22 @@ constexpr int SMEM = STAGES * STAGE + 1024 + 512 + 1024;
 constexpr uint32_t TMEM_COLS = 2 * BN;
 
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t ncluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose box is written into the same smem offset of every CTA in `mask` (and signals each one's mbarrier)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& gen, unsigned nblocks) {
   __threadfence();
@@ -176,7 +193,12 @@ __device__ __forceinline__ void epilogue32(const SPhase& e, int64_t r, int64_t t
 
 __global__ void __launch_bounds__(256, 1)
 sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict__ phases, int nphases,
-                  const int2* __restrict__ tiles, const int* __restrict__ tile_tight, int ntiles, unsigned* barrier_ctr) {
+                  const int2* __restrict__ tiles, const int* __restrict__ tile_tight, int ntiles, unsigned* barrier_ctr,
+                  int cs) {
+  // cs = cluster size along N: the cs CTAs of a cluster work on the same M-tile (consecutive N-tiles); each loads
+  // 1/cs of the A tile and TMA-multicasts it to all of them, so the activation planes cross L2->SM once per
+  // cluster instead of once per CTA.  Stage recycling therefore needs every CTA of the cluster to have consumed
+  // the stage: the MMA commit is multicast to all cs empty barriers (count cs).
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
@@ -189,7 +211,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, (uint32_t)cs);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -205,6 +227,13 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const int cr = cs > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = cs > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int ncl = cs > 1 ? (int)ncluster_id_x() : (int)gridDim.x;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const int slice_rows = BM / cs;
+  const uint32_t slice_bytes = (uint32_t)(slice_rows * BK * 2);
+  if (cs > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast
 
   // pipeline state, persistent across phases (each role keeps its own copy)
   int stage = 0;
@@ -222,7 +251,8 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
     }
     __syncthreads();
     const SPhase& P = *sph;
-    const int total = ntiles * P.NT;
+    const int gpm = P.NT / cs;           // tile groups (clusters' worth of N-tiles) per M-tile
+    const int groups = ntiles * gpm;
     const int nk1 = P.taps * P.kchunks;
     const int nk = nk1 + P.kchunks2;
 
@@ -233,8 +263,8 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
         const CUtensorMap* mW = maps + P.w1;
         const CUtensorMap* mA2 = maps + (P.a2 >= 0 ? P.a2 : P.a1);
         const CUtensorMap* mW2 = maps + (P.a2 >= 0 ? P.w2 : P.w1);
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-          const int mt = tile / P.NT, nt = tile - mt * P.NT;
+        for (int g = cid; g < groups; g += ncl) {
+          const int mt = g / gpm, nt = (g - mt * gpm) * cs + cr;
           const int row0 = tiles[mt].x;
           for (int kb = 0; kb < nk; ++kb) {
             mbar_wait(empty0 + 8 * stage, phase_bit ^ 1);
@@ -246,14 +276,24 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
               const int c0 = (kb - tap * P.kchunks) * BK;
               const int arow = row0 + (tap - P.center) * P.dil;
               const int brow = tap * P.N + nt * BN;
-              tma_load_2d(sa, mA, fb, c0, arow);
-              tma_load_2d(sa + A_TILE, mA + 1, fb, c0, arow);
+              if (cs > 1) {
+                tma_load_2d_mc(sa + cr * slice_bytes, mA, fb, c0, arow + cr * slice_rows, cmask);
+                tma_load_2d_mc(sa + A_TILE + cr * slice_bytes, mA + 1, fb, c0, arow + cr * slice_rows, cmask);
+              } else {
+                tma_load_2d(sa, mA, fb, c0, arow);
+                tma_load_2d(sa + A_TILE, mA + 1, fb, c0, arow);
+              }
               tma_load_2d(sa + 2 * A_TILE, mW, fb, c0, brow);
               tma_load_2d(sa + 2 * A_TILE + B_TILE, mW + 1, fb, c0, brow);
             } else {
               const int c0 = (kb - nk1) * BK;
-              tma_load_2d(sa, mA2, fb, c0, row0);
-              tma_load_2d(sa + A_TILE, mA2 + 1, fb, c0, row0);
+              if (cs > 1) {
+                tma_load_2d_mc(sa + cr * slice_bytes, mA2, fb, c0, row0 + cr * slice_rows, cmask);
+                tma_load_2d_mc(sa + A_TILE + cr * slice_bytes, mA2 + 1, fb, c0, row0 + cr * slice_rows, cmask);
+              } else {
+                tma_load_2d(sa, mA2, fb, c0, row0);
+                tma_load_2d(sa + A_TILE, mA2 + 1, fb, c0, row0);
+              }
               tma_load_2d(sa + 2 * A_TILE, mW2, fb, c0, nt * BN);
               tma_load_2d(sa + 2 * A_TILE + B_TILE, mW2 + 1, fb, c0, nt * BN);
             }
@@ -263,7 +303,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        for (int g = cid; g < groups; g += ncl, ++it) {
           const int a = it & 1;
           const uint32_t aph = (it >> 1) & 1;
           mbar_wait(tempty0 + 8 * a, aph ^ 1);
@@ -282,7 +322,8 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
               tc_mma(d_tmem, dah + off, dbl + off, idesc, 1u);
               tc_mma(d_tmem, dal + off, dbh + off, idesc, 1u);
             }
-            tc_commit(empty0 + 8 * stage);
+            if (cs > 1) tc_commit_mc(empty0 + 8 * stage, cmask);
+            else tc_commit(empty0 + 8 * stage);
             if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
           }
           tc_commit(tfull0 + 8 * a);
@@ -290,10 +331,10 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
       }
     } else if (warp >= 4) {
       const int ew = warp - 4;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      for (int g = cid; g < groups; g += ncl, ++it) {
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1;
-        const int mt = tile / P.NT, nt = tile - mt * P.NT;
+        const int mt = g / gpm, nt = (g - mt * gpm) * cs + cr;
         const int2 t = tiles[mt];
         const int rl = ew * 32 + lane;
         const bool valid = rl < t.y;
@@ -322,6 +363,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // nobody exits while a peer may still multicast into / arrive on its smem
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -350,30 +392,52 @@ int x80_planes(Ctx& ctx, const float* x, int64_t rows, __half* hi, __half* lo) {
   return 0;
 }
 
-int sampler_tc_max_ctas() {
-  static int v = -1;
-  if (v < 0) {
-    int dev = 0, sms = 0, per = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(sampler_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sampler_tc_kernel, 256, SMEM) != cudaSuccess) per = 0;
-    v = sms * (per > 0 ? 1 : 0);
-  }
-  return v;
+static int max_clusters(int cs) {
+  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  if (cs < 1 || cs > 8) return 0;
+  if (cache[cs] >= 0) return cache[cs];
+  cudaFuncSetAttribute(sampler_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(sms / cs * cs));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = SMEM;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, sampler_tc_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[cs] = n;
+  return n;
 }
 
+int sampler_tc_max_ctas() { return max_clusters(1); }
+
 int launch_sampler_tc(Ctx& ctx, const CUtensorMap* maps_dev, const SPhase* phases_dev, int nphases, const int2* tiles,
-                      const int* tile_tight, int ntiles, int max_nt, unsigned* barrier_ctr) {
+                      const int* tile_tight, int ntiles, int max_nt, unsigned* barrier_ctr, int cs) {
   if (ctx.dry) return 0;
-  const int cap = sampler_tc_max_ctas();
+  const int cap = max_clusters(cs);
   SSB_CHECK(cap > 0, "persistent sampler kernel cannot be resident on this device");
-  int grid = ntiles * max_nt;
-  if (grid > cap) grid = cap;
+  int ncl = ntiles * (max_nt / cs);
+  if (ncl > cap) ncl = cap;
   SSB_CUDA(cudaMemsetAsync(barrier_ctr, 0, sizeof(unsigned), ctx.stream));
-  void* args[] = {(void*)&maps_dev, (void*)&phases_dev, (void*)&nphases, (void*)&tiles, (void*)&tile_tight, (void*)&ntiles,
-                  (void*)&barrier_ctr};
-  SSB_CUDA(cudaLaunchCooperativeKernel((const void*)sampler_tc_kernel, dim3(grid), dim3(256), args, (size_t)SMEM, ctx.stream));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(ncl * cs));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = ctx.stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = (unsigned)cs; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  SSB_CUDA(cudaLaunchKernelEx(&cfg, sampler_tc_kernel, maps_dev, phases_dev, nphases, tiles, tile_tight, ntiles, barrier_ctr, cs));
   ++g_launches;
   return 0;
 }

@@ -37,7 +37,7 @@ struct SPhase {
 
 int sampler_tc_max_ctas();
 int launch_sampler_tc(Ctx& ctx, const CUtensorMap* maps_dev, const SPhase* phases_dev, int nphases, const int2* tiles,
-                      const int* tile_tight, int ntiles, int max_nt, unsigned* barrier_ctr);
+                      const int* tile_tight, int ntiles, int max_nt, unsigned* barrier_ctr, int cs);
 int x80_planes(Ctx& ctx, const float* x, int64_t rows, __half* hi, __half* lo);
 
 }  // namespace ssb

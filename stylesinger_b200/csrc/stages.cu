@@ -416,6 +416,7 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
                                         const float* noise, uint64_t seed, float* mel_tight) {
   const Denoiser& d = m.melnet;
   const int C = d.C, L = d.L, T = d.T;
+  const int CS = 4;  // cluster size along N: A tiles are TMA-multicast to the 4 CTAs that share an M-tile
   const size_t mk = c.mark();
   float* xm = alloc_rows(c, s, 80);
   float* x = alloc_rows(c, s, C);
@@ -440,8 +441,8 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
   if (!c.dry) {
     std::vector<CUtensorMap> maps((size_t)nmaps);
     for (int i = 0; i < 6; ++i) {
-      if (make_act_map(&maps[2 * i], pl[2 * i], s.rows, pcols[i])) return -1;
-      if (make_act_map(&maps[2 * i + 1], pl[2 * i + 1], s.rows, pcols[i])) return -1;
+      if (make_act_map(&maps[2 * i], pl[2 * i], s.rows, pcols[i], 128 / CS)) return -1;
+      if (make_act_map(&maps[2 * i + 1], pl[2 * i + 1], s.rows, pcols[i], 128 / CS)) return -1;
     }
     auto put = [&](int idx, const ConvTC& w) { maps[idx] = w.tm_hi[1]; maps[idx + 1] = w.tm_lo[1]; };
     const int W_IN = 12, W_L0 = 14, W_SKIP = 14 + 6 * L, W_OUT = W_SKIP + 2;
@@ -488,7 +489,7 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
       }
       {  // output_projection -> eps ; fused DDPM posterior step on x_t
         SPhase q = z;
-        q.a1 = 10; q.w1 = W_OUT; q.kchunks = C / 64; q.N = 128; q.NT = 2; q.mode = SP_MEL_SAMPLE; q.bias = d.out_bias_pad;
+        q.a1 = 10; q.w1 = W_OUT; q.kchunks = C / 64; q.N = 256; q.NT = 4; q.mode = SP_MEL_SAMPLE; q.bias = d.out_bias_pad;
         q.out = xm; q.ldo = 80; q.oh = pl[0]; q.ol = pl[1]; q.ldh = 128; q.tab = d.gtab + (size_t)t * 8;
         q.noise = noise ? noise + per * (size_t)(T - t) : nullptr; q.seed = seed; q.stream_id = 1001 + (uint64_t)t; q.n_valid = 80;
         ph[k++] = q;
@@ -496,7 +497,7 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
     }
     SSB_CUDA(cudaMemcpyAsync(maps_dev, maps.data(), sizeof(CUtensorMap) * nmaps, cudaMemcpyHostToDevice, c.stream));
     SSB_CUDA(cudaMemcpyAsync(ph_dev, ph.data(), sizeof(SPhase) * nph, cudaMemcpyHostToDevice, c.stream));
-    RUN(launch_sampler_tc(c, maps_dev, ph_dev, nph, s.tiles, s.tile_tight, s.ntiles, 2 * C / 64, ctr));
+    RUN(launch_sampler_tc(c, maps_dev, ph_dev, nph, s.tiles, s.tile_tight, s.ntiles, 2 * C / 64, ctr, CS));
   }
   RUN(mel_denorm(c, s, xm, 80, m.spec_min, m.spec_max, nullptr, mel_tight, 80));
   c.release(mk);
