@@ -186,6 +186,9 @@ int ssb_hifigan_generate(const ssb_vocoder_t* v, const float* mel, const float* 
  * (3 MMAs per product, fp32 accumulate; default when available), 0 = fp32 FFMA.  Returns the mode in effect. */
 int ssb_model_set_tensor_cores(ssb_model_t* m, int32_t enable);
 
+/* Same switch for the vocoder's wide stages (C % 64 == 0). */
+int ssb_vocoder_set_tensor_cores(ssb_vocoder_t* v, int32_t enable);
+
 /* 1 (default): small batches run the whole T-step mel sampler in ONE persistent cooperative kernel launch
  * (csrc/sampler_tc.cu); 0: one launch per GEMM (BASELINE.json configs[4] compares the two). */
 int ssb_model_set_persistent(ssb_model_t* m, int32_t enable);

@@ -145,6 +145,7 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
       float* lo = alloc_rows(c, sf, 1);
       float* hi = alloc_rows(c, sf, 1);
       float* cond = alloc_rows(c, sf, H);
+      float* cond2 = alloc_rows(c, sf, H);
       WS_OK(c);
       RUN(midi_clip_band(c, sf, midi, lo, hi));
       {
@@ -152,14 +153,34 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
         a.m[0] = dec0; a.ldm[0] = H; a.rowmask = tgt; a.out = cond; a.ldo = H; a.C = H;
         RUN(combine_rows(c, sf, a));
       }
-      RUN(run_f0_diffusion(c, m, 0, sf, cond, lo, hi, in.f0_gauss_noise[0], in.f0_unif_noise[0], in.seed, za, uva));
       {
         CombineArgs a;  // (decoder_inp + spk + emo + style) * tgt_nonpadding (:157-162)
         a.m[0] = dec0; a.ldm[0] = H; a.m[1] = style; a.ldm[1] = H; a.v[0] = spk; a.v[1] = emo;
-        a.rowmask = tgt; a.out = cond; a.ldo = H; a.C = H;
+        a.rowmask = tgt; a.out = cond2; a.ldo = H; a.C = H;
         RUN(combine_rows(c, sf, a));
       }
-      RUN(run_f0_diffusion(c, m, 1, sf, cond, lo, hi, in.f0_gauss_noise[1], in.f0_unif_noise[1], in.seed, zs, uvs));
+      // The two F0/UV samplers are independent (stylesinger.py:223-225): run the second one on the model's
+      // auxiliary stream so that their latency-bound dependent chains overlap.  Disjoint workspace regions.
+      const bool fork = !c.dry && m.aux_stream != nullptr;
+      if (fork) {
+        SSB_CUDA(cudaEventRecord(m.ev_fork, c.stream));
+        SSB_CUDA(cudaStreamWaitEvent(m.aux_stream, m.ev_fork, 0));
+      }
+      const size_t off0 = c.off;
+      RUN(run_f0_diffusion(c, m, 0, sf, cond, lo, hi, in.f0_gauss_noise[0], in.f0_unif_noise[0], in.seed, za, uva));
+      c.off = c.high;  // keep sampler 0's buffers alive: sampler 1 allocates above them
+      {
+        Ctx c2 = c;
+        if (fork) c2.stream = m.aux_stream;
+        RUN(run_f0_diffusion(c2, m, 1, sf, cond2, lo, hi, in.f0_gauss_noise[1], in.f0_unif_noise[1], in.seed, zs, uvs));
+        if (c2.high > c.high) c.high = c2.high;
+        c.failed = c.failed || c2.failed;
+      }
+      if (fork) {
+        SSB_CUDA(cudaEventRecord(m.ev_join, m.aux_stream));
+        SSB_CUDA(cudaStreamWaitEvent(c.stream, m.ev_join, 0));
+      }
+      c.off = off0;
     }
     PitchGlueArgs pg;
     pg.za = za; pg.uva = uva; pg.zs = zs; pg.uvs = uvs; pg.midi = midi; pg.mel2ph = mel2ph;
@@ -297,7 +318,16 @@ int ssb_model_create(ssb_model_t** out, const ssb_tensor_desc* tensors, int32_t 
   *out = m;
   return 0;
 }
-void ssb_model_free(ssb_model_t* m) { delete m; }
+void ssb_model_free(ssb_model_t* m) {
+  if (!m) return;
+  if (m->m.aux_stream) {
+    cudaStreamSynchronize(m->m.aux_stream);
+    cudaEventDestroy(m->m.ev_fork);
+    cudaEventDestroy(m->m.ev_join);
+    cudaStreamDestroy(m->m.aux_stream);
+  }
+  delete m;
+}
 
 int ssb_model_set_schedule(ssb_model_t* m, int32_t which, int32_t T, const float* step_emb, const float* gauss_tab,
                            const float* multi_tab, void* stream) {
@@ -454,6 +484,12 @@ int ssb_model_set_tensor_cores(ssb_model_t* m, int32_t enable) {
   SSB_CHECK(m, "null model");
   m->m.use_tc = enable != 0 && tc_available();
   return m->m.use_tc ? 1 : 0;
+}
+
+int ssb_vocoder_set_tensor_cores(ssb_vocoder_t* v, int32_t enable) {
+  SSB_CHECK(v, "null vocoder");
+  v->v.use_tc = enable != 0 && tc_available();
+  return v->v.use_tc ? 1 : 0;
 }
 
 int ssb_model_set_persistent(ssb_model_t* m, int32_t enable) {

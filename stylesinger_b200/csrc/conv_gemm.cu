@@ -78,7 +78,8 @@ __device__ __forceinline__ void epilogue4(const Epi& e, int64_t r, int n, int N,
     e.out[r * e.ldo + nn] = x;
     if (e.out2) e.out2[r * e.ldo2 + nn] = x + (e.vec2 ? e.vec2[nn] : 0.0f);
     if (e.out2_h) {
-      const float y = x + (e.vec2 ? e.vec2[nn] : 0.0f);
+      float y = x + (e.vec2 ? e.vec2[nn] : 0.0f);
+      if (e.plane_act == ACT_LRELU) y = y > 0.0f ? y : y * e.plane_slope;
       const __half h = __float2half_rn(y);
       e.out2_h[r * e.ldh + nn] = h;
       e.out2_l[r * e.ldh + nn] = __float2half_rn(y - __half2float(h));

@@ -35,6 +35,8 @@ struct Epi {
   __half* out2_h = nullptr;      // optional: (v + vec2) additionally split into fp16 hi/lo planes [rows, ldh]
   __half* out2_l = nullptr;      // (A operand of the tensor-core GEMM that consumes it)
   int ldh = 0;
+  int plane_act = ACT_NONE;      // activation applied to the plane value (ACT_LRELU: pre-activation of the consumer conv)
+  float plane_slope = 0.1f;
   // EPI_RES_SKIP: columns [0,C) -> residual path (res/beta/rowmask/out/out2), [C,2C) -> skip
   float* skip = nullptr;
   int ld_skip = 0;

@@ -42,7 +42,16 @@ struct Pre {
   float4 a[8];
 };
 __device__ __forceinline__ void prefetch32(const EpiTC& e, int64_t r, int n, bool valid, Pre& p) {
-  if (e.mode != EPI_RES_SKIP || !valid) return;
+  if (!valid) return;
+  if (e.mode == EPI_GENERIC) {
+    if (e.res) {
+      const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p.a[q] = rp[q];
+    }
+    return;
+  }
+  if (e.mode != EPI_RES_SKIP) return;
   if (n < e.C) {
     const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
 #pragma unroll
@@ -98,9 +107,41 @@ __device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, con
     }
     return;
   }
-  float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n);
+  // EPI_GENERIC
+  if (e.act == ACT_RELU) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (e.act == ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * e.act_slope;
+  }
+  if (e.res) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      v[4 * q] += pre.a[q].x; v[4 * q + 1] += pre.a[q].y; v[4 * q + 2] += pre.a[q].z; v[4 * q + 3] += pre.a[q].w;
+    }
+  }
+  if (e.out) {
+    float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n);
+    if (e.accum) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 o = op[q];
+        v[4 * q] = (v[4 * q] + o.x) * e.gamma; v[4 * q + 1] = (v[4 * q + 1] + o.y) * e.gamma;
+        v[4 * q + 2] = (v[4 * q + 2] + o.z) * e.gamma; v[4 * q + 3] = (v[4 * q + 3] + o.w) * e.gamma;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  if (e.oh) {
+    if (e.plane_act == ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * e.plane_slope;
+    }
+    split_store16(e.oh + r * e.ldh + n, e.ol + r * e.ldh + n, v);
+    split_store16(e.oh + r * e.ldh + n + 16, e.ol + r * e.ldh + n + 16, v + 16);
+  }
 }
 
 template <int BN>
@@ -320,9 +361,11 @@ bool tc_available() { return get_encode() != nullptr; }
 int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols, int box_rows) { return make_map(m, ptr, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows); }
 
 int make_weight_maps(ConvTC* w) {
-  SSB_CHECK(w->Cin % BK == 0 && w->N % 128 == 0, "tensor-core path needs Cin % 64 == 0 and N % 128 == 0");
-  if (make_map(&w->tm_hi[0], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 128)) return -1;
-  if (make_map(&w->tm_lo[0], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 128)) return -1;
+  SSB_CHECK(w->Cin % BK == 0 && w->N % 64 == 0, "tensor-core path needs Cin % 64 == 0 and N % 64 == 0");
+  if (w->N % 128 == 0) {
+    if (make_map(&w->tm_hi[0], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 128)) return -1;
+    if (make_map(&w->tm_lo[0], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 128)) return -1;
+  }
   if (make_map(&w->tm_hi[1], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 64)) return -1;
   if (make_map(&w->tm_lo[1], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 64)) return -1;
   w->ok = true;
@@ -349,7 +392,7 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   tp.dil = w.dil; tp.center = w.center; tp.N = w.N; tp.e = p.e;
   if (!tp.e.bias) tp.e.bias = w.bias;
   // small problems: 64-wide N tiles keep more SMs busy and shorten each tile's dependent chain
-  const bool small = (int64_t)p.ntiles * (w.N / 128) < (int64_t)num_sms * 2;
+  const bool small = (w.N % 128 != 0) || (int64_t)p.ntiles * (w.N / 128) < (int64_t)num_sms * 2;
   if (small) {
     tp.NT = w.N / 64;
     return launch<64>(ctx, p, tp, num_sms);

@@ -45,6 +45,13 @@ struct EpiTC {
   int ld_skip = 0;
   int C = 0;
   int skip_init = 0;
+  // EPI_GENERIC extras: v = act(acc + bias); v += res; out = accum ? (out + v) * gamma : v; planes = plane_act(v)
+  int act = ACT_NONE;
+  float act_slope = 0.1f;
+  int accum = 0;
+  float gamma = 1.0f;
+  int plane_act = ACT_NONE;      // activation applied to the value written to the fp16 planes (pre-activation of the consumer)
+  float plane_slope = 0.1f;
 };
 
 struct GemmTC {

@@ -118,6 +118,10 @@ struct Model {
   Denoiser melnet;
   Conv mel_out, ln_proj;
   float log_eps = 0.f;
+  // auxiliary stream + fork/join events: lets the two independent F0 samplers overlap (created in build_model).
+  // Calls on one model are therefore serialised with respect to these events (one in-flight forward per model).
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool persistent = true;  // single-launch persistent sampler for small batches (ssb_model_set_persistent)
   bool use_tc = true;  // tcgen05 path for the denoiser layer GEMMs (ssb_model_set_tensor_cores)
 };
@@ -126,7 +130,9 @@ struct VocStage {
   Conv up;          // transposed conv as 3-tap conv, N = u * Cout
   int u = 1, Cout = 0;
   float *nc_w = nullptr, *nc_b = nullptr; int nc_s = 1;  // noise conv
-  struct RB { Conv c1[3], c2[3]; } rb[4];
+  struct RB { Conv c1[3], c2[3]; ConvTC c1_tc[3], c2_tc[3]; } rb[4];
+  ConvTC up_tc;     // tensor-core packing of the transposed conv
+  bool res_tc = false;  // all ResBlock convs of this stage are tensor-core eligible (C % 64 == 0)
 };
 struct Vocoder {
   DevicePool pool;
@@ -136,6 +142,7 @@ struct Vocoder {
   int nk = 3;
   float *lin_w = nullptr, *lin_b = nullptr;
   bool nsf = true;
+  bool use_tc = true;
 };
 
 // ---- packing helpers (pack.cu) -------------------------------------------------------------------

@@ -511,7 +511,7 @@ __global__ void k_nsf_merge(const int4* utt1, const int4* utt256, const float* f
 }
 
 __global__ void k_noise_conv_add(const int4* uttx, const int4* utt256, float* x, int ld, int C, const float* har,
-                                 const float* w, const float* bb, int s) {
+                                 const float* w, const float* bb, int s, __half* ph, __half* pl, float pslope) {
   const int b = blockIdx.y;
   const int4 ux = uttx[b], uh = utt256[b];
   const int t = blockIdx.x * blockDim.y + threadIdx.y;
@@ -525,7 +525,14 @@ __global__ void k_noise_conv_add(const int4* uttx, const int4* utt256, float* x,
       const int64_t q = (int64_t)t * s - pad + j;
       if (q >= 0 && q < uh.y) acc = fmaf(w[c * K + j], har[(int64_t)uh.x + q], acc);
     }
-    x[r * ld + c] += acc;
+    const float v = x[r * ld + c] + acc;
+    x[r * ld + c] = v;
+    if (ph) {  // leaky_relu(v) as fp16 hi/lo planes: the A operand of the tensor-core convs that follow
+      const float y = v > 0.f ? v : v * pslope;
+      const __half h = __float2half_rn(y);
+      ph[r * C + c] = h;
+      pl[r * C + c] = __float2half_rn(y - __half2float(h));
+    }
   }
 }
 __global__ void k_tanh_out(const int4* utt, const float* x, int ld, float* wav) {
@@ -742,9 +749,9 @@ int nsf_source(Ctx& ctx, const SeqDev& s1, const SeqDev& s256, const float* f0, 
   return 0;
 }
 int noise_conv_add(Ctx& ctx, const SeqDev& sx, const SeqDev& s256, float* x, int ld, int C, const float* har,
-                   const float* w, const float* b, int s) {
+                   const float* w, const float* b, int s, __half* ph, __half* pl, float pslope) {
   if (ctx.dry || sx.B == 0) return 0;
-  k_noise_conv_add<<<row_grid(sx), dim3(32, RPB), 0, ctx.stream>>>(sx.utt, s256.utt, x, ld, C, har, w, b, s);
+  k_noise_conv_add<<<row_grid(sx), dim3(32, RPB), 0, ctx.stream>>>(sx.utt, s256.utt, x, ld, C, har, w, b, s, ph, pl, pslope);
     ++g_launches;
   SSB_CUDA(cudaGetLastError());
   return 0;

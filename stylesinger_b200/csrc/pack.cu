@@ -101,7 +101,7 @@ int pack_conv(DevicePool& pool, const HostTensor* w, const HostTensor* b, int di
 int pack_conv_tc(DevicePool& pool, const HostTensor* w, int dil, PackMode mode, const float* packed_bias, ConvTC* out) {
   if (!w) return -1;
   const int N = (int)w->shape[0], Cin = (int)w->shape[1], k = w->shape.size() == 3 ? (int)w->shape[2] : 1;
-  if (Cin % 64 != 0 || N % 128 != 0 || !tc_available()) return 0;  // not eligible: out->ok stays false
+  if (Cin % 64 != 0 || N % 64 != 0 || !tc_available()) return 0;  // not eligible: out->ok stays false
   std::vector<__half> hi((size_t)k * N * Cin), lo((size_t)k * N * Cin);
   for (int n = 0; n < N; ++n) {
     const int pn = perm_col(n, N, mode);
@@ -124,6 +124,39 @@ int pack_conv_tc(DevicePool& pool, const HostTensor* w, int dil, PackMode mode, 
   out->W_hi = (__half*)dh; out->W_lo = (__half*)dl;
   out->taps = k; out->Cin = Cin; out->N = N; out->dil = dil; out->center = (k - 1) / 2; out->bias = packed_bias;
   return make_weight_maps(out);
+}
+
+// weight-normed Conv1d -> tensor-core packing
+static int pack_conv_tc_wn(DevicePool& pool, const HostTensor* v, const HostTensor* g, int dil, const float* packed_bias, ConvTC* out) {
+  if (!v || !g) return -1;
+  std::vector<float> w;
+  fold_weight_norm(v, g, w);
+  HostTensor t;
+  t.data = w.data();
+  t.shape = v->shape;
+  return pack_conv_tc(pool, &t, dil, PACK_PLAIN, packed_bias, out);
+}
+// weight-normed ConvTranspose1d (k = 2u) -> 3-tap conv with N = u*Cout -> tensor-core packing
+static int pack_conv_transpose_tc(DevicePool& pool, const HostTensor* v, const HostTensor* g, int u, const float* packed_bias, ConvTC* out) {
+  if (!v || !g) return -1;
+  const int Cin = (int)v->shape[0], Cout = (int)v->shape[1], k = (int)v->shape[2];
+  const int p = (k - u) / 2, N = u * Cout;
+  std::vector<float> w;
+  fold_weight_norm(v, g, w);
+  std::vector<float> t((size_t)N * Cin * 3, 0.f);  // torch conv layout [N][Cin][3]
+  for (int phi = 0; phi < u; ++phi)
+    for (int j = 0; j < k; ++j) {
+      const int num = phi + p - j;
+      if (num % u != 0) continue;
+      const int d = num / u;
+      if (d < -1 || d > 1) return 0;
+      for (int c = 0; c < Cin; ++c)
+        for (int n = 0; n < Cout; ++n) t[((size_t)(phi * Cout + n) * Cin + c) * 3 + (d + 1)] = w[((size_t)c * Cout + n) * k + j];
+    }
+  HostTensor ht;
+  ht.data = t.data();
+  ht.shape = {N, Cin, 3};
+  return pack_conv_tc(pool, &ht, 1, PACK_PLAIN, packed_bias, out);
 }
 
 int pack_linear(DevicePool& pool, const HostTensor* w, const HostTensor* b, Conv* out, int row0, int nrows) {
@@ -362,6 +395,12 @@ int build_model(TensorMap& tm, const ssb_hparams& hp, Model* m) {
   PK(pack_linear(pool, tm.get("mel_out.weight"), tm.get("mel_out.bias"), &m->mel_out));
   PK(pack_linear(pool, tm.get("ln_proj.weight"), tm.get("ln_proj.bias"), &m->ln_proj));
   m->log_eps = logf(1e-30f);
+  if (cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking) != cudaSuccess) m->aux_stream = nullptr;
+  if (m->aux_stream && (cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+    cudaStreamDestroy(m->aux_stream);
+    m->aux_stream = nullptr;
+  }
   if (!tm.missing.empty()) goto fail;
   SSB_CUDA(cudaDeviceSynchronize());
   return 0;
@@ -390,6 +429,8 @@ int build_vocoder(TensorMap& tm, const ssb_vocoder_config& cfg, Vocoder* v) {
       s.Cout = c / 2;
       SSB_CHECK(cfg.up_kernels[i] == 2 * cfg.up_rates[i] || cfg.up_kernels[i] - cfg.up_rates[i] >= 0, "vocoder: bad upsample kernel");
       PK(pack_conv_transpose(pool, tm.get(u + "weight_v"), tm.get(u + "weight_g"), tm.get(u + "bias"), s.u, &s.up));
+      PK(pack_conv_transpose_tc(pool, tm.get(u + "weight_v"), tm.get(u + "weight_g"), s.u, s.up.bias, &s.up_tc));
+      s.res_tc = true;
       prod_after /= s.u;
       if (v->nsf) {
         const std::string n = "noise_convs." + std::to_string(i) + ".";
@@ -405,6 +446,9 @@ int build_vocoder(TensorMap& tm, const ssb_vocoder_config& cfg, Vocoder* v) {
           const std::string a = q + "convs1." + std::to_string(mI) + ".", b2 = q + "convs2." + std::to_string(mI) + ".";
           PK(pack_conv(pool, tm.get(a + "weight_v"), tm.get(a + "bias"), cfg.res_dilations[j][mI], PACK_PLAIN, &s.rb[j].c1[mI], tm.get(a + "weight_g")));
           PK(pack_conv(pool, tm.get(b2 + "weight_v"), tm.get(b2 + "bias"), 1, PACK_PLAIN, &s.rb[j].c2[mI], tm.get(b2 + "weight_g")));
+          PK(pack_conv_tc_wn(pool, tm.get(a + "weight_v"), tm.get(a + "weight_g"), cfg.res_dilations[j][mI], s.rb[j].c1[mI].bias, &s.rb[j].c1_tc[mI]));
+          PK(pack_conv_tc_wn(pool, tm.get(b2 + "weight_v"), tm.get(b2 + "weight_g"), 1, s.rb[j].c2[mI].bias, &s.rb[j].c2_tc[mI]));
+          if (!s.rb[j].c1_tc[mI].ok || !s.rb[j].c2_tc[mI].ok) s.res_tc = false;
         }
       }
       c /= 2;

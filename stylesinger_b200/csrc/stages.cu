@@ -563,6 +563,9 @@ int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const f
 
 // ------------------------------------------------------------------------------------------------
 // a20/a21: HifiGanGenerator.forward (hifigan_nsf.py:144-169)
+// Stages whose channel counts are multiples of 64 run on the tcgen05 kernel: every conv input is carried as
+// fp16 hi/lo planes of leaky_relu(x) written by the producing epilogue (the reference applies leaky_relu before
+// every conv), residuals / MRF accumulators stay fp32.  Narrow stages (C = 32) use the fp32 FFMA kernel.
 int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight, const float* f0_tight,
                 const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_tight) {
   const size_t mk0 = c.mark();
@@ -586,12 +589,20 @@ int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight
     RUN(nsf_source(c, s1, s256, f0g, v.lin_w, v.lin_b, rand_ini, src_noise, har, scratch, seed, hop, (float)v.cfg.sample_rate));
     c.release(mk);
   }
+  const bool tc = v.use_tc && tc_available();
   int C = v.cfg.initial_channel;
   float* x = alloc_rows(c, s1, C);
+  __half *pin_h = nullptr, *pin_l = nullptr;  // planes of leaky_relu(stage input), when the next ups runs on tensor cores
+  const bool up0_tc = tc && !v.stages.empty() && v.stages[0].up_tc.ok;
+  if (up0_tc) {
+    pin_h = alloc_half_rows(c, s1, C);
+    pin_l = alloc_half_rows(c, s1, C);
+  }
   WS_OK(c);
   {
     ConvGemm g = make_gemm(v.pre, s1, mel, 80);
     g.e.out = x; g.e.ldo = C;
+    if (up0_tc) { g.e.out2_h = pin_h; g.e.out2_l = pin_l; g.e.ldh = C; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
     RUN(conv_gemm(c, g));
   }
   int rate = 1;
@@ -603,21 +614,65 @@ int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight
     const int rate_out = rate * st.u;
     SeqDev so;
     RUN(upload_layout(c, seq, rate_out, &so));
+    const bool up_tc = tc && st.up_tc.ok && pin_h != nullptr;
+    const bool res_tc = tc && st.res_tc;
+    const bool next_up_tc = tc && i + 1 < v.stages.size() && v.stages[i + 1].up_tc.ok;
     float* xu = alloc_rows(c, so, Co);
-    float* xt = alloc_rows(c, so, Co);
     float* r = alloc_rows(c, so, Co);
     float* acc = alloc_rows(c, so, Co);
+    float* xt = nullptr;
+    __half *px_h = nullptr, *px_l = nullptr, *pt_h = nullptr, *pt_l = nullptr, *pr_h = nullptr, *pr_l = nullptr;
+    __half *pa_h = nullptr, *pa_l = nullptr;
+    if (res_tc) {
+      px_h = alloc_half_rows(c, so, Co); px_l = alloc_half_rows(c, so, Co);
+      pt_h = alloc_half_rows(c, so, Co); pt_l = alloc_half_rows(c, so, Co);
+      pr_h = alloc_half_rows(c, so, Co); pr_l = alloc_half_rows(c, so, Co);
+    } else {
+      xt = alloc_rows(c, so, Co);
+    }
+    if (next_up_tc) { pa_h = alloc_half_rows(c, so, Co); pa_l = alloc_half_rows(c, so, Co); }
     WS_OK(c);
-    {  // x = ups[i](leaky_relu(x, 0.1))
+    // x = ups[i](leaky_relu(x, 0.1))
+    if (up_tc) {
+      GemmTC g;
+      g.A_hi = pin_h; g.A_lo = pin_l; g.rows_total = sin.rows; g.w = &st.up_tc; g.tiles = sin.tiles; g.ntiles = sin.ntiles;
+      g.e.mode = EPI_GENERIC; g.e.out = xu; g.e.ldo = st.u * Co;
+      if (res_tc && !nsf) { g.e.oh = px_h; g.e.ol = px_l; g.e.ldh = st.u * Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
+      RUN(conv_gemm_tc(c, g));
+    } else {
       ConvGemm g = make_gemm(st.up, sin, xin, C);
       g.a_act = ACT_LRELU; g.a_slope = 0.1f;
       g.e.out = xu; g.e.ldo = st.u * Co;
+      if (res_tc && !nsf) { g.e.out2_h = px_h; g.e.out2_l = px_l; g.e.ldh = st.u * Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
       RUN(conv_gemm(c, g));
     }
-    if (nsf) RUN(noise_conv_add(c, so, s256, xu, Co, Co, har, st.nc_w, st.nc_b, st.nc_s));
+    if (nsf) RUN(noise_conv_add(c, so, s256, xu, Co, Co, har, st.nc_w, st.nc_b, st.nc_s, res_tc ? px_h : nullptr, px_l, 0.1f));
     for (int j = 0; j < v.nk; ++j) {  // MRF: mean of the resblocks
       const float* rin = xu;
+      const __half *rin_h = px_h, *rin_l = px_l;
       for (int mI = 0; mI < 3; ++mI) {
+        const bool last = (mI == 2);
+        const bool lastj = (j == v.nk - 1);
+        if (res_tc) {
+          {
+            GemmTC g;  // xt = c1(leaky_relu(r)) ; only leaky_relu(xt) is ever consumed -> planes only
+            g.A_hi = rin_h; g.A_lo = rin_l; g.rows_total = so.rows; g.w = &st.rb[j].c1_tc[mI]; g.tiles = so.tiles; g.ntiles = so.ntiles;
+            g.e.mode = EPI_GENERIC; g.e.oh = pt_h; g.e.ol = pt_l; g.e.ldh = Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f;
+            RUN(conv_gemm_tc(c, g));
+          }
+          GemmTC g;  // r = c2(leaky_relu(xt)) + r
+          g.A_hi = pt_h; g.A_lo = pt_l; g.rows_total = so.rows; g.w = &st.rb[j].c2_tc[mI]; g.tiles = so.tiles; g.ntiles = so.ntiles;
+          g.e.mode = EPI_GENERIC; g.e.res = rin; g.e.ld_res = Co;
+          if (!last) {
+            g.e.out = r; g.e.ldo = Co; g.e.oh = pr_h; g.e.ol = pr_l; g.e.ldh = Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f;
+          } else {
+            g.e.out = acc; g.e.ldo = Co; g.e.accum = (j > 0); g.e.gamma = lastj ? 1.0f / (float)v.nk : 1.0f;
+            if (lastj && next_up_tc) { g.e.oh = pa_h; g.e.ol = pa_l; g.e.ldh = Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
+          }
+          RUN(conv_gemm_tc(c, g));
+          rin = r; rin_h = pr_h; rin_l = pr_l;
+          continue;
+        }
         {
           ConvGemm g = make_gemm(st.rb[j].c1[mI], so, rin, Co);
           g.a_act = ACT_LRELU; g.a_slope = 0.1f;
@@ -627,22 +682,20 @@ int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight
         ConvGemm g = make_gemm(st.rb[j].c2[mI], so, xt, Co);
         g.a_act = ACT_LRELU; g.a_slope = 0.1f;
         g.e.res = rin; g.e.ld_res = Co;
-        if (mI < 2) {
+        if (!last) {
           g.e.out = r; g.e.ldo = Co;
         } else {
           g.e.out = acc; g.e.ldo = Co;
           g.e.accum = (j > 0);
-          g.e.gamma = (j == v.nk - 1) ? 1.0f / (float)v.nk : 1.0f;
-          if (j == 0 && v.nk == 1) g.e.gamma = 1.0f;
+          g.e.gamma = lastj ? 1.0f / (float)v.nk : 1.0f;
+          if (lastj && next_up_tc) { g.e.out2_h = pa_h; g.e.out2_l = pa_l; g.e.ldh = Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
         }
         RUN(conv_gemm(c, g));
         rin = r;
       }
     }
-    // NOTE: for nk == 1 the mean is the identity; for nk > 1 the last accumulation applies 1/nk.
     xin = acc; sin = so; C = Co; rate = rate_out;
-    // buffers of the previous stage stay allocated until the end (bump allocator); sizes are bounded by
-    // 4 * rows * C which is constant from stage 1 on.
+    pin_h = pa_h; pin_l = pa_l;
   }
   {
     float* y = alloc_rows(c, sin, 4);

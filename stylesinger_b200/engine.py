@@ -351,6 +351,9 @@ class Vocoder:
             lib.ssb_vocoder_free(h)
             self._h = None
 
+    def set_tensor_cores(self, enable=True):
+        return bool(lib.ssb_vocoder_set_tensor_cores(self._h, 1 if enable else 0))
+
     def generate(self, mel, f0, frame_offsets, rand_ini=None, src_noise=None, seed=0):
         """mel [sumF,80], f0 [sumF] or None (device, tight) -> wav [sumF*hop] (device)."""
         fo = np.ascontiguousarray(frame_offsets, np.int32)

@@ -43,6 +43,9 @@ for tag in ("persist", "tc", "simt"):
     res[f"{tag}.one_f0_diffusion"] = (round(ms, 2), round(wall, 2), nl)
 m.set_tensor_cores(True); m.set_persistent(True)
 melc = mel.clamp(-6, 1.5).contiguous(); f0 = out["f0_denorm"]
-ms, wall, nl, _ = timed(lambda: v.generate(melc, f0, pb.frame_offsets, seed=4))
-res["vocoder"] = (round(ms, 2), round(wall, 2), nl)
+for tcv in (True, False):
+    v.set_tensor_cores(tcv)
+    ms, wall, nl, _ = timed(lambda: v.generate(melc, f0, pb.frame_offsets, seed=4))
+    res["vocoder." + ("tc" if tcv else "simt")] = (round(ms, 2), round(wall, 2), nl)
+v.set_tensor_cores(True)
 print(json.dumps({"workload": wl, "frames": F_, "T": T, "stage: (gpu_ms, wall_ms, launches)": res}))
