@@ -23,7 +23,13 @@ def _require_cuda():
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device pointer of a tensor handed to the C ABI. The library reads plain row-major memory, so a strided
+    (e.g. transposed / Fortran-ordered) view would be silently misread: refuse it loudly."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError("stylesinger_b200: tensors passed to the C ABI must be contiguous (call .contiguous())")
+    return C.c_void_p(t.data_ptr())
 
 
 def _descs(named: Dict[str, torch.Tensor]):

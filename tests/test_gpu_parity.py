@@ -80,7 +80,10 @@ def test_denoisers_match_reference_golden():
 def test_rvq_codes_bit_exact_vs_reference_golden():
     g, meta = golden("ref_small_T4")
     m = acoustic_engine(meta["T"])
-    x = torch.from_numpy(g["rq_in"]).to(DEV)
+    # the fixture is stored Fortran-ordered (the reference's tensor is a transposed view): make it row-major
+    x = torch.from_numpy(np.ascontiguousarray(g["rq_in"])).to(DEV)
+    with pytest.raises(ValueError):
+        m.rvq(torch.from_numpy(g["rq_in"]).to(DEV), np.array([0, x.shape[0]], np.int32))  # strided view: refused
     q, codes = m.rvq(x, np.array([0, x.shape[0]], np.int32))
     assert np.array_equal(codes.cpu().numpy().astype(np.int64), g["rq_codes"])
     with torch.no_grad():
