@@ -161,6 +161,11 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
       }
       // The two F0/UV samplers are independent (stylesinger.py:223-225): run the second one on the model's
       // auxiliary stream so that their latency-bound dependent chains overlap.  Disjoint workspace regions.
+      if (f0_pair_persistent_ok(m, sf)) {
+        float* zz[2] = {za, zs};
+        int32_t* uu[2] = {uva, uvs};
+        RUN(run_f0_diffusion_pair_persistent(c, m, sf, cond, cond2, lo, hi, in.f0_gauss_noise, in.f0_unif_noise, in.seed, zz, uu));
+      } else {
       const bool fork = !c.dry && m.aux_stream != nullptr;
       if (fork) {
         SSB_CUDA(cudaEventRecord(m.ev_fork, c.stream));
@@ -181,6 +186,7 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
         SSB_CUDA(cudaStreamWaitEvent(c.stream, m.ev_join, 0));
       }
       c.off = off0;
+      }
     }
     PitchGlueArgs pg;
     pg.za = za; pg.uva = uva; pg.zs = zs; pg.uvs = uvs; pg.midi = midi; pg.mel2ph = mel2ph;

@@ -87,6 +87,7 @@ struct Denoiser {
   ConvTC skip_tc;  // skip_projection with the 1/sqrt(L) skip scale folded into the weights
   ConvTC out_tc;   // output_projection, N padded 80 -> 256 (4 N-tiles of 64: one cluster)
   float* out_bias_pad = nullptr;
+  float* skip_bias_pad = nullptr;
 };
 
 struct AlignLayer {

@@ -277,30 +277,43 @@ static int build_denoiser(TensorMap& tm, DevicePool& pool, const std::string& p,
   d->cond_all.taps = 1; d->cond_all.Cin = H; d->cond_all.N = L * N2; d->cond_all.Npad = L * N2; d->cond_all.dil = 1; d->cond_all.center = 0;
   if (pack_conv(pool, tm.get(p + "skip_projection.weight"), tm.get(p + "skip_projection.bias"), 1, PACK_PLAIN, &d->skip_proj)) return -1;
   if (pack_conv(pool, tm.get(p + "output_projection.weight"), tm.get(p + "output_projection.bias"), 1, PACK_PLAIN, &d->out_proj)) return -1;
-  if (!ddiff && C % 64 == 0 && in_dims <= 128 && out_dims <= 128) {
-    // tensor-core packing of the step's head/tail GEMMs for the persistent sampler
-    const HostTensor* iw = tm.get(p + "input_projection.weight");
+  if (C % 64 == 0 && in_dims <= 128 && out_dims <= 128) {
+    // tensor-core packing of the step's head/tail GEMMs for the persistent sampler.
+    // mel net: in_proj K 80->128, skip_proj, out_proj N 80->256.  F0 nets: skip_proj N 192->256, out_proj N 3->128.
     const HostTensor* sw = tm.get(p + "skip_projection.weight");
+    const HostTensor* sbias = tm.get(p + "skip_projection.bias");
     const HostTensor* ow = tm.get(p + "output_projection.weight");
     const HostTensor* ob = tm.get(p + "output_projection.bias");
-    if (!iw || !sw || !ow || !ob) return -1;
-    std::vector<float> wi((size_t)C * 128, 0.f), ws((size_t)C * C), wo((size_t)256 * C, 0.f), bo(256, 0.f);  // N padded to 4 x 64
-    for (int n = 0; n < C; ++n)
-      for (int c = 0; c < in_dims; ++c) wi[(size_t)n * 128 + c] = iw->data[(size_t)n * in_dims + c];
+    if (!sw || !sbias || !ow || !ob) return -1;
+    const int Ns = (C + 127) / 128 * 128 < 256 ? 256 : (C + 127) / 128 * 128;  // 256 for C = 192 and 256
+    const int No = ddiff ? 128 : 256;
+    std::vector<float> ws((size_t)Ns * C, 0.f), bs((size_t)Ns, 0.f), wo((size_t)No * C, 0.f), bo((size_t)No, 0.f);
     const float sc = 1.0f / sqrtf((float)L);
-    for (size_t i = 0; i < ws.size(); ++i) ws[i] = sw->data[i] * sc;
+    for (int n = 0; n < C; ++n) {
+      for (int c = 0; c < C; ++c) ws[(size_t)n * C + c] = sw->data[(size_t)n * C + c] * sc;
+      bs[n] = sbias->data[n];
+    }
     for (int n = 0; n < out_dims; ++n) {
       for (int c = 0; c < C; ++c) wo[(size_t)n * C + c] = ow->data[(size_t)n * C + c];
       bo[n] = ob->data[n];
     }
     d->out_bias_pad = pool.upload(bo);
-    HostTensor ti, ts, to;
-    ti.data = wi.data(); ti.shape = {C, 128, 1};
-    ts.data = ws.data(); ts.shape = {C, C, 1};
-    to.data = wo.data(); to.shape = {256, C, 1};
-    if (pack_conv_tc(pool, &ti, 1, PACK_PLAIN, d->in_proj.bias, &d->in_tc)) return -1;
-    if (pack_conv_tc(pool, &ts, 1, PACK_PLAIN, d->skip_proj.bias, &d->skip_tc)) return -1;
+    d->skip_bias_pad = pool.upload(bs);
+    HostTensor ts, to;
+    ts.data = ws.data(); ts.shape = {Ns, C, 1};
+    to.data = wo.data(); to.shape = {No, C, 1};
+    if (pack_conv_tc(pool, &ts, 1, PACK_PLAIN, d->skip_bias_pad, &d->skip_tc)) return -1;
     if (pack_conv_tc(pool, &to, 1, PACK_PLAIN, d->out_bias_pad, &d->out_tc)) return -1;
+    if (!ddiff) {
+      const HostTensor* iw = tm.get(p + "input_projection.weight");
+      if (!iw) return -1;
+      std::vector<float> wi((size_t)C * 128, 0.f);
+      for (int n = 0; n < C; ++n)
+        for (int c = 0; c < in_dims; ++c) wi[(size_t)n * 128 + c] = iw->data[(size_t)n * in_dims + c];
+      HostTensor ti;
+      ti.data = wi.data(); ti.shape = {C, 128, 1};
+      if (pack_conv_tc(pool, &ti, 1, PACK_PLAIN, d->in_proj.bias, &d->in_tc)) return -1;
+    }
   }
   return 0;
 }

@@ -144,7 +144,61 @@ __device__ __forceinline__ void epilogue32(const SPhase& e, int64_t r, int64_t t
     }
     return;
   }
+  if (e.mode == SP_F0_SAMPLE) {
+    if (n != 0) return;  // columns 0..2 of the (padded) 3-channel head: (eps, logit0, logit1)
+    const float ln2 = 0.69314718055994530942f;
+    const float zt = __ldcg(e.out + r);
+    float x0 = __ldg(e.tab + 0) * zt - __ldg(e.tab + 1) * v[0];
+    x0 = fmaxf(fminf(x0, __ldg(e.clip_hi + r)), __ldg(e.clip_lo + r));
+    const float mean = __ldg(e.tab + 2) * x0 + __ldg(e.tab + 3) * zt;
+    const float gz = e.noise ? __ldg(e.noise + ti) : philox_normal(e.seed, e.stream_id, (uint64_t)ti);
+    const float zn = mean + __ldg(e.tab + 4) * gz;
+    e.out[r] = zn;
+    const float l0a = v[1], l0b = v[2];
+    const float mx = fmaxf(l0a, l0b);
+    const float lse = mx + logf(expf(l0a - mx) + expf(l0b - mx));
+    const float ls0 = l0a - lse, ls1 = l0b - lse;
+    auto lae = [](float a, float b) { const float m = fmaxf(a, b); return m + logf(expf(a - m) + expf(b - m)); };
+    float e0, e1;
+    if (e.tstep == 0) { e0 = ls0; e1 = ls1; }
+    else {
+      e0 = lae(ls0 + __ldg(e.tab2 + 2), __ldg(e.tab2 + 3) - ln2);
+      e1 = lae(ls1 + __ldg(e.tab2 + 2), __ldg(e.tab2 + 3) - ln2);
+    }
+    const int cur = e.uv[r];
+    const float lz0 = cur == 0 ? 0.f : e.log_eps, lz1 = cur == 1 ? 0.f : e.log_eps;
+    const float u0 = e0 + lae(lz0 + __ldg(e.tab2 + 0), __ldg(e.tab2 + 1) - ln2);
+    const float u1 = e1 + lae(lz1 + __ldg(e.tab2 + 0), __ldg(e.tab2 + 1) - ln2);
+    const float m2 = fmaxf(u0, u1);
+    const float lse2 = m2 + logf(expf(u0 - m2) + expf(u1 - m2));
+    const float p0 = u0 - lse2, p1 = u1 - lse2;
+    const float r0 = e.noise2 ? __ldg(e.noise2 + ti * 2) : philox_uniform(e.seed, e.stream_id + 1, (uint64_t)(ti * 2));
+    const float r1 = e.noise2 ? __ldg(e.noise2 + ti * 2 + 1) : philox_uniform(e.seed, e.stream_id + 1, (uint64_t)(ti * 2 + 1));
+    const float g0 = -logf(-logf(r0 + 1e-30f) + 1e-30f);
+    const float g1 = -logf(-logf(r1 + 1e-30f) + 1e-30f);
+    const int cls = (g1 + p1) > (g0 + p0) ? 1 : 0;
+    e.uv[r] = cls;
+    if (e.has_next) {  // DDiffNet input of step t-1 (net.py:249-252): cat[Conv1x1(f0), Embedding(uv)] ; y = x + d0
+      const int C = e.C, h = C / 2;
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        float xv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = c0 + j;
+          xv[j] = c < h ? (zn * __ldg(e.in_w + c) + __ldg(e.in_b + c)) : __ldg(e.uv_emb + cls * h + (c - h));
+        }
+        float4* xp = reinterpret_cast<float4*>(e.x_next + r * C + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xp[q] = make_float4(xv[4 * q], xv[4 * q + 1], xv[4 * q + 2], xv[4 * q + 3]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xv[j] += __ldg(e.vec2 + c0 + j);
+        split_store16(e.oh + r * e.ldh + c0, e.ol + r * e.ldh + c0, xv);
+      }
+    }
+    return;
+  }
   if (e.mode == SP_INPROJ || e.mode == SP_SKIPPROJ) {
+    if (e.mode == SP_SKIPPROJ && e.n_valid > 0 && n >= e.n_valid) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     if (e.out) {
@@ -253,6 +307,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
     const SPhase& P = *sph;
     const int gpm = P.NT / cs;           // tile groups (clusters' worth of N-tiles) per M-tile
     const int groups = ntiles * gpm;
+    const int g_first = ((cid - P.goff) % ncl + ncl) % ncl;  // group g runs on cluster (g + goff) % ncl
     const int nk1 = P.taps * P.kchunks;
     const int nk = nk1 + P.kchunks2;
 
@@ -263,7 +318,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
         const CUtensorMap* mW = maps + P.w1;
         const CUtensorMap* mA2 = maps + (P.a2 >= 0 ? P.a2 : P.a1);
         const CUtensorMap* mW2 = maps + (P.a2 >= 0 ? P.w2 : P.w1);
-        for (int g = cid; g < groups; g += ncl) {
+        for (int g = g_first; g < groups; g += ncl) {
           const int mt = g / gpm, nt = (g - mt * gpm) * cs + cr;
           const int row0 = tiles[mt].x;
           for (int kb = 0; kb < nk; ++kb) {
@@ -303,7 +358,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        for (int g = cid; g < groups; g += ncl, ++it) {
+        for (int g = g_first; g < groups; g += ncl, ++it) {
           const int a = it & 1;
           const uint32_t aph = (it >> 1) & 1;
           mbar_wait(tempty0 + 8 * a, aph ^ 1);
@@ -331,7 +386,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
       }
     } else if (warp >= 4) {
       const int ew = warp - 4;
-      for (int g = cid; g < groups; g += ncl, ++it) {
+      for (int g = g_first; g < groups; g += ncl, ++it) {
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         const int mt = g / gpm, nt = (g - mt * gpm) * cs + cr;
@@ -359,7 +414,8 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
     }
     // the producer / MMA roles keep separate copies of (stage, phase_bit) and the MMA / epilogue roles of `it`:
     // every role advances them by exactly the same amounts per phase, so no exchange is needed.
-    grid_barrier(barrier_ctr, gen, gridDim.x);
+    if (P.sync_after) grid_barrier(barrier_ctr, gen, gridDim.x);
+    else __syncthreads();  // the next entry is independent of this one: only the descriptor slot is recycled
   }
   tc_fence_before();
   __syncthreads();
@@ -392,7 +448,7 @@ int x80_planes(Ctx& ctx, const float* x, int64_t rows, __half* hi, __half* lo) {
   return 0;
 }
 
-static int max_clusters(int cs) {
+int sampler_tc_max_clusters(int cs) {
   static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
   if (cs < 1 || cs > 8) return 0;
   if (cache[cs] >= 0) return cache[cs];
@@ -415,12 +471,12 @@ static int max_clusters(int cs) {
   return n;
 }
 
-int sampler_tc_max_ctas() { return max_clusters(1); }
+int sampler_tc_max_ctas() { return sampler_tc_max_clusters(1); }
 
 int launch_sampler_tc(Ctx& ctx, const CUtensorMap* maps_dev, const SPhase* phases_dev, int nphases, const int2* tiles,
                       const int* tile_tight, int ntiles, int max_nt, unsigned* barrier_ctr, int cs) {
   if (ctx.dry) return 0;
-  const int cap = max_clusters(cs);
+  const int cap = sampler_tc_max_clusters(cs);
   SSB_CHECK(cap > 0, "persistent sampler kernel cannot be resident on this device");
   int ncl = ntiles * (max_nt / cs);
   if (ncl > cap) ncl = cap;

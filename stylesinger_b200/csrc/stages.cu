@@ -460,7 +460,7 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
       const float* dt = d.dtab + (size_t)t * L * C;
       SPhase z;
       memset(&z, 0, sizeof(z));
-      z.a2 = -1; z.taps = 1; z.dil = 1; z.beta = 1.0f;
+      z.a2 = -1; z.taps = 1; z.dil = 1; z.beta = 1.0f; z.sync_after = 1;
       {  // input_projection + ReLU ; y = x + step bias of layer 0
         SPhase q = z;
         q.a1 = 0; q.w1 = W_IN; q.kchunks = 2; q.N = C; q.NT = C / 64; q.mode = SP_INPROJ; q.bias = d.in_proj.bias;
@@ -530,6 +530,131 @@ int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond
   RUN(mel_denorm(c, s, xm, 80, m.spec_min, m.spec_max, nullptr, mel_tight, 80));
   c.release(mk);
   return 0;
+}
+
+// a13+a14 for BOTH F0 nets in one persistent launch: the agnostic and the specific sampler are independent
+// (stylesinger.py:223-225), so each phase of the table carries two entries (one per net, no barrier between them).
+int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, const float* cond0, const float* cond1,
+                                     const float* lo, const float* hi, const float* const gnoise[2],
+                                     const float* const unoise[2], uint64_t seed, float* const z[2], int32_t* const uv[2]) {
+  const Denoiser& d0 = m.f0net[0];
+  const int C = d0.C, L = d0.L, T = d0.T;
+  const int CS = 2;
+  const size_t mk = c.mark();
+  const int NA = 10;           // activation maps per net: y, z, cond, skip, s (hi/lo)
+  const int NW = 6 * L + 4;    // weight maps per net
+  const int nmaps = 2 * (NA + NW);
+  const int per_step = 2 * L + 2;
+  const int nph = 2 * T * per_step;
+  float* x[2]; float* skip[2]; __half* pl[2][10];
+  const int pcols[5] = {C, C, 256, C, C};
+  for (int n = 0; n < 2; ++n) {
+    x[n] = alloc_rows(c, s, C);
+    skip[n] = alloc_rows(c, s, C);
+    for (int i = 0; i < 5; ++i) {
+      pl[n][2 * i] = alloc_half_rows(c, s, pcols[i]);
+      pl[n][2 * i + 1] = alloc_half_rows(c, s, pcols[i]);
+    }
+  }
+  CUtensorMap* maps_dev = c.alloc<CUtensorMap>((size_t)nmaps);
+  SPhase* ph_dev = c.alloc<SPhase>((size_t)nph);
+  unsigned* ctr = c.alloc<unsigned>(4);
+  WS_OK(c);
+  const size_t per = (size_t)s.total;
+  for (int n = 0; n < 2; ++n) {
+    const Denoiser& d = m.f0net[n];
+    const uint64_t sbase = 2000 + (uint64_t)n * 100000;
+    RUN(f0_init(c, s, z[n], uv[n], gnoise[n], seed, sbase));
+    RUN(ddiff_input(c, s, z[n], uv[n], d.in_w, d.in_b, d.uv_emb, d.dtab + (size_t)(T - 1) * L * C, x[n], nullptr, C, pl[n][0], pl[n][1]));
+    RUN(split_planes(c, n == 0 ? cond0 : cond1, 256, s.rows, 256, 1.0f, pl[n][4], pl[n][5]));
+  }
+  if (!c.dry) {
+    std::vector<CUtensorMap> maps((size_t)nmaps);
+    std::vector<SPhase> ph((size_t)nph);
+    // number of clusters the launcher will use: needed for the tile-group rotation of the second net
+    int ncl = s.ntiles * (2 * (2 * C / 64) / CS);
+    {
+      const int cap = sampler_tc_max_clusters(CS);
+      if (ncl > cap) ncl = cap;
+      if (ncl < 1) ncl = 1;
+    }
+    for (int n = 0; n < 2; ++n) {
+      const Denoiser& d = m.f0net[n];
+      const int MB = n * (NA + NW);
+      for (int i = 0; i < 5; ++i) {
+        if (make_act_map(&maps[MB + 2 * i], pl[n][2 * i], s.rows, pcols[i], 128 / CS)) return -1;
+        if (make_act_map(&maps[MB + 2 * i + 1], pl[n][2 * i + 1], s.rows, pcols[i], 128 / CS)) return -1;
+      }
+      auto put = [&](int idx, const ConvTC& w) { maps[idx] = w.tm_hi[1]; maps[idx + 1] = w.tm_lo[1]; };
+      const int W_L0 = MB + NA, W_SKIP = W_L0 + 6 * L, W_OUT = W_SKIP + 2;
+      for (int l = 0; l < L; ++l) {
+        put(W_L0 + 6 * l, d.layers[l].dil_tc);
+        put(W_L0 + 6 * l + 2, d.layers[l].cond_tc);
+        put(W_L0 + 6 * l + 4, d.layers[l].outp_tc);
+      }
+      put(W_SKIP, d.skip_tc);
+      put(W_OUT, d.out_tc);
+      const uint64_t sbase = 2000 + (uint64_t)n * 100000;
+      for (int ti = 0; ti < T; ++ti) {
+        const int t = T - 1 - ti;
+        const float* dt = d.dtab + (size_t)t * L * C;
+        SPhase zp;
+        memset(&zp, 0, sizeof(zp));
+        zp.a2 = -1; zp.taps = 1; zp.dil = 1; zp.beta = 1.0f; zp.sync_after = (n == 1);
+        // entry k of step ti for net n sits at ((ti * per_step + k) * 2 + n)
+        size_t k = 0;
+        auto slot = [&](size_t kk) -> SPhase& { return ph[((size_t)ti * per_step + kk) * 2 + n]; };
+        for (int l = 0; l < L; ++l) {
+          SPhase a = zp;
+          a.a1 = MB + 0; a.a2 = MB + 4; a.w1 = W_L0 + 6 * l; a.w2 = W_L0 + 6 * l + 2; a.taps = 3; a.kchunks = C / 64; a.kchunks2 = 4;
+          a.dil = d.layers[l].dil_tc.dil; a.center = 1; a.N = 2 * C; a.NT = 2 * C / 64; a.mode = SP_GATE;
+          a.bias = d.layers[l].bias_gate_tc; a.oh = pl[n][2]; a.ol = pl[n][3]; a.ldh = C;
+          slot(k++) = a;
+          SPhase b = zp;
+          b.a1 = MB + 2; b.w1 = W_L0 + 6 * l + 4; b.kchunks = C / 64; b.N = 2 * C; b.NT = 2 * C / 64; b.mode = SP_RES_SKIP;
+          b.bias = d.layers[l].outp.bias; b.res = x[n]; b.ld_res = C; b.out = x[n]; b.ldo = C; b.beta = 0.70710678118654752440f;
+          if (l + 1 < L) { b.oh = pl[n][0]; b.ol = pl[n][1]; b.ldh = C; b.vec2 = dt + (size_t)(l + 1) * C; }
+          b.skip = skip[n]; b.ld_skip = C; b.C = C; b.skip_init = (l == 0);
+          if (l == L - 1) { b.sh = pl[n][6]; b.sl = pl[n][7]; }
+          slot(k++) = b;
+        }
+        {
+          SPhase q = zp;
+          q.a1 = MB + 6; q.w1 = W_SKIP; q.kchunks = C / 64; q.N = d.skip_tc.N; q.NT = d.skip_tc.N / 64; q.mode = SP_SKIPPROJ;
+          q.bias = d.skip_bias_pad; q.oh = pl[n][8]; q.ol = pl[n][9]; q.ldh = C; q.n_valid = C;
+          slot(k++) = q;
+        }
+        {
+          SPhase q = zp;
+          q.a1 = MB + 8; q.w1 = W_OUT; q.kchunks = C / 64; q.N = d.out_tc.N; q.NT = d.out_tc.N / 64; q.mode = SP_F0_SAMPLE;
+          q.bias = d.out_bias_pad; q.out = z[n]; q.uv = uv[n]; q.clip_lo = lo; q.clip_hi = hi;
+          q.tab = d.gtab + (size_t)t * 8; q.tab2 = d.mtab + (size_t)t * 8; q.tstep = t; q.log_eps = m.log_eps;
+          q.noise = gnoise[n] ? gnoise[n] + per * (size_t)(T - t) : nullptr;
+          q.noise2 = unoise[n] ? unoise[n] + per * 2 * (size_t)(T - 1 - t) : nullptr;
+          q.seed = seed; q.stream_id = sbase + 10 + 2 * (uint64_t)t;
+          q.has_next = t > 0; q.C = C; q.in_w = d.in_w; q.in_b = d.in_b; q.uv_emb = d.uv_emb; q.x_next = x[n];
+          q.oh = pl[n][0]; q.ol = pl[n][1]; q.ldh = C;
+          q.vec2 = t > 0 ? d.dtab + (size_t)(t - 1) * L * C : nullptr;
+          slot(k++) = q;
+        }
+      }
+    }
+    // net 1's tile groups start where net 0's end, so one phase pair spreads over all clusters
+    for (size_t i = 1; i < ph.size(); i += 2) ph[i].goff = (s.ntiles * (ph[i - 1].NT / CS)) % ncl;
+    SSB_CUDA(cudaMemcpyAsync(maps_dev, maps.data(), sizeof(CUtensorMap) * nmaps, cudaMemcpyHostToDevice, c.stream));
+    SSB_CUDA(cudaMemcpyAsync(ph_dev, ph.data(), sizeof(SPhase) * nph, cudaMemcpyHostToDevice, c.stream));
+    RUN(launch_sampler_tc(c, maps_dev, ph_dev, nph, s.tiles, s.tile_tight, s.ntiles, 2 * (2 * C / 64), ctr, CS));
+  }
+  c.release(mk);
+  return 0;
+}
+bool f0_pair_persistent_ok(const Model& m, const SeqDev& s) {
+  if (!m.persistent || !m.use_tc || s.ntiles > 48 || sampler_tc_max_ctas() <= 0) return false;
+  for (int n = 0; n < 2; ++n) {
+    const Denoiser& d = m.f0net[n];
+    if (!denoiser_tc_ok(m, d) || !d.skip_tc.ok || !d.out_tc.ok || d.T <= 0) return false;
+  }
+  return m.f0net[0].C == m.f0net[1].C && m.f0net[0].L == m.f0net[1].L && m.f0net[0].T == m.f0net[1].T;
 }
 
 // a13+a14: GaussianMultinomialDiffusion.sample (gaussian_multinomial_diffusion.py:921-942)

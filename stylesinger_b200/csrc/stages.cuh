@@ -26,6 +26,10 @@ int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond
                       const float* noise, uint64_t seed, float* mel_tight);
 int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const float* cond_g, const float* lo,
                      const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv);
+int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, const float* cond0, const float* cond1,
+                                     const float* lo, const float* hi, const float* const gnoise[2],
+                                     const float* const unoise[2], uint64_t seed, float* const z[2], int32_t* const uv[2]);
+bool f0_pair_persistent_ok(const Model& m, const SeqDev& s);
 int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight, const float* f0_tight,
                 const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_tight);
 int denoiser_eval_api(Ctx& c, const Model& m, int which, const SeqDev& s, const float* x_tight, const int32_t* uv_tight,

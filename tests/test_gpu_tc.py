@@ -125,3 +125,32 @@ def test_persistent_matches_per_launch_on_ragged_batch_philox():
     err = _maxabs(a, b)
     print("persistent vs per-launch (philox, ragged):", err)
     assert torch.isfinite(a).all() and err < 1e-3
+
+
+def test_f0_pair_persistent_matches_oracle_and_per_launch():
+    """Full forward (T=12 F0 steps, mel diffusion skipped) with injected noise: the persistent two-net F0 sampler
+    vs the per-launch path vs the oracle (pitch_pred, f0_denorm; UV decisions must not flip)."""
+    from stylesinger_b200 import synth
+    from stylesinger_b200.engine import pack_batch
+    from tests.common import engine_noise_from_stream, oracle_forward
+    T = 12
+    hp = hp_for(T)
+    u = synth.make_utterance(150 / 187.5, utt_idx=321, ref_frames=40, frames=150, phones=11)
+    r, _ = oracle_forward(u, hp, 555, skip_diffusion=True)
+    m = acoustic_engine(T)
+    pb = pack_batch([u]).to(DEV)
+    outs = {}
+    try:
+        for mode in ("persistent", "per_launch"):
+            m.set_persistent(mode == "persistent")
+            noise, _ = engine_noise_from_stream(555, T, T, 150, DEV)
+            outs[mode] = m.forward(pb, noise=noise, skip_mel_diffusion=True, want=("pitch_pred", "f0_denorm", "decoder_inp"))
+            for k in ("pitch_pred", "f0_denorm"):
+                outs[mode][k] = outs[mode][k].clone()
+    finally:
+        m.set_persistent(True)
+    for mode, o in outs.items():
+        e_pp = _maxabs(o["pitch_pred"], r["pitch_pred"][0])
+        e_f0 = _maxabs(o["f0_denorm"], r["f0_denorm"][0])
+        print(mode, "pitch_pred err", e_pp, "f0_denorm err (Hz)", e_f0)
+        assert e_pp < 1e-3 and e_f0 < 0.5
