@@ -360,10 +360,28 @@ class Vocoder:
     def set_tensor_cores(self, enable=True):
         return bool(lib.ssb_vocoder_set_tensor_cores(self._h, 1 if enable else 0))
 
+    max_frames_per_call = 24000  # ~0.9 MB of stage buffers per frame: bounds the workspace to ~20 GB
+
     def generate(self, mel, f0, frame_offsets, rand_ini=None, src_noise=None, seed=0):
-        """mel [sumF,80], f0 [sumF] or None (device, tight) -> wav [sumF*hop] (device)."""
+        """mel [sumF,80], f0 [sumF] or None (device, tight) -> wav [sumF*hop] (device).
+        Large batches are processed in groups of utterances (results are per-utterance, so grouping is exact)."""
         fo = np.ascontiguousarray(frame_offsets, np.int32)
         B = len(fo) - 1
+        if B > 1 and int(fo[-1]) > self.max_frames_per_call:
+            wav = torch.empty(int(fo[-1]) * self.hop, dtype=torch.float32, device=self.device)
+            b0 = 0
+            while b0 < B:
+                b1 = b0 + 1
+                while b1 < B and int(fo[b1 + 1] - fo[b0]) <= self.max_frames_per_call:
+                    b1 += 1
+                sub_fo = (fo[b0:b1 + 1] - fo[b0]).astype(np.int32)
+                a, e = int(fo[b0]), int(fo[b1])
+                w = self.generate(mel[a:e], None if f0 is None else f0[a:e], sub_fo,
+                                  None if rand_ini is None else rand_ini[b0:b1].contiguous(),
+                                  None if src_noise is None else src_noise[a * self.hop:e * self.hop], seed + b0)
+                wav[a * self.hop:e * self.hop] = w
+                b0 = b1
+            return wav
         n = lib.ssb_vocoder_workspace_bytes(self._h, fo.ctypes.data, B)
         if n == 0:
             check(-1, "ssb_vocoder_workspace_bytes")
