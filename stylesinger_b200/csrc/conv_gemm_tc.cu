@@ -9,6 +9,7 @@
 // smem ring: BN=128: 3 stages x 64 KB, BN=64: 4 stages x 48 KB; mbarriers: full/empty per stage,
 // tmem_full/tmem_empty per accumulator buffer.  BN=64 is picked for small problems (more CTAs in flight).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "conv_gemm_tc.cuh"
 #include "tc_common.cuh"
@@ -24,9 +25,9 @@ template <int BN>
 struct Cfg {
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // BN = 256: the whole 512-column TMEM
 };
 
 struct TCParams {
@@ -335,7 +336,7 @@ template <int BN>
 int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   const ConvTC& w = *p.w;
   const ConvTC& w2 = p.w2 ? *p.w2 : *p.w;
-  const int bi = BN == 128 ? 0 : 1;
+  const int bi = BN == 128 ? 0 : (BN == 64 ? 1 : 2);
   CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo;
   if (make_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
   if (make_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
@@ -368,6 +369,10 @@ int make_weight_maps(ConvTC* w) {
   }
   if (make_map(&w->tm_hi[1], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 64)) return -1;
   if (make_map(&w->tm_lo[1], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 64)) return -1;
+  if (w->N % 256 == 0) {
+    if (make_map(&w->tm_hi[2], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 256)) return -1;
+    if (make_map(&w->tm_lo[2], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 256)) return -1;
+  }
   w->ok = true;
   return 0;
 }
@@ -381,6 +386,7 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   if (!configured) {
     SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
     SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -396,6 +402,13 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   if (small) {
     tp.NT = w.N / 64;
     return launch<64>(ctx, p, tp, num_sms);
+  }
+  // large problems with N % 256 == 0: 256-wide tiles halve the A-operand bytes per FLOP (the kernel is bound by
+  // L2->SM operand traffic, profiles/r01_ncu_*), at the price of a 2-stage ring (2 x 96 KB) and the whole TMEM
+  static const bool wide_ok = getenv("SSB_TC_NO_BN256") == nullptr;
+  if (wide_ok && w.N % 256 == 0 && (!p.w2 || p.w2->N % 256 == 0) && (int64_t)p.ntiles * (w.N / 256) >= (int64_t)num_sms * 2) {
+    tp.NT = w.N / 256;
+    return launch<256>(ctx, p, tp, num_sms);
   }
   tp.NT = w.N / 128;
   return launch<128>(ctx, p, tp, num_sms);

@@ -23,7 +23,7 @@ namespace ssb {
 struct ConvTC {            // packed weights for the tensor-core path
   __half* W_hi = nullptr;  // [taps][N][Cin]
   __half* W_lo = nullptr;
-  CUtensorMap tm_hi[2], tm_lo[2];  // [0]: box 128 rows (BN=128), [1]: box 64 rows (BN=64)
+  CUtensorMap tm_hi[3], tm_lo[3];  // [0]: box 128 rows (BN=128), [1]: box 64 rows (BN=64), [2]: box 256 rows (BN=256)
   int taps = 1, Cin = 0, N = 0, dil = 1, center = 0;
   const float* bias = nullptr;  // [N] (packed column order)
   bool ok = false;

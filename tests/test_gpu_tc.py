@@ -38,15 +38,17 @@ def test_conv1d_tc_matches_torch(cin, n, k, dil):
     assert worst < 1e-4  # tensor-core fp32 accumulation truncates: ~1e-5 relative after 144 chained MMAs
 
 
-def test_conv1d_tc_large_problem_uses_wide_tiles():
-    """> 2 waves of 128-wide tiles: exercises the BN=128 / 3-stage instantiation and the persistent tile loop."""
+@pytest.mark.parametrize("n_out", [512, 384])
+def test_conv1d_tc_large_problem_uses_wide_tiles(n_out):
+    """> 2 waves of tiles: N=512 exercises the BN=256 / 2-stage instantiation, N=384 the BN=128 / 3-stage one,
+    both with the persistent tile loop and TMEM double buffering."""
     from stylesinger_b200.engine import op_conv1d_tc
     g = torch.Generator().manual_seed(11)
     lens = [2800, 1500, 2999, 700, 2100, 1900, 2500, 3000, 1234, 2222]
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     x = torch.randn(int(offs[-1]), 256, generator=g)
-    w = torch.randn(512, 256, 3, generator=g) / (256 * 3) ** 0.5
-    b = torch.randn(512, generator=g)
+    w = torch.randn(n_out, 256, 3, generator=g) / (256 * 3) ** 0.5
+    b = torch.randn(n_out, generator=g)
     y = op_conv1d_tc(x.to(DEV), offs, w, b, dilation=4).cpu()
     worst = 0.0
     for i in (0, 3, 9):
