@@ -403,9 +403,10 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
     tp.NT = w.N / 64;
     return launch<64>(ctx, p, tp, num_sms);
   }
-  // large problems with N % 256 == 0: 256-wide tiles halve the A-operand bytes per FLOP (the kernel is bound by
-  // L2->SM operand traffic, profiles/r01_ncu_*), at the price of a 2-stage ring (2 x 96 KB) and the whole TMEM
-  static const bool wide_ok = getenv("SSB_TC_NO_BN256") == nullptr;
+  // 256-wide tiles halve the A-operand bytes per FLOP (the kernel is bound by L2->SM operand traffic,
+  // profiles/r01_ncu_*) but leave room for only a 2-stage ring (2 x 96 KB) and use the whole TMEM.  Measured on the
+  // batch64 mel stage: 1587 ms vs 1441 ms with 128-wide tiles / 3 stages, so it is opt-in (SSB_TC_BN256=1) only.
+  static const bool wide_ok = getenv("SSB_TC_BN256") != nullptr;
   if (wide_ok && w.N % 256 == 0 && (!p.w2 || p.w2->N % 256 == 0) && (int64_t)p.ntiles * (w.N / 256) >= (int64_t)num_sms * 2) {
     tp.NT = w.N / 256;
     return launch<256>(ctx, p, tp, num_sms);
