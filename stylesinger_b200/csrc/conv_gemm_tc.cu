@@ -43,7 +43,7 @@ struct Pre {
   float4 a[8];
 };
 __device__ __forceinline__ void prefetch32(const EpiTC& e, int64_t r, int n, bool valid, Pre& p) {
-  if (!valid) return;
+  if (!valid || (e.n_valid > 0 && n >= e.n_valid)) return;
   if (e.mode == EPI_GENERIC) {
     if (e.res) {
       const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
@@ -66,6 +66,7 @@ __device__ __forceinline__ void prefetch32(const EpiTC& e, int64_t r, int n, boo
 
 // fused epilogue for 32 consecutive columns [n, n+32) of row r
 __device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, const uint32_t (&raw)[32], const Pre& pre) {
+  if (e.n_valid > 0 && n >= e.n_valid) return;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n + j) : 0.0f);
@@ -95,15 +96,19 @@ __device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, con
         split_store16(e.oh + r * e.ldh + n + 16, e.ol + r * e.ldh + n + 16, v + 16);
       }
     } else {
-      float4* sp = reinterpret_cast<float4*>(e.skip + r * e.ld_skip + (n - e.C));
+      const int sc = n - e.C;
+      float4* sp = reinterpret_cast<float4*>(e.skip + r * e.ld_skip + sc);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float4 s = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         if (!e.skip_init) {
           const float4 o = pre.a[q];
-          s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+          v[4 * q] += o.x; v[4 * q + 1] += o.y; v[4 * q + 2] += o.z; v[4 * q + 3] += o.w;
         }
-        sp[q] = s;
+        sp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (e.sh) {
+        split_store16(e.sh + r * e.C + sc, e.sl + r * e.C + sc, v);
+        split_store16(e.sh + r * e.C + sc + 16, e.sl + r * e.C + sc + 16, v + 16);
       }
     }
     return;
@@ -136,6 +141,10 @@ __device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, con
     for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   if (e.oh) {
+    if (e.vec2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __ldg(e.vec2 + n + j);
+    }
     if (e.plane_act == ACT_LRELU) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * e.plane_slope;

@@ -134,6 +134,7 @@ struct VocStage {
   struct RB { Conv c1[3], c2[3]; ConvTC c1_tc[3], c2_tc[3]; } rb[4];
   ConvTC up_tc;     // tensor-core packing of the transposed conv
   bool res_tc = false;  // all ResBlock convs of this stage are tensor-core eligible (C % 64 == 0)
+  bool paired = false;  // C == 32: ResBlock convs packed as 64-channel convs over PAIRS of time steps (see pack.cu)
 };
 struct Vocoder {
   DevicePool pool;

@@ -136,6 +136,42 @@ static int pack_conv_tc_wn(DevicePool& pool, const HostTensor* v, const HostTens
   t.shape = v->shape;
   return pack_conv_tc(pool, &t, dil, PACK_PLAIN, packed_bias, out);
 }
+// Narrow convs (C = 32) on the 64-wide tensor-core K block: view [rows, 32] as [rows/2, 64] (two consecutive time
+// steps per "super row", super channel = phase*32 + c).  y[2q+phi, n] = sum_j sum_c W[n][c][j] x[2q + phi + s_j, c]
+// with s_j = (j - cen)*d becomes a conv over super rows with taps delta = floor((phi + s_j)/2) and input phase
+// (phi + s_j) mod 2:  W'[delta][phi'*32 + c][phi*32 + n] = W[n][c][j].  Half of each 64x64 block is zero, which the
+// tensor cores absorb easily (the fp32 FFMA kernel ran these convs at ~15 TFLOP/s).
+static int pack_conv_paired_tc(DevicePool& pool, const HostTensor* v, const HostTensor* g, int dil, const float* bias_host,
+                               ConvTC* out, float** bias_pair) {
+  if (!v || !g) return -1;
+  const int N = (int)v->shape[0], Cin = (int)v->shape[1], k = (int)v->shape[2];
+  if (N != 32 || Cin != 32 || k % 2 == 0) return 0;
+  std::vector<float> w;
+  fold_weight_norm(v, g, w);
+  const int cen = (k - 1) / 2, reach = cen * dil;
+  auto fdiv2 = [](int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); };  // floor(a / 2)
+  const int dmin = fdiv2(-reach), dmax = fdiv2(1 + reach), taps = dmax - dmin + 1;
+  std::vector<float> t((size_t)64 * 64 * taps, 0.f);  // torch conv layout [N'=64][Cin'=64][taps]
+  for (int phi = 0; phi < 2; ++phi)
+    for (int j = 0; j < k; ++j) {
+      const int s = (j - cen) * dil;
+      const int delta = fdiv2(phi + s), ph_in = (phi + s) - 2 * delta;
+      for (int n = 0; n < 32; ++n)
+        for (int c = 0; c < 32; ++c)
+          t[((size_t)(phi * 32 + n) * 64 + (ph_in * 32 + c)) * taps + (delta - dmin)] = w[((size_t)n * 32 + c) * k + j];
+    }
+  std::vector<float> b2(64, 0.f);
+  if (bias_host)
+    for (int i = 0; i < 64; ++i) b2[i] = bias_host[i % 32];
+  *bias_pair = pool.upload(b2);
+  HostTensor ht;
+  ht.data = t.data();
+  ht.shape = {64, 64, taps};
+  if (pack_conv_tc(pool, &ht, 1, PACK_PLAIN, *bias_pair, out)) return -1;
+  if (out->ok && out->center != -dmin) return -1;  // symmetric by construction
+  return 0;
+}
+
 // weight-normed ConvTranspose1d (k = 2u) -> 3-tap conv with N = u*Cout -> tensor-core packing
 static int pack_conv_transpose_tc(DevicePool& pool, const HostTensor* v, const HostTensor* g, int u, const float* packed_bias, ConvTC* out) {
   if (!v || !g) return -1;
@@ -462,6 +498,15 @@ int build_vocoder(TensorMap& tm, const ssb_vocoder_config& cfg, Vocoder* v) {
           PK(pack_conv_tc_wn(pool, tm.get(a + "weight_v"), tm.get(a + "weight_g"), cfg.res_dilations[j][mI], s.rb[j].c1[mI].bias, &s.rb[j].c1_tc[mI]));
           PK(pack_conv_tc_wn(pool, tm.get(b2 + "weight_v"), tm.get(b2 + "weight_g"), 1, s.rb[j].c2[mI].bias, &s.rb[j].c2_tc[mI]));
           if (!s.rb[j].c1_tc[mI].ok || !s.rb[j].c2_tc[mI].ok) s.res_tc = false;
+          if (s.Cout == 32) {  // narrow stage: time-paired packing instead
+            const HostTensor* b1 = tm.get(a + "bias");
+            const HostTensor* b3 = tm.get(b2 + "bias");
+            float* bp = nullptr;
+            PK(pack_conv_paired_tc(pool, tm.get(a + "weight_v"), tm.get(a + "weight_g"), cfg.res_dilations[j][mI], b1 ? b1->data : nullptr, &s.rb[j].c1_tc[mI], &bp));
+            PK(pack_conv_paired_tc(pool, tm.get(b2 + "weight_v"), tm.get(b2 + "weight_g"), 1, b3 ? b3->data : nullptr, &s.rb[j].c2_tc[mI], &bp));
+            if (mI == 0 && j == 0) s.paired = true;
+            if (!s.rb[j].c1_tc[mI].ok || !s.rb[j].c2_tc[mI].ok) s.paired = false;
+          }
         }
       }
       c /= 2;

@@ -323,6 +323,7 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
         g.e.out = b.x; g.e.ldo = C;
         if (l + 1 < L) { g.e.oh = b.yh; g.e.ol = b.yl; g.e.ldh = C; g.e.vec2 = dt + (size_t)(l + 1) * C; }
         g.e.skip = b.skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
+        if (b.tc_heads && l == L - 1) { g.e.sh = b.skh; g.e.sl = b.skl; }
         RUN(conv_gemm_tc(c, g));
       }
       continue;
@@ -340,6 +341,23 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
       g.e.skip = b.skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
       RUN(conv_gemm(c, g));
     }
+  }
+  if (b.tc_heads) {
+    {  // skip_projection (1/sqrt(L) folded into the packed weights) + ReLU -> planes
+      GemmTC g;
+      g.A_hi = b.skh; g.A_lo = b.skl; g.rows_total = s.rows; g.w = &d.skip_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+      g.e.mode = EPI_GENERIC; g.e.bias = d.skip_bias_pad; g.e.act = ACT_RELU; g.e.oh = b.sh; g.e.ol = b.sl; g.e.ldh = C;
+      g.e.n_valid = C;
+      RUN(conv_gemm_tc(c, g));
+    }
+    {  // output_projection (N padded to a tile multiple; only the first out_dims columns are meaningful)
+      GemmTC g;
+      g.A_hi = b.sh; g.A_lo = b.sl; g.rows_total = s.rows; g.w = &d.out_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+      g.e.mode = EPI_GENERIC; g.e.bias = d.out_bias_pad; g.e.out = b.head; g.e.ldo = b.ld_head;
+      g.e.n_valid = (d.out_dims + 31) / 32 * 32;
+      RUN(conv_gemm_tc(c, g));
+    }
+    return 0;
   }
   {
     ConvGemm g = make_gemm(d.skip_proj, s, b.skip, C);
@@ -371,7 +389,19 @@ int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, Denoiser
   b->x = alloc_rows(c, s, d.C);
   b->y = b->zg = nullptr;
   b->yh = b->yl = b->zh = b->zl = b->ch = b->cl = nullptr;
+  b->skh = b->skl = b->sh = b->sl = b->x80h = b->x80l = nullptr;
   b->condall = nullptr;
+  b->tc_heads = tc && d.skip_tc.ok && d.out_tc.ok;
+  if (b->tc_heads) {
+    b->skh = alloc_half_rows(c, s, d.C);
+    b->skl = alloc_half_rows(c, s, d.C);
+    b->sh = alloc_half_rows(c, s, d.C);
+    b->sl = alloc_half_rows(c, s, d.C);
+    if (!d.ddiff && d.in_tc.ok) {
+      b->x80h = alloc_half_rows(c, s, 128);
+      b->x80l = alloc_half_rows(c, s, 128);
+    }
+  }
   if (tc) {
     b->yh = alloc_half_rows(c, s, d.C);
     b->yl = alloc_half_rows(c, s, d.C);
@@ -385,8 +415,8 @@ int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, Denoiser
     b->condall = alloc_rows(c, s, d.L * 2 * d.C, false);
   }
   b->skip = alloc_rows(c, s, d.C);
-  b->sbuf = alloc_rows(c, s, d.C);
-  b->ld_head = (d.out_dims + 3) & ~3;
+  b->sbuf = b->tc_heads ? nullptr : alloc_rows(c, s, d.C);
+  b->ld_head = b->tc_heads ? d.out_tc.N : ((d.out_dims + 3) & ~3);
   b->head = alloc_rows(c, s, b->ld_head);
   WS_OK(c);
   return 0;
@@ -402,6 +432,15 @@ int prepare_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g
 
 // a18 entry for one evaluation (mel): x80 [rows,80] guarded -> head
 int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const float* x80, DenoiserBufs& b) {
+  if (b.x80h) {  // tensor-core input projection: K padded 80 -> 128
+    RUN(x80_planes(c, x80, s.rows, b.x80h, b.x80l));
+    GemmTC g;
+    g.A_hi = b.x80h; g.A_lo = b.x80l; g.rows_total = s.rows; g.w = &d.in_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+    g.e.mode = EPI_GENERIC; g.e.bias = d.in_proj.bias; g.e.act = ACT_RELU; g.e.out = b.x; g.e.ldo = d.C;
+    g.e.oh = b.yh; g.e.ol = b.yl; g.e.ldh = d.C; g.e.vec2 = d.dtab + (size_t)t * d.L * d.C;
+    RUN(conv_gemm_tc(c, g));
+    return denoiser_stack(c, d, s, t, b);
+  }
   ConvGemm g = make_gemm(d.in_proj, s, x80, 80);
   g.e.act = ACT_RELU; g.e.out = b.x; g.e.ldo = d.C;
   g.e.vec2 = d.dtab + (size_t)t * d.L * d.C;
@@ -740,7 +779,15 @@ int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight
     SeqDev so;
     RUN(upload_layout(c, seq, rate_out, &so));
     const bool up_tc = tc && st.up_tc.ok && pin_h != nullptr;
-    const bool res_tc = tc && st.res_tc;
+    const bool paired = tc && st.paired && (rate_out % 2 == 0);
+    const bool res_tc = tc && (st.res_tc || paired);
+    // paired stage: [rows, 32] is processed as [rows/2, 64] (same memory) with the time-paired weight packing
+    SeqDev sw = so;
+    const int Cw = paired ? 2 * Co : Co;
+    if (paired) {
+      RUN(upload_layout(c, seq, rate_out / 2, &sw));
+      sw.rows = so.rows / 2;  // exactly the memory of the [so.rows, Co] buffers (TMA zero-fills beyond)
+    }
     const bool next_up_tc = tc && i + 1 < v.stages.size() && v.stages[i + 1].up_tc.ok;
     float* xu = alloc_rows(c, so, Co);
     float* r = alloc_rows(c, so, Co);
@@ -781,18 +828,18 @@ int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight
         if (res_tc) {
           {
             GemmTC g;  // xt = c1(leaky_relu(r)) ; only leaky_relu(xt) is ever consumed -> planes only
-            g.A_hi = rin_h; g.A_lo = rin_l; g.rows_total = so.rows; g.w = &st.rb[j].c1_tc[mI]; g.tiles = so.tiles; g.ntiles = so.ntiles;
-            g.e.mode = EPI_GENERIC; g.e.oh = pt_h; g.e.ol = pt_l; g.e.ldh = Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f;
+            g.A_hi = rin_h; g.A_lo = rin_l; g.rows_total = sw.rows; g.w = &st.rb[j].c1_tc[mI]; g.tiles = sw.tiles; g.ntiles = sw.ntiles;
+            g.e.mode = EPI_GENERIC; g.e.oh = pt_h; g.e.ol = pt_l; g.e.ldh = Cw; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f;
             RUN(conv_gemm_tc(c, g));
           }
           GemmTC g;  // r = c2(leaky_relu(xt)) + r
-          g.A_hi = pt_h; g.A_lo = pt_l; g.rows_total = so.rows; g.w = &st.rb[j].c2_tc[mI]; g.tiles = so.tiles; g.ntiles = so.ntiles;
-          g.e.mode = EPI_GENERIC; g.e.res = rin; g.e.ld_res = Co;
+          g.A_hi = pt_h; g.A_lo = pt_l; g.rows_total = sw.rows; g.w = &st.rb[j].c2_tc[mI]; g.tiles = sw.tiles; g.ntiles = sw.ntiles;
+          g.e.mode = EPI_GENERIC; g.e.res = rin; g.e.ld_res = Cw;
           if (!last) {
-            g.e.out = r; g.e.ldo = Co; g.e.oh = pr_h; g.e.ol = pr_l; g.e.ldh = Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f;
+            g.e.out = r; g.e.ldo = Cw; g.e.oh = pr_h; g.e.ol = pr_l; g.e.ldh = Cw; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f;
           } else {
-            g.e.out = acc; g.e.ldo = Co; g.e.accum = (j > 0); g.e.gamma = lastj ? 1.0f / (float)v.nk : 1.0f;
-            if (lastj && next_up_tc) { g.e.oh = pa_h; g.e.ol = pa_l; g.e.ldh = Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
+            g.e.out = acc; g.e.ldo = Cw; g.e.accum = (j > 0); g.e.gamma = lastj ? 1.0f / (float)v.nk : 1.0f;
+            if (lastj && next_up_tc) { g.e.oh = pa_h; g.e.ol = pa_l; g.e.ldh = Cw; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
           }
           RUN(conv_gemm_tc(c, g));
           rin = r; rin_h = pr_h; rin_l = pr_l;

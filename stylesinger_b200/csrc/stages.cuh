@@ -14,6 +14,9 @@ struct DenoiserBufs {
   float *x, *y, *zg, *skip, *sbuf, *head, *condall;
   __half *yh, *yl, *zh, *zl;  // tensor-core path: fp16 hi/lo planes of y = x + step bias and of the gate output
   __half *ch, *cl;            // tensor-core path: fp16 hi/lo planes of the conditioner [rows,256]
+  __half *skh, *skl, *sh, *sl;  // tensor-core heads: planes of the skip sum and of relu(skip_proj)
+  __half *x80h, *x80l;          // mel net, tensor-core in_proj: planes of x_t padded to 128 columns
+  bool tc_heads;
   int ld_head;
   bool tc;
 };
