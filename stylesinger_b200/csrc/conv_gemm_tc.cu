@@ -20,141 +20,160 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE = BM * BK * 2;  // 16 KB
+constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;  // epilogue transpose buffers: 4 warps x [32 x 32] fp32
 
 template <int BN>
 struct Cfg {
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE + XPOSE_BYTES + 1024 + 256;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // BN = 256: the whole 512-column TMEM
 };
 
 struct TCParams {
   const int2* tiles;
   int ntiles, NT, taps, kchunks, kchunks2, dil, center, N;
+  int dbg;  // SSB_TC_DEBUG probe bits (tools/gemm_probe.py): 1 = epilogue drains TMEM only, 2 = no MMAs, 4 = no TMA loads
   EpiTC e;
 };
 
 using namespace tc;
 
-// Global operands of the epilogue for 32 columns [n, n+32) of row r, fetched ahead of use.
+// ---- epilogue ------------------------------------------------------------------------------------------------
+// tcgen05.ld hands every lane one ROW of the accumulator (32 consecutive columns).  Writing rows straight from that
+// mapping makes each warp store touch 32 different 128-byte lines (16 B each); measured with tools/gemm_probe.py the
+// epilogue alone then costs as much as the MMAs.  So each epilogue warp transposes its 32 x 32 chunk through a 4 KB
+// shared-memory buffer (float4 chunks XOR-swizzled by row: conflict-free both ways) and works in a COALESCED mapping:
+// step i of 8 handles rows 4i + lane/8, columns 4*(lane%8) .. +3, i.e. every warp access covers 4 full 128-byte lines.
+
 struct Pre {
-  float4 a[8];
+  float4 a[8];  // epilogue global operands (residual / skip) of the 8 steps of one chunk, fetched ahead of use
 };
-__device__ __forceinline__ void prefetch32(const EpiTC& e, int64_t r, int n, bool valid, Pre& p) {
-  if (!valid || (e.n_valid > 0 && n >= e.n_valid)) return;
-  if (e.mode == EPI_GENERIC) {
-    if (e.res) {
-      const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) p.a[q] = rp[q];
-    }
-    return;
-  }
-  if (e.mode != EPI_RES_SKIP) return;
-  if (n < e.C) {
-    const float4* rp = reinterpret_cast<const float4*>(e.res + r * e.ld_res + n);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) p.a[q] = rp[q];
-  } else if (!e.skip_init) {
-    const float4* sp = reinterpret_cast<const float4*>(e.skip + r * e.ld_skip + (n - e.C));
-#pragma unroll
-    for (int q = 0; q < 8; ++q) p.a[q] = sp[q];
-  }
-}
 
-// fused epilogue for 32 consecutive columns [n, n+32) of row r
-__device__ __forceinline__ void epilogue32(const EpiTC& e, int64_t r, int n, const uint32_t (&raw)[32], const Pre& pre) {
+// rows of this warp: r0 + [0, 32); nrows valid ones.  Lane's row in step i: 4i + (lane >> 3); columns n4 .. n4+3.
+template <int MODE>
+__device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int nrows, int n, int lane, Pre& p) {
   if (e.n_valid > 0 && n >= e.n_valid) return;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + (e.bias ? __ldg(e.bias + n + j) : 0.0f);
-  if (e.mode == EPI_GATE) {
-    float z[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) z[q] = sigmoidf_(v[2 * q]) * tanhf(v[2 * q + 1]);
-    split_store16(e.oh + r * e.ldh + (n >> 1), e.ol + r * e.ldh + (n >> 1), z);
+  const float* src = nullptr;
+  int ld = 0;
+  if constexpr (MODE == EPI_GENERIC) {
+    if (!e.res) return;
+    src = e.res + n; ld = e.ld_res;
+  } else if constexpr (MODE == EPI_RES_SKIP) {
+    if (n < e.C) { src = e.res + n; ld = e.ld_res; }
+    else if (!e.skip_init) { src = e.skip + (n - e.C); ld = e.ld_skip; }
+    else return;
+  } else {
     return;
   }
-  if (e.mode == EPI_RES_SKIP) {
-    if (n < e.C) {
-      float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n);
+  src += (lane & 7) * 4;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 x0 = pre.a[q];
-        v[4 * q] = (v[4 * q] + x0.x) * e.beta;
-        v[4 * q + 1] = (v[4 * q + 1] + x0.y) * e.beta;
-        v[4 * q + 2] = (v[4 * q + 2] + x0.z) * e.beta;
-        v[4 * q + 3] = (v[4 * q + 3] + x0.w) * e.beta;
-        op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-      if (e.oh) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(e.vec2 + n + j);
-        split_store16(e.oh + r * e.ldh + n, e.ol + r * e.ldh + n, v);
-        split_store16(e.oh + r * e.ldh + n + 16, e.ol + r * e.ldh + n + 16, v + 16);
-      }
-    } else {
-      const int sc = n - e.C;
-      float4* sp = reinterpret_cast<float4*>(e.skip + r * e.ld_skip + sc);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (!e.skip_init) {
-          const float4 o = pre.a[q];
-          v[4 * q] += o.x; v[4 * q + 1] += o.y; v[4 * q + 2] += o.z; v[4 * q + 3] += o.w;
-        }
-        sp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-      if (e.sh) {
-        split_store16(e.sh + r * e.C + sc, e.sl + r * e.C + sc, v);
-        split_store16(e.sh + r * e.C + sc + 16, e.sl + r * e.C + sc + 16, v + 16);
-      }
-    }
-    return;
-  }
-  // EPI_GENERIC
-  if (e.act == ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (e.act == ACT_LRELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * e.act_slope;
-  }
-  if (e.res) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      v[4 * q] += pre.a[q].x; v[4 * q + 1] += pre.a[q].y; v[4 * q + 2] += pre.a[q].z; v[4 * q + 3] += pre.a[q].w;
-    }
-  }
-  if (e.out) {
-    float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n);
-    if (e.accum) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 o = op[q];
-        v[4 * q] = (v[4 * q] + o.x) * e.gamma; v[4 * q + 1] = (v[4 * q + 1] + o.y) * e.gamma;
-        v[4 * q + 2] = (v[4 * q + 2] + o.z) * e.gamma; v[4 * q + 3] = (v[4 * q + 3] + o.w) * e.gamma;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  }
-  if (e.oh) {
-    if (e.vec2) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += __ldg(e.vec2 + n + j);
-    }
-    if (e.plane_act == ACT_LRELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * e.plane_slope;
-    }
-    split_store16(e.oh + r * e.ldh + n, e.ol + r * e.ldh + n, v);
-    split_store16(e.oh + r * e.ldh + n + 16, e.ol + r * e.ldh + n + 16, v + 16);
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    if (rr < nrows) p.a[i] = *reinterpret_cast<const float4*>(src + (r0 + rr) * ld);
   }
 }
 
-template <int BN>
+__device__ __forceinline__ void split_store4(__half* hi, __half* lo, float a, float b, float c, float d) {
+  const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(a - f0.x, b - f0.y), l1 = __floats2half2_rn(c - f1.x, d - f1.y);
+  uint2 uh, ul;
+  uh.x = *reinterpret_cast<const uint32_t*>(&h0); uh.y = *reinterpret_cast<const uint32_t*>(&h1);
+  ul.x = *reinterpret_cast<const uint32_t*>(&l0); ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(hi) = uh;
+  *reinterpret_cast<uint2*>(lo) = ul;
+}
+__device__ __forceinline__ void split_store2(__half* hi, __half* lo, float a, float b) {
+  const __half2 h0 = __floats2half2_rn(a, b);
+  const float2 f0 = __half22float2(h0);
+  const __half2 l0 = __floats2half2_rn(a - f0.x, b - f0.y);
+  *reinterpret_cast<__half2*>(hi) = h0;
+  *reinterpret_cast<__half2*>(lo) = l0;
+}
+
+// One 32 x 32 accumulator chunk (columns [n, n+32)) of this warp: transpose, then the fused epilogue.
+// MODE is a template parameter (and the chunk loop is not unrolled) to keep the epilogue's code small: the first
+// version carried all three modes x 4-8 unrolled chunks = 13k SASS instructions and ran out of the instruction cache.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64_t r0, int nrows, int n, int lane,
+                                               const uint32_t (&raw)[32], const Pre& pre) {
+  if (e.n_valid > 0 && n >= e.n_valid) return;  // warp-uniform
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    xb[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                                  __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+  __syncwarp();
+  const int q = lane & 7;
+  const int n4 = n + 4 * q;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  if (e.bias) { b0 = __ldg(e.bias + n4); b1 = __ldg(e.bias + n4 + 1); b2 = __ldg(e.bias + n4 + 2); b3 = __ldg(e.bias + n4 + 3); }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // step bias folded into the planes
+  const bool planes_vec2 = e.vec2 != nullptr && e.oh != nullptr && (MODE == EPI_GENERIC || (MODE == EPI_RES_SKIP && n < e.C));
+  if (planes_vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    if (rr >= nrows) continue;
+    const int64_t r = r0 + rr;
+    const float4 acc = xb[rr * 8 + (q ^ (rr & 7))];
+    float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
+    if constexpr (MODE == EPI_GATE) {
+      const float z0 = sigmoidf_(v0) * tanhf(v1), z1 = sigmoidf_(v2) * tanhf(v3);
+      split_store2(e.oh + r * e.ldh + (n4 >> 1), e.ol + r * e.ldh + (n4 >> 1), z0, z1);
+      continue;
+    }
+    if constexpr (MODE == EPI_RES_SKIP) {
+      if (n < e.C) {
+        const float4 x0 = pre.a[i];
+        v0 = (v0 + x0.x) * e.beta; v1 = (v1 + x0.y) * e.beta; v2 = (v2 + x0.z) * e.beta; v3 = (v3 + x0.w) * e.beta;
+        *reinterpret_cast<float4*>(e.out + r * e.ldo + n4) = make_float4(v0, v1, v2, v3);
+        if (e.oh) split_store4(e.oh + r * e.ldh + n4, e.ol + r * e.ldh + n4, v0 + s0, v1 + s1, v2 + s2, v3 + s3);
+      } else {
+        const int sc = n4 - e.C;
+        if (!e.skip_init) {
+          const float4 o = pre.a[i];
+          v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
+        }
+        *reinterpret_cast<float4*>(e.skip + r * e.ld_skip + sc) = make_float4(v0, v1, v2, v3);
+        if (e.sh) split_store4(e.sh + r * e.C + sc, e.sl + r * e.C + sc, v0, v1, v2, v3);
+      }
+      continue;
+    }
+    if constexpr (MODE == EPI_GENERIC) {
+    if (e.act == ACT_RELU) {
+      v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+    } else if (e.act == ACT_LRELU) {
+      v0 = v0 > 0.f ? v0 : v0 * e.act_slope; v1 = v1 > 0.f ? v1 : v1 * e.act_slope;
+      v2 = v2 > 0.f ? v2 : v2 * e.act_slope; v3 = v3 > 0.f ? v3 : v3 * e.act_slope;
+    }
+    if (e.res) {
+      const float4 x0 = pre.a[i];
+      v0 += x0.x; v1 += x0.y; v2 += x0.z; v3 += x0.w;
+    }
+    if (e.out) {
+      float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n4);
+      if (e.accum) {
+        const float4 o = *op;
+        v0 = (v0 + o.x) * e.gamma; v1 = (v1 + o.y) * e.gamma; v2 = (v2 + o.z) * e.gamma; v3 = (v3 + o.w) * e.gamma;
+      }
+      *op = make_float4(v0, v1, v2, v3);
+    }
+    if (e.oh) {
+      v0 += s0; v1 += s1; v2 += s2; v3 += s3;
+      if (e.plane_act == ACT_LRELU) {
+        v0 = v0 > 0.f ? v0 : v0 * e.plane_slope; v1 = v1 > 0.f ? v1 : v1 * e.plane_slope;
+        v2 = v2 > 0.f ? v2 : v2 * e.plane_slope; v3 = v3 > 0.f ? v3 : v3 * e.plane_slope;
+      }
+      split_store4(e.oh + r * e.ldh + n4, e.ol + r * e.ldh + n4, v0, v1, v2, v3);
+    }
+    }
+  }
+  __syncwarp();  // the next chunk reuses the transpose buffer
+}
+
+template <int BN, int MODE>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -165,7 +184,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   constexpr int STAGES = K::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * K::STAGE);
+  float4* xpose = reinterpret_cast<float4*>(smem + STAGES * K::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * K::STAGE + XPOSE_BYTES);
   // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base address
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const uint32_t sbase = smem_u32(smem);
@@ -206,6 +226,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t fb = full0 + 8 * stage;
+          if (p.dbg & 4) {
+            mbar_arrive(fb);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(fb, K::STAGE);
           const uint32_t sa = sbase + stage * K::STAGE;
           if (kb < nk1) {
@@ -250,6 +275,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
           for (int ks = 0; ks < BK / 16; ++ks) {
             const uint64_t off = (uint64_t)((ks * 32) >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle atom
+            if (p.dbg & 2) continue;
             tc_mma(d_tmem, dah + off, dbh + off, idesc, (kb | ks) != 0 ? 1u : 0u);
             tc_mma(d_tmem, dah + off, dbl + off, idesc, 1u);
             tc_mma(d_tmem, dal + off, dbh + off, idesc, 1u);
@@ -269,19 +295,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const uint32_t aph = (it >> 1) & 1;
       const int mt = tile / p.NT, nt = tile - mt * p.NT;
       const int2 t = p.tiles[mt];
-      const int rl = ew * 32 + lane;
-      const bool valid = rl < t.y;
-      const int64_t r = (int64_t)t.x + rl;
+      const int64_t r0 = (int64_t)t.x + ew * 32;
+      const int nrows = min(32, max(0, t.y - ew * 32));
+      float4* xb = xpose + ew * 256;
       Pre cur, nxt;
-      prefetch32(p.e, r, nt * BN, valid, cur);  // issued before the accumulator is ready: overlaps the MMAs
+      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN, lane, cur);  // issued before the accumulator is ready: overlaps the MMAs
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
-        if (ch + 1 < NCH) prefetch32(p.e, r, nt * BN + (ch + 1) * 32, valid, nxt);
+        if (ch + 1 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 1) * 32, lane, nxt);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN + ch * 32), v);
-        if (valid) epilogue32(p.e, r, nt * BN + ch * 32, v, cur);
+        if (nrows > 0 && !(p.dbg & 1)) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
         cur = nxt;
       }
       tc_fence_before();
@@ -294,6 +320,185 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x (2*HB) tile.  Each CTA stages its own
+// 128 rows of A (its own row tile of the ragged layout: the two row tiles of a pair need not be adjacent) and HB of
+// the 2*HB weight rows; the leader issues M=256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.
+// Per FLOP this halves the bytes each SM pulls through L2 (the limiter of the single-CTA kernel, profiles/r01_ncu_*).
+//   full[s]    leader only: 1 arrival (leader's expect_tx of 2 x STAGE bytes) + both CTAs' TMA transaction bytes
+//   empty[s]   per CTA: signalled by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[a]   per CTA: same multicast commit;  tempty[a] leader only: 8 arrivals (4 epilogue warps x 2 CTAs)
+template <int HB>
+struct Cfg2 {
+  static constexpr int BN = 2 * HB;
+  static constexpr int B_TILE = HB * BK * 2;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = HB >= 96 ? 3 : (HB == 32 ? 5 : 4);
+  static constexpr int SMEM = STAGES * STAGE + XPOSE_BYTES + 1024 + 256;
+  static constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+};
+
+template <int HB, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                     const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
+                     const __grid_constant__ CUtensorMap tmB2_hi, const __grid_constant__ CUtensorMap tmB2_lo,
+                     const TCParams p) {
+  using K = Cfg2<HB>;
+  constexpr int STAGES = K::STAGES;
+  constexpr int BN = K::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float4* xpose = reinterpret_cast<float4*>(smem + STAGES * K::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * K::STAGE + XPOSE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int npairs = (p.ntiles + 1) >> 1;
+  const int total = npairs * p.NT;
+  const int nk1 = p.taps * p.kchunks;
+  const int nk = nk1 + p.kchunks2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t lfull0 = mapa_u32(full0, 0);  // the leader's full barriers (cluster address)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cid; tile < total; tile += ncl) {
+        const int mp = tile / p.NT, nt = tile - mp * p.NT;
+        int mt = 2 * mp + (int)rank;
+        if (mt >= p.ntiles) mt = 2 * mp;  // odd tile count: the peer duplicates the leader's rows, writes nothing
+        const int row0 = p.tiles[mt].x;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          if (p.dbg & 4) {
+            if (rank == 0) mbar_arrive(full0 + 8 * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * K::STAGE);
+          const uint32_t fb = lfull0 + 8 * stage;
+          const uint32_t sa = sbase + stage * K::STAGE;
+          if (kb < nk1) {
+            const int tap = kb / p.kchunks;
+            const int c0 = (kb - tap * p.kchunks) * BK;
+            const int arow = row0 + (tap - p.center) * p.dil;
+            const int brow = tap * p.N + nt * BN + (int)rank * HB;
+            tma_load_2d_pair(sa, &tmA_hi, fb, c0, arow);
+            tma_load_2d_pair(sa + A_TILE, &tmA_lo, fb, c0, arow);
+            tma_load_2d_pair(sa + 2 * A_TILE, &tmB_hi, fb, c0, brow);
+            tma_load_2d_pair(sa + 2 * A_TILE + K::B_TILE, &tmB_lo, fb, c0, brow);
+          } else {
+            const int c0 = (kb - nk1) * BK;
+            const int brow = nt * BN + (int)rank * HB;
+            tma_load_2d_pair(sa, &tmA2_hi, fb, c0, row0);
+            tma_load_2d_pair(sa + A_TILE, &tmA2_lo, fb, c0, row0);
+            tma_load_2d_pair(sa + 2 * A_TILE, &tmB2_hi, fb, c0, brow);
+            tma_load_2d_pair(sa + 2 * A_TILE + K::B_TILE, &tmB2_lo, fb, c0, brow);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor: D=F32, A=B=F16, both K-major, N = 2*HB, M = 256 (two CTAs x 128 rows)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cid; tile < total; tile += ncl, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * a, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * K::ACC_STRIDE;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * K::STAGE;
+          const uint64_t dah = make_sdesc(sa), dal = make_sdesc(sa + A_TILE);
+          const uint64_t dbh = make_sdesc(sa + 2 * A_TILE), dbl = make_sdesc(sa + 2 * A_TILE + K::B_TILE);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t off = (uint64_t)((ks * 32) >> 4);
+            if (p.dbg & 2) continue;
+            tc_mma_pair(d_tmem, dah + off, dbh + off, idesc, (kb | ks) != 0 ? 1u : 0u);
+            tc_mma_pair(d_tmem, dah + off, dbl + off, idesc, 1u);
+            tc_mma_pair(d_tmem, dal + off, dbh + off, idesc, 1u);
+          }
+          tc_commit_pair(empty0 + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(tfull0 + 8 * a);
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    constexpr int NCH = BN / 32;
+    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
+    int it = 0;
+    for (int tile = cid; tile < total; tile += ncl, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      const int mt = 2 * mp + (int)rank;
+      const bool have = mt < p.ntiles;
+      const int2 t = have ? p.tiles[mt] : make_int2(0, 0);
+      const int64_t r0 = (int64_t)t.x + ew * 32;
+      const int nrows = min(32, max(0, t.y - ew * 32));
+      float4* xb = xpose + ew * 256;
+      Pre cur, nxt;
+      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN, lane, cur);
+      mbar_wait(tfull0 + 8 * a, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ++ch) {
+        if (ch + 1 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 1) * 32, lane, nxt);
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * K::ACC_STRIDE + (uint32_t)(ch * 32), v);
+        if (nrows > 0 && !(p.dbg & 1)) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
+        cur = nxt;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its pair still reads / signals it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS) : "memory");
   }
 }
 
@@ -341,8 +546,14 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint
   return 0;
 }
 
-template <int BN>
-int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
+template <int BN, int MODE>
+int launch_m(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
+  using KCfg = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::SMEM));
+    configured = true;
+  }
   const ConvTC& w = *p.w;
   const ConvTC& w2 = p.w2 ? *p.w2 : *p.w;
   const int bi = BN == 128 ? 0 : (BN == 64 ? 1 : 2);
@@ -358,11 +569,57 @@ int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   }
   const int total = tp.ntiles * tp.NT;
   const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_tc_kernel<BN><<<grid, 256, Cfg<BN>::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm_hi[bi], w.tm_lo[bi], ta2_hi, ta2_lo,
-                                                                    w2.tm_hi[bi], w2.tm_lo[bi], tp);
+  conv_gemm_tc_kernel<BN, MODE><<<grid, 256, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm_hi[bi], w.tm_lo[bi], ta2_hi, ta2_lo,
+                                                                       w2.tm_hi[bi], w2.tm_lo[bi], tp);
   SSB_CUDA(cudaGetLastError());
   ++g_launches;
   return 0;
+}
+template <int BN>
+int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
+  switch (tp.e.mode) {
+    case EPI_GATE: return launch_m<BN, EPI_GATE>(ctx, p, tp, num_sms);
+    case EPI_RES_SKIP: return launch_m<BN, EPI_RES_SKIP>(ctx, p, tp, num_sms);
+    default: return launch_m<BN, EPI_GENERIC>(ctx, p, tp, num_sms);
+  }
+}
+
+template <int HB, int MODE>
+int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
+  using KCfg = Cfg2<HB>;
+  const ConvTC& w = *p.w;
+  const ConvTC& w2 = p.w2 ? *p.w2 : *p.w;
+  static bool configured = false;
+  if (!configured) {
+    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc2_kernel<HB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::SMEM));
+    configured = true;
+  }
+  CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo;
+  if (make_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (make_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (p.w2) {
+    if (make_map(&ta2_hi, p.A2_hi, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+    if (make_map(&ta2_lo, p.A2_lo, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+  } else {
+    ta2_hi = ta_hi;
+    ta2_lo = ta_lo;
+  }
+  tp.NT = w.N / (2 * HB);
+  const int total = ((tp.ntiles + 1) / 2) * tp.NT;
+  const int ncl = total < num_sms / 2 ? total : num_sms / 2;
+  conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, 256, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
+                                                                           w2.tm2_hi, w2.tm2_lo, tp);
+  SSB_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+template <int HB>
+int launch_pair(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
+  switch (tp.e.mode) {
+    case EPI_GATE: return launch_pair_m<HB, EPI_GATE>(ctx, p, tp, num_sms);
+    case EPI_RES_SKIP: return launch_pair_m<HB, EPI_RES_SKIP>(ctx, p, tp, num_sms);
+    default: return launch_pair_m<HB, EPI_GENERIC>(ctx, p, tp, num_sms);
+  }
 }
 
 }  // namespace
@@ -382,6 +639,18 @@ int make_weight_maps(ConvTC* w) {
     if (make_map(&w->tm_hi[2], w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 256)) return -1;
     if (make_map(&w->tm_lo[2], w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, 256)) return -1;
   }
+  // CTA-pair kernel: the widest half-tile hb in {128, 96, 64, 32} with N % (2*hb) == 0
+  w->hb = 0;
+  for (int hb : {128, 96, 64, 32}) {
+    if (w->N % (2 * hb) == 0) {
+      w->hb = hb;
+      break;
+    }
+  }
+  if (w->hb) {
+    if (make_map(&w->tm2_hi, w->W_hi, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, (uint32_t)w->hb)) return -1;
+    if (make_map(&w->tm2_lo, w->W_lo, (uint64_t)w->taps * w->N, (uint64_t)w->Cin, (uint32_t)w->hb)) return -1;
+  }
   w->ok = true;
   return 0;
 }
@@ -393,9 +662,6 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
-    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
-    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
-    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -405,7 +671,22 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   tp.tiles = p.tiles; tp.ntiles = p.ntiles; tp.taps = w.taps; tp.kchunks = w.Cin / BK;
   tp.kchunks2 = p.w2 ? p.w2->Cin / BK : 0;
   tp.dil = w.dil; tp.center = w.center; tp.N = w.N; tp.e = p.e;
+  {
+    const char* d = getenv("SSB_TC_DEBUG");
+    tp.dbg = d ? atoi(d) : 0;
+  }
   if (!tp.e.bias) tp.e.bias = w.bias;
+  // large problems: CTA pairs (256 x 2*hb tiles) halve the operand bytes each SM pulls through L2
+  const bool pair_off = getenv("SSB_TC_NO_PAIR") != nullptr;
+  if (!pair_off && w.hb > 0 && (!p.w2 || p.w2->hb == w.hb) &&
+      (int64_t)((p.ntiles + 1) / 2) * (w.N / (2 * w.hb)) >= (int64_t)num_sms) {
+    switch (w.hb) {
+      case 128: return launch_pair<128>(ctx, p, tp, num_sms);
+      case 96: return launch_pair<96>(ctx, p, tp, num_sms);
+      case 64: return launch_pair<64>(ctx, p, tp, num_sms);
+      default: return launch_pair<32>(ctx, p, tp, num_sms);
+    }
+  }
   // small problems: 64-wide N tiles keep more SMs busy and shorten each tile's dependent chain
   const bool small = (w.N % 128 != 0) || (int64_t)p.ntiles * (w.N / 128) < (int64_t)num_sms * 2;
   if (small) {

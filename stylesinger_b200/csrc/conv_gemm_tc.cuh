@@ -24,6 +24,8 @@ struct ConvTC {            // packed weights for the tensor-core path
   __half* W_hi = nullptr;  // [taps][N][Cin]
   __half* W_lo = nullptr;
   CUtensorMap tm_hi[3], tm_lo[3];  // [0]: box 128 rows (BN=128), [1]: box 64 rows (BN=64), [2]: box 256 rows (BN=256)
+  CUtensorMap tm2_hi, tm2_lo;       // CTA-pair kernel: box hb rows (each CTA of a pair stages half of a 2*hb-wide N tile)
+  int hb = 0;                       // 0: no pair packing
   int taps = 1, Cin = 0, N = 0, dil = 1, center = 0;
   const float* bias = nullptr;  // [N] (packed column order)
   bool ok = false;

@@ -38,25 +38,51 @@ def test_conv1d_tc_matches_torch(cin, n, k, dil):
     assert worst < 1e-4  # tensor-core fp32 accumulation truncates: ~1e-5 relative after 144 chained MMAs
 
 
-@pytest.mark.parametrize("n_out", [512, 384])
-def test_conv1d_tc_large_problem_uses_wide_tiles(n_out):
-    """> 2 waves of tiles: N=512 exercises the BN=256 / 2-stage instantiation, N=384 the BN=128 / 3-stage one,
-    both with the persistent tile loop and TMEM double buffering."""
+@pytest.mark.parametrize("cin,n_out,k,dil,reps,extra", [(256, 512, 3, 4, 1, 0), (256, 384, 3, 4, 1, 0), (256, 512, 3, 2, 1, 100),
+                                                       (192, 384, 1, 1, 1, 77), (128, 128, 7, 1, 1, 0), (64, 64, 11, 1, 2, 5),
+                                                       (64, 2048, 3, 1, 1, 0)])
+def test_conv1d_tc_large_problem_uses_cta_pairs(cin, n_out, k, dil, reps, extra):
+    """Enough row tiles for the CTA-pair kernel (cta_group::2, 256 x 2*hb tiles; hb = 128 / 96 / 64 / 32 by N):
+    persistent tile loop, TMEM double buffering, odd tile counts (the peer CTA of the last pair idles)."""
     from stylesinger_b200.engine import op_conv1d_tc
-    g = torch.Generator().manual_seed(11)
-    lens = [2800, 1500, 2999, 700, 2100, 1900, 2500, 3000, 1234, 2222]
+    g = torch.Generator().manual_seed(11 + n_out + k)
+    lens = [2800, 1500, 2999, 700, 2100, 1900, 2500, 3000, 1234, 2222] * reps + ([extra] if extra else [])
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-    x = torch.randn(int(offs[-1]), 256, generator=g)
-    w = torch.randn(n_out, 256, 3, generator=g) / (256 * 3) ** 0.5
+    x = torch.randn(int(offs[-1]), cin, generator=g)
+    w = torch.randn(n_out, cin, k, generator=g) / (cin * k) ** 0.5
     b = torch.randn(n_out, generator=g)
-    y = op_conv1d_tc(x.to(DEV), offs, w, b, dilation=4).cpu()
+    y = op_conv1d_tc(x.to(DEV), offs, w, b, dilation=dil).cpu()
     worst = 0.0
-    for i in (0, 3, 9):
+    for i in (0, 3, 9, len(lens) - 1):
         xi = x[offs[i]:offs[i + 1]].t()[None]
-        ref = F.conv1d(xi, w, b, padding=4, dilation=4)[0].t()
+        ref = F.conv1d(xi, w, b, padding=dil * (k - 1) // 2, dilation=dil)[0].t()
         worst = max(worst, _maxabs(y[offs[i]:offs[i + 1]], ref))
-    print(f"tc conv large: max err {worst:.3e}")
+    print(f"tc conv large {cin}->{n_out} k{k}: max err {worst:.3e}")
     assert worst < 1e-4
+
+
+def test_denoiser_large_batch_pair_kernel_matches_simt():
+    """DiffNet / DDiffNet evaluation on ~20k frames (CTA-pair kernel territory) against the fp32 FFMA path."""
+    T = 4
+    m = acoustic_engine(T)
+    gen = torch.Generator().manual_seed(3)
+    lens = [2900, 1700, 2999, 800, 2300, 1950, 2450, 3000, 1300, 1111]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n = int(offs[-1])
+    cond = torch.randn(n, 256, generator=gen).to(DEV)
+    spec = torch.randn(n, 80, generator=gen).to(DEV)
+    f0 = torch.randn(n, generator=gen).to(DEV)
+    uv = (torch.rand(n, generator=gen) > 0.5).to(torch.int32).to(DEV)
+    out = {}
+    try:
+        for tc in (True, False):
+            m.set_tensor_cores(tc)
+            out[tc] = (m.denoiser_eval(0, spec, None, 2, cond, offs).clone(), m.denoiser_eval(1, f0, uv, 1, cond, offs).clone())
+    finally:
+        m.set_tensor_cores(True)
+    errs = (_maxabs(out[True][0], out[False][0]), _maxabs(out[True][1], out[False][1]))
+    print("pair-kernel denoisers vs simt:", errs)
+    assert max(errs) < 1e-4
 
 
 @pytest.mark.parametrize("tc", [True, False])
