@@ -166,7 +166,10 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
         int32_t* uu[2] = {uva, uvs};
         RUN(run_f0_diffusion_pair_persistent(c, m, sf, cond, cond2, lo, hi, in.f0_gauss_noise, in.f0_unif_noise, in.seed, zz, uu));
       } else {
-      const bool fork = !c.dry && m.aux_stream != nullptr;
+      // Two streams only for small batches (latency-bound chains).  From ~8k frames on every GEMM fills the GPU on its
+      // own, and the CTA-pair (cluster) kernels used there must not run concurrently with each other from two streams:
+      // that combination hung on B200 (gpurun diag, round 1; root cause open - see DESIGN.md "known issues").
+      const bool fork = !c.dry && m.aux_stream != nullptr && sf.ntiles <= 64;
       if (fork) {
         SSB_CUDA(cudaEventRecord(m.ev_fork, c.stream));
         SSB_CUDA(cudaStreamWaitEvent(m.aux_stream, m.ev_fork, 0));

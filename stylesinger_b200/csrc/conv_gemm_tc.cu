@@ -1,10 +1,10 @@
 // tcgen05 + TMA + TMEM implicit-GEMM conv1d (see conv_gemm_tc.cuh).  sm_100a only.
 //
-// CTA = 256 threads, persistent over (M-tile, N-tile) pairs:
+// CTA = 384 threads, persistent over (M-tile, N-tile) pairs:
 //   warp 0 (1 lane)  TMA producer: per K block loads A_hi, A_lo [128x64] and W_hi, W_lo [BNx64] (128B swizzle)
 //   warp 1 (1 lane)  MMA issuer:   4 K-steps x 3 products of tcgen05.mma.kind::f16 (M128 N=BN K16), fp32 in TMEM
 //   warp 2           TMEM allocator (2 x BN columns = 2 accumulator buffers)
-//   warps 4-7        epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global,
+//   warps 4-11       epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global,
 //                    with the epilogue's own global operands (residual / skip) prefetched one chunk ahead
 // smem ring: BN=128: 3 stages x 64 KB, BN=64: 4 stages x 48 KB; mbarriers: full/empty per stage,
 // tmem_full/tmem_empty per accumulator buffer.  BN=64 is picked for small problems (more CTAs in flight).
@@ -20,7 +20,9 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE = BM * BK * 2;  // 16 KB
-constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;  // epilogue transpose buffers: 4 warps x [32 x 32] fp32
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int NTHREADS = 128 + 32 * EPI_WARPS;
+constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;  // epilogue transpose buffers: one [32 x 32] fp32 per warp
 
 template <int BN>
 struct Cfg {
@@ -96,85 +98,123 @@ __device__ __forceinline__ void split_store2(__half* hi, __half* lo, float a, fl
 // One 32 x 32 accumulator chunk (columns [n, n+32)) of this warp: transpose, then the fused epilogue.
 // MODE is a template parameter (and the chunk loop is not unrolled) to keep the epilogue's code small: the first
 // version carried all three modes x 4-8 unrolled chunks = 13k SASS instructions and ran out of the instruction cache.
+// Everything that does not depend on the step (pointers, flags, slopes) is hoisted into registers: the epilogue warps
+// run alone on their scheduler, so every instruction and every constant-bank reload is exposed latency.
+__device__ __forceinline__ float act_slope_of(int act, float slope) {  // act(v) == fmaxf(v, v * s) for s in [0, 1]
+  return act == ACT_RELU ? 0.0f : (act == ACT_LRELU ? slope : 1.0f);
+}
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64_t r0, int nrows, int n, int lane,
                                                const uint32_t (&raw)[32], const Pre& pre) {
   if (e.n_valid > 0 && n >= e.n_valid) return;  // warp-uniform
 #pragma unroll
-  for (int q = 0; q < 8; ++q)
-    xb[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
-                                                  __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+  for (int c = 0; c < 8; ++c)
+    xb[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(raw[4 * c]), __uint_as_float(raw[4 * c + 1]),
+                                                  __uint_as_float(raw[4 * c + 2]), __uint_as_float(raw[4 * c + 3]));
   __syncwarp();
-  const int q = lane & 7;
+  const int q = lane & 7, rq = lane >> 3;  // step i: row rq + 4i, columns n4 .. n4 + 3
   const int n4 = n + 4 * q;
+  const int64_t rb = r0 + rq;
+  const float4* xr = xb + rq * 8;          // row rq + 4i, chunk q ^ ((rq + 4i) & 7) = (q ^ rq) ^ (4 * (i & 1))
+  const int qx = q ^ rq;
   float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
   if (e.bias) { b0 = __ldg(e.bias + n4); b1 = __ldg(e.bias + n4 + 1); b2 = __ldg(e.bias + n4 + 2); b3 = __ldg(e.bias + n4 + 3); }
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // step bias folded into the planes
-  const bool planes_vec2 = e.vec2 != nullptr && e.oh != nullptr && (MODE == EPI_GENERIC || (MODE == EPI_RES_SKIP && n < e.C));
-  if (planes_vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
+  const int nsteps = nrows > rq ? (nrows - rq + 3) >> 2 : 0;  // steps i < nsteps have a valid row
+  if constexpr (MODE == EPI_GATE) {
+    const int64_t st = 4 * (int64_t)e.ldh;
+    __half* ph = e.oh + rb * e.ldh + (n4 >> 1);
+    __half* pl = e.ol + rb * e.ldh + (n4 >> 1);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = 4 * i + (lane >> 3);
-    if (rr >= nrows) continue;
-    const int64_t r = r0 + rr;
-    const float4 acc = xb[rr * 8 + (q ^ (rr & 7))];
-    float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
-    if constexpr (MODE == EPI_GATE) {
-      const float z0 = sigmoidf_(v0) * tanhf(v1), z1 = sigmoidf_(v2) * tanhf(v3);
-      split_store2(e.oh + r * e.ldh + (n4 >> 1), e.ol + r * e.ldh + (n4 >> 1), z0, z1);
-      continue;
+    for (int i = 0; i < 8; ++i) {
+      if (i < nsteps) {
+        const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+        const float z0 = sigmoidf_(acc.x + b0) * tanhf(acc.y + b1), z1 = sigmoidf_(acc.z + b2) * tanhf(acc.w + b3);
+        split_store2(ph + i * st, pl + i * st, z0, z1);
+      }
     }
-    if constexpr (MODE == EPI_RES_SKIP) {
-      if (n < e.C) {
-        const float4 x0 = pre.a[i];
-        v0 = (v0 + x0.x) * e.beta; v1 = (v1 + x0.y) * e.beta; v2 = (v2 + x0.z) * e.beta; v3 = (v3 + x0.w) * e.beta;
-        *reinterpret_cast<float4*>(e.out + r * e.ldo + n4) = make_float4(v0, v1, v2, v3);
-        if (e.oh) split_store4(e.oh + r * e.ldh + n4, e.ol + r * e.ldh + n4, v0 + s0, v1 + s1, v2 + s2, v3 + s3);
-      } else {
-        const int sc = n4 - e.C;
-        if (!e.skip_init) {
-          const float4 o = pre.a[i];
-          v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
+  } else if constexpr (MODE == EPI_RES_SKIP) {
+    if (n < e.C) {
+      const float beta = e.beta;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const bool planes = e.oh != nullptr;
+      if (planes && e.vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
+      float* po = e.out + rb * e.ldo + n4;
+      const int64_t sto = 4 * (int64_t)e.ldo, sth = 4 * (int64_t)e.ldh;
+      __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
+      __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nsteps) {
+          const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+          const float4 x0 = pre.a[i];
+          const float v0 = (acc.x + b0 + x0.x) * beta, v1 = (acc.y + b1 + x0.y) * beta;
+          const float v2 = (acc.z + b2 + x0.z) * beta, v3 = (acc.w + b3 + x0.w) * beta;
+          *reinterpret_cast<float4*>(po + i * sto) = make_float4(v0, v1, v2, v3);
+          if (planes) split_store4(ph + i * sth, pl + i * sth, v0 + s0, v1 + s1, v2 + s2, v3 + s3);
         }
-        *reinterpret_cast<float4*>(e.skip + r * e.ld_skip + sc) = make_float4(v0, v1, v2, v3);
-        if (e.sh) split_store4(e.sh + r * e.C + sc, e.sl + r * e.C + sc, v0, v1, v2, v3);
       }
-      continue;
-    }
-    if constexpr (MODE == EPI_GENERIC) {
-    if (e.act == ACT_RELU) {
-      v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-    } else if (e.act == ACT_LRELU) {
-      v0 = v0 > 0.f ? v0 : v0 * e.act_slope; v1 = v1 > 0.f ? v1 : v1 * e.act_slope;
-      v2 = v2 > 0.f ? v2 : v2 * e.act_slope; v3 = v3 > 0.f ? v3 : v3 * e.act_slope;
-    }
-    if (e.res) {
-      const float4 x0 = pre.a[i];
-      v0 += x0.x; v1 += x0.y; v2 += x0.z; v3 += x0.w;
-    }
-    if (e.out) {
-      float4* op = reinterpret_cast<float4*>(e.out + r * e.ldo + n4);
-      if (e.accum) {
-        const float4 o = *op;
-        v0 = (v0 + o.x) * e.gamma; v1 = (v1 + o.y) * e.gamma; v2 = (v2 + o.z) * e.gamma; v3 = (v3 + o.w) * e.gamma;
+    } else {
+      const int sc = n4 - e.C;
+      const bool init = e.skip_init != 0;
+      const bool planes = e.sh != nullptr;
+      float* ps = e.skip + rb * e.ld_skip + sc;
+      const int64_t sts = 4 * (int64_t)e.ld_skip, sth = 4 * (int64_t)e.C;
+      __half* ph = planes ? e.sh + rb * e.C + sc : nullptr;
+      __half* pl = planes ? e.sl + rb * e.C + sc : nullptr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nsteps) {
+          const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+          float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
+          if (!init) {
+            const float4 o = pre.a[i];
+            v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
+          }
+          *reinterpret_cast<float4*>(ps + i * sts) = make_float4(v0, v1, v2, v3);
+          if (planes) split_store4(ph + i * sth, pl + i * sth, v0, v1, v2, v3);
+        }
       }
-      *op = make_float4(v0, v1, v2, v3);
     }
-    if (e.oh) {
-      v0 += s0; v1 += s1; v2 += s2; v3 += s3;
-      if (e.plane_act == ACT_LRELU) {
-        v0 = v0 > 0.f ? v0 : v0 * e.plane_slope; v1 = v1 > 0.f ? v1 : v1 * e.plane_slope;
-        v2 = v2 > 0.f ? v2 : v2 * e.plane_slope; v3 = v3 > 0.f ? v3 : v3 * e.plane_slope;
+  } else {  // EPI_GENERIC: v = act(acc + bias) (+ res); out = accum ? (out + v) * gamma : v; planes = plane_act(v + vec2)
+    const float sa = act_slope_of(e.act, e.act_slope), sp = act_slope_of(e.plane_act, e.plane_slope);
+    const bool has_res = e.res != nullptr, has_out = e.out != nullptr, accum = e.accum != 0, planes = e.oh != nullptr;
+    const float gamma = e.gamma;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (planes && e.vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
+    float* po = has_out ? e.out + rb * e.ldo + n4 : nullptr;
+    const int64_t sto = 4 * (int64_t)e.ldo, sth = 4 * (int64_t)e.ldh;
+    __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
+    __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nsteps) {
+        const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+        float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
+        v0 = fmaxf(v0, v0 * sa); v1 = fmaxf(v1, v1 * sa); v2 = fmaxf(v2, v2 * sa); v3 = fmaxf(v3, v3 * sa);
+        if (has_res) {
+          const float4 x0 = pre.a[i];
+          v0 += x0.x; v1 += x0.y; v2 += x0.z; v3 += x0.w;
+        }
+        if (has_out) {
+          float4* op = reinterpret_cast<float4*>(po + i * sto);
+          if (accum) {
+            const float4 o = *op;
+            v0 = (v0 + o.x) * gamma; v1 = (v1 + o.y) * gamma; v2 = (v2 + o.z) * gamma; v3 = (v3 + o.w) * gamma;
+          }
+          *op = make_float4(v0, v1, v2, v3);
+        }
+        if (planes) {
+          v0 += s0; v1 += s1; v2 += s2; v3 += s3;
+          split_store4(ph + i * sth, pl + i * sth, fmaxf(v0, v0 * sp), fmaxf(v1, v1 * sp), fmaxf(v2, v2 * sp), fmaxf(v3, v3 * sp));
+        }
       }
-      split_store4(e.oh + r * e.ldh + n4, e.ol + r * e.ldh + n4, v0, v1, v2, v3);
-    }
     }
   }
   __syncwarp();  // the next chunk reuses the transpose buffer
 }
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
@@ -199,7 +239,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);
+      mbar_init(tempty0 + 8 * a, EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -287,7 +327,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;  // == warp % 4: TMEM lanes [32*ew, 32*ew + 32)
+    const int ew = warp & 3;          // TMEM lanes [32*ew, 32*ew + 32)
+    const int eg = (warp - 4) >> 2;   // chunk parity handled by this warp
     constexpr int NCH = BN / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -297,14 +338,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const int2 t = p.tiles[mt];
       const int64_t r0 = (int64_t)t.x + ew * 32;
       const int nrows = min(32, max(0, t.y - ew * 32));
-      float4* xb = xpose + ew * 256;
+      float4* xb = xpose + (warp - 4) * 256;
       Pre cur, nxt;
-      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN, lane, cur);  // issued before the accumulator is ready: overlaps the MMAs
+      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + eg * 32, lane, cur);  // issued before the accumulator is ready: overlaps the MMAs
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch) {
-        if (ch + 1 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 1) * 32, lane, nxt);
+      for (int ch = eg; ch < NCH; ch += 2) {
+        if (ch + 2 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN + ch * 32), v);
         if (nrows > 0 && !(p.dbg & 1)) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
@@ -330,20 +371,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // Per FLOP this halves the bytes each SM pulls through L2 (the limiter of the single-CTA kernel, profiles/r01_ncu_*).
 //   full[s]    leader only: 1 arrival (leader's expect_tx of 2 x STAGE bytes) + both CTAs' TMA transaction bytes
 //   empty[s]   per CTA: signalled by the leader's tcgen05.commit multicast to both CTAs
-//   tfull[a]   per CTA: same multicast commit;  tempty[a] leader only: 8 arrivals (4 epilogue warps x 2 CTAs)
+//   tfull[a]   per CTA: same multicast commit;  tempty[a] leader only: 16 arrivals (8 epilogue warps x 2 CTAs)
 template <int HB>
 struct Cfg2 {
   static constexpr int BN = 2 * HB;
   static constexpr int B_TILE = HB * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-  static constexpr int STAGES = HB >= 96 ? 3 : (HB == 32 ? 5 : 4);
+  static constexpr int STAGES = HB >= 96 ? 3 : 4;
   static constexpr int SMEM = STAGES * STAGE + XPOSE_BYTES + 1024 + 256;
   static constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
 };
 
 template <int HB, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                      const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
@@ -370,7 +411,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 8);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -463,7 +504,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    const int ew = warp & 3;
+    const int eg = (warp - 4) >> 2;
     constexpr int NCH = BN / 32;
     const uint32_t ltempty0 = mapa_u32(tempty0, 0);
     int it = 0;
@@ -476,14 +518,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int2 t = have ? p.tiles[mt] : make_int2(0, 0);
       const int64_t r0 = (int64_t)t.x + ew * 32;
       const int nrows = min(32, max(0, t.y - ew * 32));
-      float4* xb = xpose + ew * 256;
+      float4* xb = xpose + (warp - 4) * 256;
       Pre cur, nxt;
-      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN, lane, cur);
+      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + eg * 32, lane, cur);
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch) {
-        if (ch + 1 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 1) * 32, lane, nxt);
+      for (int ch = eg; ch < NCH; ch += 2) {
+        if (ch + 2 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * K::ACC_STRIDE + (uint32_t)(ch * 32), v);
         if (nrows > 0 && !(p.dbg & 1)) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
@@ -569,7 +611,7 @@ int launch_m(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   }
   const int total = tp.ntiles * tp.NT;
   const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_tc_kernel<BN, MODE><<<grid, 256, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm_hi[bi], w.tm_lo[bi], ta2_hi, ta2_lo,
+  conv_gemm_tc_kernel<BN, MODE><<<grid, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm_hi[bi], w.tm_lo[bi], ta2_hi, ta2_lo,
                                                                        w2.tm_hi[bi], w2.tm_lo[bi], tp);
   SSB_CUDA(cudaGetLastError());
   ++g_launches;
@@ -607,7 +649,7 @@ int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
   tp.NT = w.N / (2 * HB);
   const int total = ((tp.ntiles + 1) / 2) * tp.NT;
   const int ncl = total < num_sms / 2 ? total : num_sms / 2;
-  conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, 256, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
+  conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
                                                                            w2.tm2_hi, w2.tm2_lo, tp);
   SSB_CUDA(cudaGetLastError());
   ++g_launches;

@@ -1,4 +1,5 @@
-"""Per-stage device times (CUDA events) of one ph->mel->wav pass. Usage: python tools/stage_times.py [utt10s|batch8|batch64] [T]"""
+"""Per-stage device times (CUDA events) of one ph->mel->wav pass.
+Usage: python tools/stage_times.py [utt10s|batch8|batch64] [T] [fast]   (fast: default engine mode only, no FFMA comparison)"""
 import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -11,6 +12,7 @@ from stylesinger_b200.infer import StyleSingerInfer
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "utt10s"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+FAST = len(sys.argv) > 3 and sys.argv[3] == "fast"
 dev = torch.device("cuda:0")
 hp = resolve(timesteps=T, K_step=T, f0_timesteps=T)
 eng = StyleSingerInfer(hp, dev, synth.acoustic_state_dict(hp, seed=0), synth.vocoder_state_dict(DEFAULT_VOCODER_CONFIG, seed=0), DEFAULT_VOCODER_CONFIG)
@@ -30,7 +32,7 @@ def timed(fn, n=2):
     return a.elapsed_time(b) / n, (time.perf_counter() - t0) * 1000 / n, (lib.ssb_launch_count() - l0) // n, r
 
 res = {}
-for tag in ("persist", "tc", "simt"):
+for tag in (("persist",) if FAST else ("persist", "tc", "simt")):
     m.set_tensor_cores(tag != "simt")
     m.set_persistent(tag == "persist")
     ms, wall, nl, out = timed(lambda: m.forward(pb, seed=1, skip_mel_diffusion=True, want=("coarse_mel", "diff_cond", "f0_denorm")))
@@ -43,7 +45,7 @@ for tag in ("persist", "tc", "simt"):
     res[f"{tag}.one_f0_diffusion"] = (round(ms, 2), round(wall, 2), nl)
 m.set_tensor_cores(True); m.set_persistent(True)
 melc = mel.clamp(-6, 1.5).contiguous(); f0 = out["f0_denorm"]
-for tcv in (True, False):
+for tcv in ((True,) if FAST else (True, False)):
     v.set_tensor_cores(tcv)
     ms, wall, nl, _ = timed(lambda: v.generate(melc, f0, pb.frame_offsets, seed=4))
     res["vocoder." + ("tc" if tcv else "simt")] = (round(ms, 2), round(wall, 2), nl)
