@@ -399,7 +399,7 @@ sampler_tc_kernel(const CUtensorMap* __restrict__ maps, const SPhase* __restrict
         prefetch32(P, r, nt * BN, valid, cur);
         mbar_wait(tfull0 + 8 * a, aph);
         tc_fence_after();
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           if (ch + 1 < BN / 32) prefetch32(P, r, nt * BN + (ch + 1) * 32, valid, nxt);
           uint32_t v[32];
