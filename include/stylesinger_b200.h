@@ -192,6 +192,10 @@ int ssb_vocoder_set_tensor_cores(ssb_vocoder_t* v, int32_t enable);
 /* 1 (default): small batches run the whole T-step mel sampler in ONE persistent cooperative kernel launch
  * (csrc/sampler_tc.cu); 0: one launch per GEMM (BASELINE.json configs[4] compares the two). */
 int ssb_model_set_persistent(ssb_model_t* m, int32_t enable);
+/* Decoder FFT blocks (modules/commons/transformer.py TransformerFFNLayer, conv k=9 -> gelu -> linear): run the FFN GEMMs
+ * on the tcgen05 kernel for batches of >= 1024 frames (default on; 0 keeps them on the fp32 FFMA kernel). Returns the
+ * new setting. */
+int ssb_model_set_fft_tensor_cores(ssb_model_t* m, int32_t enable);
 
 /* Unit-test granularity: ssb_op_conv1d through the tcgen05 path (Cin % 64 == 0, N % 128 == 0, no activation). */
 int ssb_op_conv1d_tc(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,

@@ -54,7 +54,7 @@ EXPORTS = [
     "ssb_mel_diffusion_workspace_bytes", "ssb_mel_diffusion_sample", "ssb_denoiser_eval", "ssb_f0_diffusion_sample",
     "ssb_rvq_lookup", "ssb_vocoder_create", "ssb_vocoder_free", "ssb_vocoder_workspace_bytes", "ssb_hifigan_generate",
     "ssb_op_conv1d", "ssb_op_attention", "ssb_mel_postprocess", "ssb_launch_count",
-    "ssb_model_set_tensor_cores", "ssb_op_conv1d_tc", "ssb_model_set_persistent",
+    "ssb_model_set_tensor_cores", "ssb_op_conv1d_tc", "ssb_model_set_persistent", "ssb_model_set_fft_tensor_cores",
     "ssb_vocoder_set_tensor_cores",
 ]
 
@@ -91,6 +91,7 @@ def _load():
         "ssb_launch_count": (C.c_int64, []),
         "ssb_model_set_tensor_cores": (C.c_int, [vp, i32]),
         "ssb_model_set_persistent": (C.c_int, [vp, i32]),
+        "ssb_model_set_fft_tensor_cores": (C.c_int, [vp, i32]),
         "ssb_vocoder_set_tensor_cores": (C.c_int, [vp, i32]),
         "ssb_op_conv1d_tc": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
     }

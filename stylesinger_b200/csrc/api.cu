@@ -235,7 +235,9 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
       a.m[0] = xd; a.ldm[0] = H; a.rowmask = keep; a.out = xd; a.ldo = H; a.C = H;
       RUN(combine_rows(c, sf, a));
     }
-    RUN(fft_blocks(c, m.dec, sf, xd, keep));
+    // long batches: the decoder's FFN GEMMs on the tcgen05 kernel (short ones stay on the fp32 FFMA path, which is
+    // what the reference-golden parity tests pin)
+    RUN(fft_blocks(c, m.dec, sf, xd, keep, m.use_tc && m.fft_tc && tc_available() && sf.ntiles >= 8));
     {
       ConvGemm g = make_gemm(m.mel_out, sf, xd, H);
       g.e.rowmask = tgt; g.e.out = coarse; g.e.ldo = 80;
@@ -499,6 +501,12 @@ int ssb_vocoder_set_tensor_cores(ssb_vocoder_t* v, int32_t enable) {
   SSB_CHECK(v, "null vocoder");
   v->v.use_tc = enable != 0 && tc_available();
   return v->v.use_tc ? 1 : 0;
+}
+
+int ssb_model_set_fft_tensor_cores(ssb_model_t* m, int32_t enable) {
+  SSB_CHECK(m, "null model");
+  m->m.fft_tc = enable != 0;
+  return m->m.fft_tc ? 1 : 0;
 }
 
 int ssb_model_set_persistent(ssb_model_t* m, int32_t enable) {

@@ -4,6 +4,7 @@
 //   warp 0 (1 lane)  TMA producer: per K block loads A_hi, A_lo [128x64] and W_hi, W_lo [BNx64] (128B swizzle)
 //   warp 1 (1 lane)  MMA issuer:   4 K-steps x 3 products of tcgen05.mma.kind::f16 (M128 N=BN K16), fp32 in TMEM
 //   warp 2           TMEM allocator (2 x BN columns = 2 accumulator buffers)
+//   warp 3           L2 prefetch of the next tile's epilogue operands (residual / skip rows)
 //   warps 4-11       epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global,
 //                    with the epilogue's own global operands (residual / skip) prefetched one chunk ahead
 // smem ring: BN=128: 3 stages x 64 KB, BN=64: 4 stages x 48 KB; mbarriers: full/empty per stage,
@@ -95,6 +96,29 @@ __device__ __forceinline__ void split_store2(__half* hi, __half* lo, float a, fl
   *reinterpret_cast<__half2*>(lo) = l0;
 }
 
+// Warp 3 pulls the NEXT tile's epilogue operands (residual / skip / accumulate rows) from HBM into L2 while the current
+// tile is being finished: the epilogue warps can keep only one chunk of loads in flight each, so with DRAM latency the
+// residual-layer kernels ran at 22 % tensor activity / 43 % of the DRAM bandwidth (profiles/r01_ncu_full_pair_v2_*).
+template <int MODE>
+__device__ __forceinline__ void prefetch_tile_l2(const EpiTC& e, int2 t, int n0, int bn, int lane) {
+  if (e.n_valid > 0 && n0 >= e.n_valid) return;
+  const float* s1 = nullptr;
+  const float* s2 = nullptr;
+  int ld1 = 0, ld2 = 0;
+  if constexpr (MODE == EPI_GENERIC) {
+    if (e.res) { s1 = e.res + n0; ld1 = e.ld_res; }
+    if (e.accum && e.out) { s2 = e.out + n0; ld2 = e.ldo; }
+  } else if constexpr (MODE == EPI_RES_SKIP) {
+    if (n0 < e.C) { s1 = e.res + n0; ld1 = e.ld_res; }
+    else if (!e.skip_init) { s1 = e.skip + (n0 - e.C); ld1 = e.ld_skip; }
+  }
+  const uint32_t bytes = (uint32_t)bn * 4u;
+  for (int rr = lane; rr < t.y; rr += 32) {
+    if (s1) bulk_prefetch_l2(s1 + (int64_t)(t.x + rr) * ld1, bytes);
+    if (s2) bulk_prefetch_l2(s2 + (int64_t)(t.x + rr) * ld2, bytes);
+  }
+}
+
 // One 32 x 32 accumulator chunk (columns [n, n+32)) of this warp: transpose, then the fused epilogue.
 // MODE is a template parameter (and the chunk loop is not unrolled) to keep the epilogue's code small: the first
 // version carried all three modes x 4-8 unrolled chunks = 13k SASS instructions and ran out of the instruction cache.
@@ -177,6 +201,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     }
   } else {  // EPI_GENERIC: v = act(acc + bias) (+ res); out = accum ? (out + v) * gamma : v; planes = plane_act(v + vec2)
     const float sa = act_slope_of(e.act, e.act_slope), sp = act_slope_of(e.plane_act, e.plane_slope);
+    const bool gelu = e.act == ACT_GELU;
+    const float alpha = e.alpha;
+    const float* rmask = e.rowmask ? e.rowmask + rb : nullptr;
     const bool has_res = e.res != nullptr, has_out = e.out != nullptr, accum = e.accum != 0, planes = e.oh != nullptr;
     const float gamma = e.gamma;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -189,11 +216,19 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     for (int i = 0; i < 8; ++i) {
       if (i < nsteps) {
         const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
-        float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
-        v0 = fmaxf(v0, v0 * sa); v1 = fmaxf(v1, v1 * sa); v2 = fmaxf(v2, v2 * sa); v3 = fmaxf(v3, v3 * sa);
+        float v0 = (acc.x + b0) * alpha, v1 = (acc.y + b1) * alpha, v2 = (acc.z + b2) * alpha, v3 = (acc.w + b3) * alpha;
+        if (gelu) {
+          v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+        } else {
+          v0 = fmaxf(v0, v0 * sa); v1 = fmaxf(v1, v1 * sa); v2 = fmaxf(v2, v2 * sa); v3 = fmaxf(v3, v3 * sa);
+        }
         if (has_res) {
           const float4 x0 = pre.a[i];
           v0 += x0.x; v1 += x0.y; v2 += x0.z; v3 += x0.w;
+        }
+        if (rmask) {
+          const float mk = rmask[4 * i];
+          v0 *= mk; v1 *= mk; v2 *= mk; v3 *= mk;
         }
         if (has_out) {
           float4* op = reinterpret_cast<float4*>(po + i * sto);
@@ -239,7 +274,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, EPI_WARPS);
+      mbar_init(tempty0 + 8 * a, EPI_WARPS + 1);  // + the L2 prefetch warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -326,6 +361,27 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         tc_commit(tfull0 + 8 * a);        // accumulator complete -> epilogue
       }
     }
+  } else if (warp == 3) {
+    if constexpr (MODE != EPI_GATE) {
+      if ((int)blockIdx.x < total) {
+        const int mt = (int)blockIdx.x / p.NT, nt = (int)blockIdx.x - mt * p.NT;
+        prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+      }
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);  // pace: one tile ahead of the epilogue
+      __syncwarp();
+      if constexpr (MODE != EPI_GATE) {
+        const int nx = tile + gridDim.x;
+        if (nx < total) {
+          const int mt = nx / p.NT, nt = nx - mt * p.NT;
+          prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+        }
+      }
+      if (lane == 0) mbar_arrive(tempty0 + 8 * a);
+    }
   } else if (warp >= 4) {
     const int ew = warp & 3;          // TMEM lanes [32*ew, 32*ew + 32)
     const int eg = (warp - 4) >> 2;   // chunk parity handled by this warp
@@ -371,7 +427,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // Per FLOP this halves the bytes each SM pulls through L2 (the limiter of the single-CTA kernel, profiles/r01_ncu_*).
 //   full[s]    leader only: 1 arrival (leader's expect_tx of 2 x STAGE bytes) + both CTAs' TMA transaction bytes
 //   empty[s]   per CTA: signalled by the leader's tcgen05.commit multicast to both CTAs
-//   tfull[a]   per CTA: same multicast commit;  tempty[a] leader only: 16 arrivals (8 epilogue warps x 2 CTAs)
+//   tfull[a]   per CTA: same multicast commit;  tempty[a] leader only: 18 arrivals ((8 epilogue warps + the L2 prefetch warp) x 2 CTAs)
 template <int HB>
 struct Cfg2 {
   static constexpr int BN = 2 * HB;
@@ -411,7 +467,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);  // + the two L2 prefetch warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -502,6 +558,26 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         }
         tc_commit_pair(tfull0 + 8 * a);
       }
+    }
+  } else if (warp == 3) {
+    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
+    auto pf = [&](int tile) {
+      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      const int mt = 2 * mp + (int)rank;
+      if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+    };
+    if constexpr (MODE != EPI_GATE) {
+      if (cid < total) pf(cid);
+    }
+    int it = 0;
+    for (int tile = cid; tile < total; tile += ncl, ++it) {
+      const int a = it & 1;
+      if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
+      __syncwarp();
+      if constexpr (MODE != EPI_GATE) {
+        if (tile + ncl < total) pf(tile + ncl);
+      }
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
     }
   } else if (warp >= 4) {
     const int ew = warp & 3;

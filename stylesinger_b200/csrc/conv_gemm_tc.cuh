@@ -54,6 +54,8 @@ struct EpiTC {
   float gamma = 1.0f;
   int plane_act = ACT_NONE;      // activation applied to the value written to the fp16 planes (pre-activation of the consumer)
   float plane_slope = 0.1f;
+  float alpha = 1.0f;            // GENERIC: v = act((acc + bias) * alpha)   (ACT_GELU supported here for the FFT FFN)
+  const float* rowmask = nullptr;  // GENERIC: v = (v + res) * rowmask[row]
   int n_valid = 0;               // > 0: output columns >= n_valid are padding (weights padded to a tile multiple): skipped
   __half* sh = nullptr;          // RES_SKIP (last layer): the finished skip sum also as fp16 planes [rows, C]
   __half* sl = nullptr;

@@ -51,6 +51,7 @@ struct TensorMap {
 struct FFTLayer {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   Conv qkv, out, ffn1, ffn2;
+  ConvTC ffn1_tc, ffn2_tc;  // the FFN (92 % of the block's FLOPs) on the tcgen05 path, used for long sequences
 };
 struct FFT {
   std::vector<FFTLayer> layers;
@@ -125,6 +126,7 @@ struct Model {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool persistent = true;  // single-launch persistent sampler for small batches (ssb_model_set_persistent)
   bool use_tc = true;  // tcgen05 path for the denoiser layer GEMMs (ssb_model_set_tensor_cores)
+  bool fft_tc = true;  // tcgen05 path for the decoder FFT blocks' FFN on long batches (ssb_model_set_fft_tensor_cores)
 };
 
 struct VocStage {

@@ -260,6 +260,15 @@ static int build_fft(TensorMap& tm, DevicePool& pool, const std::string& p, int 
     if (pack_linear(pool, tm.get(q + "self_attn.out_proj.weight"), nullptr, &L.out)) return -1;
     if (pack_conv(pool, tm.get(q + "ffn.ffn_1.weight"), tm.get(q + "ffn.ffn_1.bias"), 1, PACK_PLAIN, &L.ffn1)) return -1;
     if (pack_linear(pool, tm.get(q + "ffn.ffn_2.weight"), tm.get(q + "ffn.ffn_2.bias"), &L.ffn2)) return -1;
+    if (pack_conv_tc(pool, tm.get(q + "ffn.ffn_1.weight"), 1, PACK_PLAIN, L.ffn1.bias, &L.ffn1_tc)) return -1;
+    {
+      const HostTensor* w2 = tm.get(q + "ffn.ffn_2.weight");  // Linear [H, 4H] as a 1-tap conv
+      if (!w2) return -1;
+      HostTensor ht;
+      ht.data = w2->data;
+      ht.shape = {w2->shape[0], w2->shape[1], 1};
+      if (pack_conv_tc(pool, &ht, 1, PACK_PLAIN, L.ffn2.bias, &L.ffn2_tc)) return -1;
+    }
   }
   f->ln_g = upload_tensor(pool, tm.get(p + "layer_norm.weight"));
   f->ln_b = upload_tensor(pool, tm.get(p + "layer_norm.bias"));

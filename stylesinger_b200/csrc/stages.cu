@@ -69,13 +69,19 @@ static __half* alloc_half_rows(Ctx& c, const SeqDev& s, int C);
 // ------------------------------------------------------------------------------------------------
 // a2-a5: FFTBlocks body (tts_modules.py:293-305 + EncSALayer common_layers.py:649-673)
 // x [rows,256] in/out; keep = 1 - padding_mask (row mask, also the key mask)
-int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* keep) {
+int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* keep, bool tc) {
   const int H = 256;
   const size_t mk = c.mark();
+  for (auto& L : f.layers) tc = tc && L.ffn1_tc.ok && L.ffn2_tc.ok;
   float* h = alloc_rows(c, s, H);
   float* qkv = alloc_rows(c, s, 3 * H);
   float* att = alloc_rows(c, s, H);
-  float* ff = alloc_rows(c, s, 4 * H);
+  float* ff = tc ? nullptr : alloc_rows(c, s, 4 * H);
+  __half *hh = nullptr, *hl = nullptr, *fh = nullptr, *fl = nullptr;  // fp16 hi/lo planes of h and of gelu(ffn_1)
+  if (tc) {
+    hh = alloc_half_rows(c, s, H); hl = alloc_half_rows(c, s, H);
+    fh = alloc_half_rows(c, s, 4 * H); fl = alloc_half_rows(c, s, 4 * H);
+  }
   WS_OK(c);
   for (size_t i = 0; i < f.layers.size(); ++i) {
     const FFTLayer& L = f.layers[i];
@@ -99,6 +105,19 @@ int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* kee
       RUN(conv_gemm(c, g));
     }
     RUN(layernorm_rows(c, s, x, H, h, H, H, L.ln2_g, L.ln2_b, 1e-5f, nullptr));
+    if (tc) {  // TransformerFFNLayer (transformer.py): ffn_2(gelu(ffn_1(x) * k^-0.5)) on the tcgen05 kernel
+      RUN(split_planes(c, h, H, s.rows, H, 1.0f, hh, hl));
+      GemmTC g1;
+      g1.A_hi = hh; g1.A_lo = hl; g1.rows_total = s.rows; g1.w = &L.ffn1_tc; g1.tiles = s.tiles; g1.ntiles = s.ntiles;
+      g1.e.mode = EPI_GENERIC; g1.e.alpha = 1.0f / sqrtf((float)f.kernel); g1.e.act = ACT_GELU;
+      g1.e.oh = fh; g1.e.ol = fl; g1.e.ldh = 4 * H;
+      RUN(conv_gemm_tc(c, g1));
+      GemmTC g2;
+      g2.A_hi = fh; g2.A_lo = fl; g2.rows_total = s.rows; g2.w = &L.ffn2_tc; g2.tiles = s.tiles; g2.ntiles = s.ntiles;
+      g2.e.mode = EPI_GENERIC; g2.e.res = x; g2.e.ld_res = H; g2.e.rowmask = keep; g2.e.out = x; g2.e.ldo = H;
+      RUN(conv_gemm_tc(c, g2));
+      continue;
+    }
     {
       ConvGemm g = make_gemm(L.ffn1, s, h, H);
       g.e.alpha = 1.0f / sqrtf((float)f.kernel); g.e.act = ACT_GELU; g.e.out = ff; g.e.ldo = 4 * H;

@@ -3,7 +3,7 @@
 
 namespace ssb {
 
-int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* keep);
+int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* keep, bool tc = false);
 int run_encoder(Ctx& c, const Model& m, const SeqDev& sp, const int32_t* tok_g, const int32_t* note_g,
                 const int32_t* type_g, const float* ndur_g, float* srcmask, float* enc_out);
 int run_duration_predictor(Ctx& c, const Model& m, const SeqDev& sp, const float* dur_inp, const float* srcmask,

@@ -171,6 +171,10 @@ class AcousticModel:
         """Single-launch persistent sampler kernel for small batches (True) vs one launch per GEMM (False)."""
         return bool(lib.ssb_model_set_persistent(self._h, 1 if enable else 0))
 
+    def set_fft_tensor_cores(self, enable: bool) -> bool:
+        """Decoder FFT-block FFN GEMMs on the tcgen05 kernel for batches of >= 1024 frames (default on)."""
+        return bool(lib.ssb_model_set_fft_tensor_cores(self._h, 1 if enable else 0))
+
     # -- schedules -------------------------------------------------------------------------------
     def set_timesteps(self, T=None, f0_T=None):
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -182,3 +182,28 @@ def test_f0_pair_persistent_matches_oracle_and_per_launch():
         e_f0 = _maxabs(o["f0_denorm"], r["f0_denorm"][0])
         print(mode, "pitch_pred err", e_pp, "f0_denorm err (Hz)", e_f0)
         assert e_pp < 1e-3 and e_f0 < 0.5
+
+
+def test_decoder_fft_ffn_tensor_cores_match_ffma():
+    """A 12 s utterance (2250 frames) puts the decoder's FFN GEMMs (conv k=9 -> gelu -> linear, 92 % of the FFT block's
+    FLOPs) on the tcgen05 kernel; the same pass with that switch off keeps them on the fp32 FFMA kernel. Everything
+    upstream is identical (same Philox streams), so decoder_inp must agree exactly and coarse_mel to fp32 rounding."""
+    from stylesinger_b200 import synth
+    from stylesinger_b200.engine import pack_batch
+    T = 4
+    u = synth.make_utterance(12.0, utt_idx=77)
+    m = acoustic_engine(T)
+    pb = pack_batch([u]).to(DEV)
+    out = {}
+    try:
+        for on in (True, False):
+            assert m.set_fft_tensor_cores(on) == on
+            o = m.forward(pb, seed=11, skip_mel_diffusion=True, want=("decoder_inp", "coarse_mel"))
+            out[on] = {k: v.clone() for k, v in o.items()}
+    finally:
+        m.set_fft_tensor_cores(True)
+    assert torch.equal(out[True]["decoder_inp"], out[False]["decoder_inp"])
+    err = _maxabs(out[True]["coarse_mel"], out[False]["coarse_mel"])
+    scale = float(out[False]["coarse_mel"].abs().max())
+    print(f"decoder FFN tcgen05 vs FFMA: coarse_mel max |diff| {err:.3e} (max |value| {scale:.2f})")
+    assert err < 1e-4 * max(1.0, scale)
