@@ -32,6 +32,9 @@ UNIT = "frames/s"
 # conditioner projection is hoisted out of the T loop and costs 20*2*256*512 once per frame)
 MEL_STEP_FLOPS = 2 * 80 * 256 + 20 * (2 * 768 * 512 + 2 * 256 * 512 + 2 * 256 * 512) + 2 * 256 * 256 + 2 * 256 * 80  # 26.43 MFLOP
 MEL_HOIST_FLOPS = 0  # the conditioner projection is contracted inside every layer GEMM (second K segment)
+# HBM bytes one frame streams per reverse step in this layout: per residual layer y planes in (1024) + cond planes in (1024)
+# + z planes out/in (2 x 1024) + x fp32 in/out (2 x 1024) + y planes out (1024) + skip read-modify-write (2048); heads ~4 KB
+MEL_STEP_STREAM_BYTES = 20 * 9216 + 4096
 
 
 def peaks():
@@ -226,12 +229,17 @@ def run_b200(args, rank, world, local_rank):
     gemm_launches = T * (2 * hp["residual_layers"] + 3) + 1
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"] + " (cuBLAS bf16, sustained)",
-            "kernel": "conv_gemm_tc_kernel (tcgen05; mel denoiser stage: %d launches per sampler call, of which %d residual-layer GEMMs)" % (n_mel, 2 * T * hp["residual_layers"]),
+            "kernel": "conv_gemm_tc2_kernel<128, GATE|RES_SKIP> (tcgen05 cta_group::2; mel denoiser stage: %d launches per sampler call, of which %d residual-layer GEMMs)" % (n_mel, 2 * T * hp["residual_layers"]),
             "avg_launch_us": 1000.0 * ms_mel / max(n_mel, 1), "stage_ms": ms_mel,
             "note": "useful FLOPs (26.43 MFLOP per frame-step, SURVEY 8d) over the CUDA-event time of the mel-diffusion stage; "
                     "the GEMMs run as 3 tcgen05 fp16 MMAs per product (hi/lo split) for fp32-class accuracy, so the issued-MMA "
                     "rate is 3x this figure and the effective ceiling of this precision scheme is peak/3",
-            "issued_mma_tflops": 3.0 * achieved}
+            "issued_mma_tflops": 3.0 * achieved,
+            # the same stage against the HBM roofline under the per-layer-streamed byte model of THIS layout
+            # (fp32 residual stream + fp16 hi/lo operand planes, nothing stays in L2 at this size)
+            "hbm_streamed": {"bytes_per_frame_step": MEL_STEP_STREAM_BYTES,
+                             "achieved_gbs": frames * T * MEL_STEP_STREAM_BYTES / (ms_mel / 1000.0) / 1e9,
+                             "peak_gbs": pk["hbm_gbs"]}}
 
     tot = torch.tensor([float(frames)], dtype=torch.float64, device=dev)
     if world > 1:

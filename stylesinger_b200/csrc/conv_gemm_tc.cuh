@@ -7,11 +7,16 @@
 //
 // Layout: A = activation planes [rows, C] fp16 row-major (guard-banded rows, see common.cuh), loaded by
 // TMA as [128 rows x 64 ch] boxes with 128B swizzle at row offset (tap - center) * dilation;
-// B = weights [taps*N, Cin] fp16 (K-major), boxes [BN n x 64 ch].  D = 128 x BN fp32 in TMEM,
-// double buffered so the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs).
+// B = weights [taps*N, Cin] fp16 (K-major), boxes [BN n x 64 ch] (single-CTA kernel) or [hb x 64] (CTA-pair kernel:
+// each CTA of a 2-CTA cluster stages half of a 2*hb-wide N tile and its own 128 rows of A; the leader issues
+// cta_group::2 MMAs with M = 256).  D = fp32 in TMEM, double buffered so the epilogue of tile i overlaps the MMAs
+// of tile i+1 (persistent CTAs).  The pair kernel is used when there are >= num_SMs pair tiles, the 64-wide
+// single-CTA kernel otherwise (conv_gemm_tc()).
 // An optional SECOND operand pair (A2, W2: 1 tap, no shift) extends the K loop: the DiffNet layer
 // GEMM contracts [3 taps x C of y | 256 of cond] in one accumulator, so the conditioner projection
 // needs neither a hoisted [rows, L*2C] fp32 buffer nor an epilogue read.
+// Env switches (diagnostics): SSB_TC_NO_PAIR=1 disables the pair kernel, SSB_TC_BN256=1 enables 256-wide single-CTA
+// tiles, SSB_TC_DEBUG=<bits> switches parts of the kernel off for tools/gemm_probe.py (results are then garbage).
 #pragma once
 #include <cuda.h>
 
