@@ -258,7 +258,7 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
   if (out.diff_cond) RUN(unpack_rows(c, sf, cond, H, out.diff_cond, H, H));
   if (!in.skip_mel_diffusion) {
     SSB_CHECK(out.mel_out != nullptr, "acoustic: mel_out required");
-    RUN(run_mel_diffusion(c, m, sf, cond, coarse, in.mel_noise, in.seed, out.mel_out));
+    RUN(run_mel_diffusion(c, m, sf, cond, coarse, in.mel_noise, in.seed, out.mel_out, &qf));
   }
   return 0;
 }
@@ -387,7 +387,7 @@ static int mel_diff_impl(Ctx& c, const Model& m, const float* cond, const float*
   WS_OK(c);
   RUN(pack_rows(c, s, cond, 256, cg, 256, 256));
   RUN(pack_rows(c, s, coarse, 80, co, 80, 80));
-  return run_mel_diffusion(c, m, s, cg, co, noise, seed, mel_out);
+  return run_mel_diffusion(c, m, s, cg, co, noise, seed, mel_out, &q);
 }
 size_t ssb_mel_diffusion_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, int32_t B) {
   Ctx c = make_ctx(nullptr, 0, nullptr, true);

@@ -564,9 +564,44 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
 
 // a18+a19: DiffusionDecoder.forward(infer=True) (shallow_diffusion_tts.py:284-307)
 int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
-                      const float* noise /*tight [(T+1), total, 80] or null*/, uint64_t seed, float* mel_tight) {
+                      const float* noise /*tight [(T+1), total, 80] or null*/, uint64_t seed, float* mel_tight,
+                      const Seq* host_seq) {
   const Denoiser& d = m.melnet;
   SSB_CHECK(d.T > 0, "mel schedule not set: call ssb_model_set_schedule(which=0)");
+  // EXPERIMENTAL, off unless SSB_MEL_GROUP_FRAMES=<n> is set: utterances are independent,
+  // so the T x L loop can run per GROUP of utterances of ~n frames whose working set (x, skip, planes, cond:
+  // ~5 KB/frame) stays L2-resident across layers and steps.  A group of consecutive utterances is a contiguous slice
+  // of the guard-banded layout, so the sub-batch simply aliases the big buffers.  Production (Philox) mode only: the
+  // injected-noise tensors are strided by the whole batch; each group gets its own seed.
+  if (host_seq && !noise && !c.dry) {
+    const char* ge = getenv("SSB_MEL_GROUP_FRAMES");
+    const long gf = ge ? atol(ge) : 0;
+    if (gf > 0 && host_seq->total > gf + gf / 2) {
+      int b0 = 0;
+      int64_t tight0 = 0;
+      int gi = 0;
+      while (b0 < host_seq->B) {
+        int b1 = b0;
+        int64_t fr = 0;
+        while (b1 < host_seq->B && (b1 == b0 || fr + host_seq->len[b1] <= gf)) fr += host_seq->len[b1++];
+        std::vector<int32_t> offs((size_t)(b1 - b0) + 1, 0);
+        for (int b = b0; b < b1; ++b) offs[(size_t)(b - b0) + 1] = offs[(size_t)(b - b0)] + host_seq->len[b];
+        Seq q;
+        q.build(offs.data(), b1 - b0);
+        const size_t mkg = c.mark();
+        SeqDev sg;
+        RUN(upload_layout(c, q, 1, &sg));
+        const int64_t row_off = (int64_t)host_seq->rs[b0] - GUARD;  // the sub-layout's row 0 inside the big buffers
+        RUN(run_mel_diffusion(c, m, sg, cond_g + row_off * 256, coarse_g + row_off * 80, nullptr,
+                              seed + 0x9E3779B97F4A7C15ull * (uint64_t)gi, mel_tight + tight0 * 80, nullptr));
+        c.release(mkg);
+        tight0 += fr;
+        b0 = b1;
+        ++gi;
+      }
+      return 0;
+    }
+  }
   if (m.persistent && denoiser_tc_ok(m, d) && d.in_tc.ok && d.skip_tc.ok && d.out_tc.ok && s.ntiles <= 48 &&
       sampler_tc_max_ctas() > 0)
     return run_mel_diffusion_persistent(c, m, s, cond_g, coarse_g, noise, seed, mel_tight);
