@@ -175,12 +175,12 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
         SSB_CUDA(cudaStreamWaitEvent(m.aux_stream, m.ev_fork, 0));
       }
       const size_t off0 = c.off;
-      RUN(run_f0_diffusion(c, m, 0, sf, cond, lo, hi, in.f0_gauss_noise[0], in.f0_unif_noise[0], in.seed, za, uva));
+      RUN(run_f0_diffusion(c, m, 0, sf, cond, lo, hi, in.f0_gauss_noise[0], in.f0_unif_noise[0], in.seed, za, uva, &qf));
       c.off = c.high;  // keep sampler 0's buffers alive: sampler 1 allocates above them
       {
         Ctx c2 = c;
         if (fork) c2.stream = m.aux_stream;
-        RUN(run_f0_diffusion(c2, m, 1, sf, cond2, lo, hi, in.f0_gauss_noise[1], in.f0_unif_noise[1], in.seed, zs, uvs));
+        RUN(run_f0_diffusion(c2, m, 1, sf, cond2, lo, hi, in.f0_gauss_noise[1], in.f0_unif_noise[1], in.seed, zs, uvs, &qf));
         if (c2.high > c.high) c.high = c2.high;
         c.failed = c.failed || c2.failed;
       }
@@ -434,7 +434,7 @@ int ssb_f0_diffusion_sample(const ssb_model_t* m, int32_t which, const float* co
   RUN(pack_rows(c, s, cond, 256, cg, 256, 256));
   RUN(pack_rows(c, s, clip_lo, 1, lo, 1, 1));
   RUN(pack_rows(c, s, clip_hi, 1, hi, 1, 1));
-  RUN(run_f0_diffusion(c, m->m, which, s, cg, lo, hi, gauss_noise, unif_noise, seed, z, uv));
+  RUN(run_f0_diffusion(c, m->m, which, s, cg, lo, hi, gauss_noise, unif_noise, seed, z, uv, &q));
   RUN(unpack_rows(c, s, z, 1, f0_norm_out, 1, 1));
   RUN(unpack_rows_i32(c, s, uv, uv_out));
   return 0;

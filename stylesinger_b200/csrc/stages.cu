@@ -752,9 +752,37 @@ bool f0_pair_persistent_ok(const Model& m, const SeqDev& s) {
 
 // a13+a14: GaussianMultinomialDiffusion.sample (gaussian_multinomial_diffusion.py:921-942)
 int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const float* cond_g, const float* lo,
-                     const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv) {
+                     const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv,
+                     const Seq* host_seq) {
   const Denoiser& d = m.f0net[which];
   SSB_CHECK(d.T > 0, "f0 schedule not set: call ssb_model_set_schedule(which=1)");
+  // EXPERIMENTAL utterance grouping, off unless SSB_F0_GROUP_FRAMES=<n> is set: see run_mel_diffusion.
+  if (host_seq && !gnoise && !unoise && !c.dry) {
+    const char* ge = getenv("SSB_F0_GROUP_FRAMES");
+    const long gf = ge ? atol(ge) : 0;
+    if (gf > 0 && host_seq->total > gf + gf / 2) {
+      int b0 = 0, gi = 0;
+      while (b0 < host_seq->B) {
+        int b1 = b0;
+        int64_t fr = 0;
+        while (b1 < host_seq->B && (b1 == b0 || fr + host_seq->len[b1] <= gf)) fr += host_seq->len[b1++];
+        std::vector<int32_t> offs((size_t)(b1 - b0) + 1, 0);
+        for (int b = b0; b < b1; ++b) offs[(size_t)(b - b0) + 1] = offs[(size_t)(b - b0)] + host_seq->len[b];
+        Seq q;
+        q.build(offs.data(), b1 - b0);
+        const size_t mkg = c.mark();
+        SeqDev sg;
+        RUN(upload_layout(c, q, 1, &sg));
+        const int64_t ro = (int64_t)host_seq->rs[b0] - GUARD;  // all operands here are guard-banded [rows, ld] buffers
+        RUN(run_f0_diffusion(c, m, which, sg, cond_g + ro * 256, lo + ro, hi + ro, nullptr, nullptr,
+                             seed + 0x9E3779B97F4A7C15ull * (uint64_t)gi, z + ro, uv + ro, nullptr));
+        c.release(mkg);
+        b0 = b1;
+        ++gi;
+      }
+      return 0;
+    }
+  }
   const size_t mk = c.mark();
   DenoiserBufs b;
   RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));

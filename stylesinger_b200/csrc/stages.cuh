@@ -29,7 +29,8 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
 int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
                       const float* noise, uint64_t seed, float* mel_tight, const Seq* host_seq = nullptr);
 int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const float* cond_g, const float* lo,
-                     const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv);
+                     const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv,
+                     const Seq* host_seq = nullptr);  // host_seq: see run_mel_diffusion (SSB_F0_GROUP_FRAMES)
 int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, const float* cond0, const float* cond1,
                                      const float* lo, const float* hi, const float* const gnoise[2],
                                      const float* const unoise[2], uint64_t seed, float* const z[2], int32_t* const uv[2]);
