@@ -777,6 +777,10 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   if (ctx.dry || p.ntiles == 0) return 0;
   const ConvTC& w = *p.w;
   SSB_CHECK(w.ok && (!p.w2 || (p.w2->ok && p.w2->N == w.N && p.w2->taps == 1)), "conv_gemm_tc: weights not packed for the tensor-core path");
+  SSB_CHECK(p.e.act == ACT_NONE || p.e.act == ACT_RELU || p.e.act == ACT_LRELU || p.e.act == ACT_GELU,
+            "conv_gemm_tc: unsupported epilogue activation");
+  SSB_CHECK(p.e.plane_act == ACT_NONE || p.e.plane_act == ACT_LRELU, "conv_gemm_tc: unsupported plane activation");
+  SSB_CHECK(p.e.mode != EPI_GENERIC || p.e.out || p.e.oh, "conv_gemm_tc: GENERIC epilogue without an output");
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
