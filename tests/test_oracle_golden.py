@@ -60,6 +60,18 @@ def test_T25_sampler_matches_reference():
     assert _maxabs(r["pitch_pred"][0].numpy(), g["pitch_pred"]) < TOL
 
 
+def test_T100_sampler_matches_reference():
+    """The bench's step count (T=100 mel steps, 2 x 100 F0 steps): 300 chained sampler steps of the oracle against
+    the unmodified reference on the same injected draws."""
+    g, meta = golden("ref_f32_T100")
+    hp = hp_for(meta["T"])
+    r, _ = oracle_forward(utt_from_meta(meta), hp, meta["seed"])
+    assert np.array_equal(r["rq_codes"][0].numpy(), g["rq_codes"])
+    assert _maxabs(r["pitch_pred"][0].numpy(), g["pitch_pred"]) < TOL
+    assert _maxabs(r["f0_denorm"][0].numpy(), g["f0_denorm"]) < 1e-2  # Hz
+    assert _maxabs(r["mel_out"][0].numpy(), g["mel_out"]) < 1e-4
+
+
 def test_vocoder_matches_reference():
     g, meta = golden("ref_vocoder_f24")
     ns = O.NoiseSource(meta["seed"] + 5)

@@ -165,10 +165,12 @@ def case_vocoder(name, frames, seed):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["small", "t25", "voc"]
+    which = sys.argv[1:] or ["small", "t25", "t100", "voc"]
     if "small" in which:
         case_model("ref_small_T4", T=4, frames=96, phones=12, ref_frames=64, seed=11, utt_idx=100)
     if "t25" in which:
         case_model("ref_f64_T25", T=25, frames=64, phones=8, ref_frames=48, seed=21, utt_idx=101, with_dur_case=False)
+    if "t100" in which:  # the bench's step count (T=100 mel + 2 x 100 F0 steps) on a tiny utterance
+        case_model("ref_f32_T100", T=100, frames=32, phones=4, ref_frames=32, seed=41, utt_idx=102, with_dur_case=False)
     if "voc" in which:
         case_vocoder("ref_vocoder_f24", frames=24, seed=31)
