@@ -77,12 +77,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_workload(name, rank, world):
+def make_workload(name, rank, world, describe_only=False):
     from stylesinger_b200 import synth
     from stylesinger_b200.dist import lpt_assign
     if name == "utt10s":
-        return [synth.make_utterance(10.0, utt_idx=rank)], "single 10 s utterance per GPU (BASELINE.json configs[1])"
+        desc = "single 10 s utterance per GPU (BASELINE.json configs[1])"
+        return desc if describe_only else ([synth.make_utterance(10.0, utt_idx=rank)], desc)
     n_per = {"batch64": 64, "batch8": 8}[name]
+    if describe_only:
+        return f"{n_per} variable-length (2-15 s) utterances per GPU, LPT-sharded (BASELINE.json configs[2]/[3])"
     secs = synth.batch_seconds(n_per * world, seed=1234)
     mine = lpt_assign(secs, world)[rank]
     utts = [synth.make_utterance(float(secs[i]), utt_idx=i) for i in mine]
@@ -138,8 +141,13 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"CPU oracle port of the reference (reference is Python, cannot travel): one "
-                                   f"{sample_s:g} s utterance, T={args.T} (mel + 2 F0 loops) + HiFi-GAN-NSF, per step"},
+            # same workload naming as the b200 arm; each step is a bounded sample of it (frames/s is per frame, and the
+            # CPU path's cost is linear in frames at these lengths)
+            "config": {"workload": f"{args.workload}: {make_workload(args.workload, 0, 1, describe_only=True)}; T={args.T} mel + "
+                                   f"2x{args.T} F0 steps; full ph->mel->wav",
+                       "sample": f"one {sample_s:g} s utterance of that workload per step, CPU oracle port of the reference "
+                                 f"(the reference is Python and cannot travel to the GPU box)",
+                       "parallelism": f"{threads} host threads (torch intra-op)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "host_logical_cores": os.cpu_count(), "kind": "port",
                              "sample": f"{sample_s:g} s utterance ({frames} frames), full ph->wav, T={args.T}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
