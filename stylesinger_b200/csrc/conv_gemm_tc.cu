@@ -702,6 +702,24 @@ int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   }
 }
 
+// Diagnostic for the open two-stream issue, off unless SSB_TC_PAIR_SERIALIZE=1: never let two
+// CTA-pair kernels from DIFFERENT streams be in flight together - each launch waits (on the device) for the previous
+// pair kernel of any other stream.  If the hang disappears with this switch, two co-resident cluster kernels are the trigger.
+cudaEvent_t g_pair_evt = nullptr;
+cudaStream_t g_pair_last_stream = nullptr;
+bool g_pair_evt_valid = false;
+bool pair_serialize_begin(cudaStream_t st) {
+  static const bool on = getenv("SSB_TC_PAIR_SERIALIZE") != nullptr;
+  if (!on) return false;
+  if (!g_pair_evt && cudaEventCreateWithFlags(&g_pair_evt, cudaEventDisableTiming) != cudaSuccess) return false;
+  if (g_pair_evt_valid && g_pair_last_stream != st) cudaStreamWaitEvent(st, g_pair_evt, 0);
+  return true;
+}
+void pair_serialize_end(cudaStream_t st) {
+  g_pair_evt_valid = cudaEventRecord(g_pair_evt, st) == cudaSuccess;
+  g_pair_last_stream = st;
+}
+
 template <int HB, int MODE>
 int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
   using KCfg = Cfg2<HB>;
@@ -725,9 +743,11 @@ int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
   tp.NT = w.N / (2 * HB);
   const int total = ((tp.ntiles + 1) / 2) * tp.NT;
   const int ncl = total < num_sms / 2 ? total : num_sms / 2;
+  const bool serialize = pair_serialize_begin(ctx.stream);
   conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
                                                                            w2.tm2_hi, w2.tm2_lo, tp);
   SSB_CUDA(cudaGetLastError());
+  if (serialize) pair_serialize_end(ctx.stream);
   ++g_launches;
   return 0;
 }
