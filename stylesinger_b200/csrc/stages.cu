@@ -811,7 +811,8 @@ int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const f
 // a20/a21: HifiGanGenerator.forward (hifigan_nsf.py:144-169)
 // Stages whose channel counts are multiples of 64 run on the tcgen05 kernel: every conv input is carried as
 // fp16 hi/lo planes of leaky_relu(x) written by the producing epilogue (the reference applies leaky_relu before
-// every conv), residuals / MRF accumulators stay fp32.  Narrow stages (C = 32) use the fp32 FFMA kernel.
+// every conv), residuals / MRF accumulators stay fp32.  The narrow stage (C = 32) runs its ResBlocks through a
+// time-paired [rows/2, 64] view of the same memory with repacked weights (pack.cu, pack_conv_paired_tc).
 int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight, const float* f0_tight,
                 const float* rand_ini, const float* src_noise, uint64_t seed, float* wav_tight) {
   const size_t mk0 = c.mark();
