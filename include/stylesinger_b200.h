@@ -209,6 +209,15 @@ int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, in
 /* Number of kernels this library has launched in this process so far (bench.py reports the delta). */
 int64_t ssb_launch_count(void);
 
+/* Diagnostics of the tensor-core GEMM dispatcher (csrc/conv_gemm_tc.cu): launches of one kernel variant, named
+ * "tc<BN,MODE>" (single CTA) or "tc2<HB,MODE>" (CTA pair), MODE in GATE / RES_SKIP / GENERIC, e.g. "tc2<64,GENERIC>";
+ * the ';'-separated list of variants launched so far (returns their number); and the counters of the activation
+ * TMA-descriptor cache (descriptors encoded / served from the cache).  Tests use these to assert WHICH kernel a problem
+ * size took; nothing in the reference corresponds to them. */
+int64_t ssb_variant_launch_count(const char* variant);
+int32_t ssb_variant_names(char* buf, int32_t cap);
+void ssb_tensor_map_cache_stats(int64_t* encodes, int64_t* hits);
+
 /* Unit-test granularity: one Conv1d over ragged rows with torch-layout HOST weights [N,Cin,k]
  * (packs on the fly with cudaMalloc; not for production use).  act: 0 none 1 relu 2 gelu 3 leaky(0.1) 4 tanh. */
 int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,

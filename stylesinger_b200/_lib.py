@@ -55,7 +55,7 @@ EXPORTS = [
     "ssb_rvq_lookup", "ssb_vocoder_create", "ssb_vocoder_free", "ssb_vocoder_workspace_bytes", "ssb_hifigan_generate",
     "ssb_op_conv1d", "ssb_op_attention", "ssb_mel_postprocess", "ssb_launch_count",
     "ssb_model_set_tensor_cores", "ssb_op_conv1d_tc", "ssb_model_set_persistent", "ssb_model_set_fft_tensor_cores",
-    "ssb_vocoder_set_tensor_cores",
+    "ssb_vocoder_set_tensor_cores", "ssb_variant_launch_count", "ssb_variant_names", "ssb_tensor_map_cache_stats",
 ]
 
 
@@ -94,6 +94,9 @@ def _load():
         "ssb_model_set_fft_tensor_cores": (C.c_int, [vp, i32]),
         "ssb_vocoder_set_tensor_cores": (C.c_int, [vp, i32]),
         "ssb_op_conv1d_tc": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
+        "ssb_variant_launch_count": (C.c_int64, [C.c_char_p]),
+        "ssb_variant_names": (i32, [C.c_char_p, i32]),
+        "ssb_tensor_map_cache_stats": (None, [P(C.c_int64), P(C.c_int64)]),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
@@ -102,6 +105,14 @@ def _load():
 
 
 lib = _load()
+
+
+def variant_launches():
+    """{kernel variant name: launches so far} of the tcgen05 GEMM dispatcher (ssb_variant_names / _launch_count)."""
+    buf = C.create_string_buffer(4096)
+    lib.ssb_variant_names(buf, 4096)
+    names = [n for n in buf.value.decode().split(";") if n]
+    return {n: int(lib.ssb_variant_launch_count(n.encode())) for n in names}
 
 
 def check(rc, what=""):

@@ -563,7 +563,15 @@ int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, in
   SSB_CHECK(mel && nonzero_frames && n_frames >= 0, "bad argument");
   return mel_postprocess_flat((cudaStream_t)stream, mel, n_frames, vmin, vmax, nonzero_frames);
 }
-int64_t ssb_launch_count(void) { return (int64_t)ssb::g_launches; }
+int64_t ssb_launch_count(void) { return (int64_t)ssb::g_launches.load(); }
+int64_t ssb_variant_launch_count(const char* variant) { return variant ? (int64_t)ssb::variant_launch_count(variant) : 0; }
+int32_t ssb_variant_names(char* buf, int32_t cap) { return buf && cap > 0 ? ssb::variant_names(buf, cap) : 0; }
+void ssb_tensor_map_cache_stats(int64_t* encodes, int64_t* hits) {
+  long long e = 0, h = 0;
+  ssb::tensor_map_cache_stats(&e, &h);
+  if (encodes) *encodes = e;
+  if (hits) *hits = h;
+}
 
 int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
                   const float* b_host, int32_t N, int32_t k, int32_t dilation, int32_t act, float* out, void* stream) {

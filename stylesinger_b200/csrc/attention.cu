@@ -4,6 +4,8 @@
 //   and the style aligner's cross-attention (reference modules/StyleSinger/lse.py:41).
 // The [L,S] score matrix is never materialised (63 MB / utterance / layer in the reference at F=2812).
 // One CTA = 64 queries of one (utterance, head); keys/values streamed in tiles of 64.
+#include <atomic>
+
 #include "attention.cuh"
 
 namespace ssb {
@@ -156,10 +158,15 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(AttnArgs a) {
 
 int attention(Ctx& ctx, const AttnArgs& a) {
   if (ctx.dry || a.B == 0 || a.max_q == 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    SSB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem)));
-    configured = true;
+  {  // the attribute is per device (one process may drive several GPUs)
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev].load(std::memory_order_acquire)) {
+      SSB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem)));
+      configured[dev].store(true, std::memory_order_release);
+    }
   }
   dim3 grid((a.max_q + BQ - 1) / BQ, a.heads, a.B);
   attention_kernel<<<grid, 256, sizeof(AttnSmem), ctx.stream>>>(a);

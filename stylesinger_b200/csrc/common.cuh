@@ -15,6 +15,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -24,7 +25,7 @@ constexpr int GUARD = 16;        // guard rows at rate 1 (>= max conv reach at r
 constexpr int TAIL_SLACK = 256;  // rows appended so that a partially valid tile can over-read safely
 constexpr int TILE_M = 128;      // rows per GEMM tile
 
-extern long long g_launches;  // kernels launched by this library (diagnostic; see ssb_launch_count)
+extern std::atomic<long long> g_launches;  // kernels launched by this library (diagnostic; see ssb_launch_count)
 void set_error(const std::string& msg);
 const char* last_error();
 

@@ -11,6 +11,11 @@
 // tmem_full/tmem_empty per accumulator buffer.  BN=64 is picked for small problems (more CTAs in flight).
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "conv_gemm_tc.cuh"
 #include "tc_common.cuh"
@@ -634,19 +639,23 @@ __global__ void k_split_planes(const float* x, int ld, int64_t rows, int C, floa
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-bool g_encode_tried = false;
+std::mutex g_host_mu;  // guards the driver entry point, the per-device kernel attributes and the descriptor cache
 
 EncodeTiledFn get_encode() {
-  if (!g_encode_tried) {
-    g_encode_tried = true;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      g_encode = (EncodeTiledFn)fn;
+  static std::atomic<EncodeTiledFn> fn_cached{nullptr};
+  static std::atomic<bool> tried{false};
+  if (!tried.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!tried.load(std::memory_order_relaxed)) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+          q == cudaDriverEntryPointSuccess)
+        fn_cached.store((EncodeTiledFn)fn, std::memory_order_relaxed);
+      tried.store(true, std::memory_order_release);
+    }
   }
-  return g_encode;
+  return fn_cached.load(std::memory_order_relaxed);
 }
 
 // 2-D fp16 row-major [rows, cols] tensor, box [box_rows x 64 cols], 128B swizzle, zero OOB fill
@@ -664,23 +673,105 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint
   return 0;
 }
 
+// Activation descriptors are a pure function of (pointer, rows, cols, box): a sampler loop re-launches the same GEMMs
+// on the same workspace buffers T x L times, so they are encoded once and looked up afterwards.
+struct MapKey {
+  const void* ptr; uint64_t rows; uint32_t cols, box;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box == o.box; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x7F4A7C15u) * 0xC2B2AE3D27D4EB4Full;
+    h ^= ((uint64_t)k.cols << 32 | k.box) * 0x165667B19E3779F9ull;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+long long g_map_encodes = 0, g_map_hits = 0;
+
+int cached_act_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const MapKey k{ptr, rows, (uint32_t)cols, box_rows};
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  auto it = g_map_cache.find(k);
+  if (it != g_map_cache.end()) {
+    *m = it->second;
+    ++g_map_hits;
+    return 0;
+  }
+  if (g_map_cache.size() > 8192) g_map_cache.clear();  // bounded: workspaces move when a batch shape changes
+  if (make_map(m, ptr, rows, cols, box_rows)) return -1;
+  g_map_cache.emplace(k, *m);
+  ++g_map_encodes;
+  return 0;
+}
+
+// Kernel attributes (cudaFuncSetAttribute) and the SM count are PER DEVICE: one process may drive several GPUs.
+constexpr int MAX_DEV = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < MAX_DEV ? dev : 0;
+}
+int device_sms() {
+  static std::atomic<int> sms[MAX_DEV];
+  const int dev = current_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+template <typename KernelT>
+int configure_once(KernelT kernel, std::atomic<bool>* done /*[MAX_DEV]*/, int smem) {
+  const int dev = current_device();
+  if (done[dev].load(std::memory_order_acquire)) return 0;
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  if (!done[dev].load(std::memory_order_relaxed)) {
+    SSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done[dev].store(true, std::memory_order_release);
+  }
+  return 0;
+}
+
+// Per-variant launch counters (ssb_variant_launch_count): lets a test assert WHICH kernel a problem size took.
+struct VariantCounter { const char* name; std::atomic<long long> n; };
+VariantCounter g_variants[48];
+std::atomic<int> g_nvariants{0};
+std::atomic<long long>* variant_counter(const char* name) {
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  const int n = g_nvariants.load();
+  for (int i = 0; i < n; ++i)
+    if (strcmp(g_variants[i].name, name) == 0) return &g_variants[i].n;
+  if (n >= 48) return &g_variants[47].n;
+  g_variants[n].name = name;
+  g_variants[n].n.store(0);
+  g_nvariants.store(n + 1);
+  return &g_variants[n].n;
+}
+const char* mode_name(int mode) { return mode == EPI_GATE ? "GATE" : (mode == EPI_RES_SKIP ? "RES_SKIP" : "GENERIC"); }
+
 template <int BN, int MODE>
 int launch_m(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   using KCfg = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::SMEM));
-    configured = true;
-  }
+  static std::atomic<bool> configured[MAX_DEV];
+  if (configure_once(conv_gemm_tc_kernel<BN, MODE>, configured, KCfg::SMEM)) return -2;
+  static std::atomic<long long>* const counter = [] {
+    static char name[48];
+    snprintf(name, sizeof(name), "tc<%d,%s>", BN, mode_name(MODE));
+    return variant_counter(name);
+  }();
   const ConvTC& w = *p.w;
   const ConvTC& w2 = p.w2 ? *p.w2 : *p.w;
   const int bi = BN == 128 ? 0 : (BN == 64 ? 1 : 2);
   CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo;
-  if (make_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
-  if (make_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (cached_act_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (cached_act_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
   if (p.w2) {
-    if (make_map(&ta2_hi, p.A2_hi, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
-    if (make_map(&ta2_lo, p.A2_lo, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+    if (cached_act_map(&ta2_hi, p.A2_hi, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+    if (cached_act_map(&ta2_lo, p.A2_lo, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
   } else {
     ta2_hi = ta_hi;
     ta2_lo = ta_lo;
@@ -691,6 +782,7 @@ int launch_m(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
                                                                        w2.tm_hi[bi], w2.tm_lo[bi], tp);
   SSB_CUDA(cudaGetLastError());
   ++g_launches;
+  counter->fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 template <int BN>
@@ -702,22 +794,32 @@ int launch(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   }
 }
 
-// Diagnostic for the open two-stream issue, off unless SSB_TC_PAIR_SERIALIZE=1: never let two
-// CTA-pair kernels from DIFFERENT streams be in flight together - each launch waits (on the device) for the previous
-// pair kernel of any other stream.  If the hang disappears with this switch, two co-resident cluster kernels are the trigger.
-cudaEvent_t g_pair_evt = nullptr;
-cudaStream_t g_pair_last_stream = nullptr;
-bool g_pair_evt_valid = false;
-bool pair_serialize_begin(cudaStream_t st) {
-  static const bool on = getenv("SSB_TC_PAIR_SERIALIZE") != nullptr;
-  if (!on) return false;
-  if (!g_pair_evt && cudaEventCreateWithFlags(&g_pair_evt, cudaEventDisableTiming) != cudaSuccess) return false;
-  if (g_pair_evt_valid && g_pair_last_stream != st) cudaStreamWaitEvent(st, g_pair_evt, 0);
-  return true;
+// Two CTA-pair (cluster, cta_group::2) kernels in flight from DIFFERENT streams hung the B200 in round 1 (DESIGN.md
+// section 4; tools/repro_two_stream_hang.py).  Until that is root-caused the safe behaviour is the default: a pair
+// kernel never overlaps a pair kernel of another stream - each launch on a new stream first waits (on the device,
+// cudaStreamWaitEvent) for the last pair kernel launched on any other stream.  Same-stream launches are already
+// ordered and pay nothing.  SSB_TC_PAIR_CONCURRENT=1 switches the guard off (reproducer / diagnosis only).
+// Process-wide and thread-safe: the event and the "last stream" are guarded by a mutex held across wait + launch +
+// record, so two host threads cannot interleave between the wait and the record.
+std::mutex g_pair_mu;
+cudaEvent_t g_pair_evt[MAX_DEV];
+cudaStream_t g_pair_last_stream[MAX_DEV];
+bool g_pair_evt_valid[MAX_DEV];
+bool pair_guard_enabled() {
+  static const bool off = getenv("SSB_TC_PAIR_CONCURRENT") != nullptr;
+  return !off;
 }
-void pair_serialize_end(cudaStream_t st) {
-  g_pair_evt_valid = cudaEventRecord(g_pair_evt, st) == cudaSuccess;
-  g_pair_last_stream = st;
+void pair_guard_begin(int dev, cudaStream_t st) {  // g_pair_mu held
+  if (!g_pair_evt[dev] && cudaEventCreateWithFlags(&g_pair_evt[dev], cudaEventDisableTiming) != cudaSuccess) {
+    g_pair_evt[dev] = nullptr;
+    return;
+  }
+  if (g_pair_evt_valid[dev] && g_pair_last_stream[dev] != st) cudaStreamWaitEvent(st, g_pair_evt[dev], 0);
+}
+void pair_guard_end(int dev, cudaStream_t st) {  // g_pair_mu held
+  if (!g_pair_evt[dev]) return;
+  g_pair_evt_valid[dev] = cudaEventRecord(g_pair_evt[dev], st) == cudaSuccess;
+  g_pair_last_stream[dev] = st;
 }
 
 template <int HB, int MODE>
@@ -725,17 +827,19 @@ int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
   using KCfg = Cfg2<HB>;
   const ConvTC& w = *p.w;
   const ConvTC& w2 = p.w2 ? *p.w2 : *p.w;
-  static bool configured = false;
-  if (!configured) {
-    SSB_CUDA(cudaFuncSetAttribute(conv_gemm_tc2_kernel<HB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::SMEM));
-    configured = true;
-  }
+  static std::atomic<bool> configured[MAX_DEV];
+  if (configure_once(conv_gemm_tc2_kernel<HB, MODE>, configured, KCfg::SMEM)) return -2;
+  static std::atomic<long long>* const counter = [] {
+    static char name[48];
+    snprintf(name, sizeof(name), "tc2<%d,%s>", HB, mode_name(MODE));
+    return variant_counter(name);
+  }();
   CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo;
-  if (make_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
-  if (make_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (cached_act_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
+  if (cached_act_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, BM)) return -1;
   if (p.w2) {
-    if (make_map(&ta2_hi, p.A2_hi, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
-    if (make_map(&ta2_lo, p.A2_lo, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+    if (cached_act_map(&ta2_hi, p.A2_hi, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
+    if (cached_act_map(&ta2_lo, p.A2_lo, (uint64_t)p.rows_total, (uint64_t)w2.Cin, BM)) return -1;
   } else {
     ta2_hi = ta_hi;
     ta2_lo = ta_lo;
@@ -743,12 +847,22 @@ int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
   tp.NT = w.N / (2 * HB);
   const int total = ((tp.ntiles + 1) / 2) * tp.NT;
   const int ncl = total < num_sms / 2 ? total : num_sms / 2;
-  const bool serialize = pair_serialize_begin(ctx.stream);
-  conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
-                                                                           w2.tm2_hi, w2.tm2_lo, tp);
-  SSB_CUDA(cudaGetLastError());
-  if (serialize) pair_serialize_end(ctx.stream);
+  {
+    const bool guard = pair_guard_enabled();
+    const int dev = guard ? current_device() : 0;
+    std::unique_lock<std::mutex> lk(g_pair_mu, std::defer_lock);
+    if (guard) {
+      lk.lock();
+      pair_guard_begin(dev, ctx.stream);
+    }
+    conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
+                                                                             w2.tm2_hi, w2.tm2_lo, tp);
+    const cudaError_t le = cudaGetLastError();
+    if (guard) pair_guard_end(dev, ctx.stream);
+    SSB_CUDA(le);
+  }
   ++g_launches;
+  counter->fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 template <int HB>
@@ -763,7 +877,33 @@ int launch_pair(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
 }  // namespace
 
 bool tc_available() { return get_encode() != nullptr; }
-int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols, int box_rows) { return make_map(m, ptr, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows); }
+int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols, int box_rows) {
+  return cached_act_map(m, ptr, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows);
+}
+long long variant_launch_count(const char* name) {
+  const int n = g_nvariants.load();
+  for (int i = 0; i < n; ++i)
+    if (strcmp(g_variants[i].name, name) == 0) return g_variants[i].n.load();
+  return 0;
+}
+int variant_names(char* buf, int cap) {  // ';'-separated list of the variants launched so far
+  int o = 0;
+  const int n = g_nvariants.load();
+  for (int i = 0; i < n; ++i) {
+    const int l = (int)strlen(g_variants[i].name);
+    if (o + l + 2 > cap) break;
+    memcpy(buf + o, g_variants[i].name, l);
+    o += l;
+    buf[o++] = ';';
+  }
+  if (cap > 0) buf[o < cap ? o : cap - 1] = 0;
+  return n;
+}
+void tensor_map_cache_stats(long long* encodes, long long* hits) {
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  *encodes = g_map_encodes;
+  *hits = g_map_hits;
+}
 
 int make_weight_maps(ConvTC* w) {
   SSB_CHECK(w->Cin % BK == 0 && w->N % 64 == 0, "tensor-core path needs Cin % 64 == 0 and N % 64 == 0");
@@ -801,14 +941,7 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
             "conv_gemm_tc: unsupported epilogue activation");
   SSB_CHECK(p.e.plane_act == ACT_NONE || p.e.plane_act == ACT_LRELU, "conv_gemm_tc: unsupported plane activation");
   SSB_CHECK(p.e.mode != EPI_GENERIC || p.e.out || p.e.oh, "conv_gemm_tc: GENERIC epilogue without an output");
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
-  }
+  const int num_sms = device_sms();
   TCParams tp;
   tp.tiles = p.tiles; tp.ntiles = p.ntiles; tp.taps = w.taps; tp.kchunks = w.Cin / BK;
   tp.kchunks2 = p.w2 ? p.w2->Cin / BK : 0;

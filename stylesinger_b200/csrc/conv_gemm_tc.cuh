@@ -15,7 +15,8 @@
 // An optional SECOND operand pair (A2, W2: 1 tap, no shift) extends the K loop: the DiffNet layer
 // GEMM contracts [3 taps x C of y | 256 of cond] in one accumulator, so the conditioner projection
 // needs neither a hoisted [rows, L*2C] fp32 buffer nor an epilogue read.
-// Env switches (diagnostics): SSB_TC_NO_PAIR=1 disables the pair kernel, SSB_TC_BN256=1 enables 256-wide single-CTA
+// Env switches (diagnostics): SSB_TC_NO_PAIR=1 disables the pair kernel, SSB_TC_PAIR_CONCURRENT=1 lifts the cross-stream
+// serialisation of pair kernels (conv_gemm_tc.cu), SSB_TC_BN256=1 enables 256-wide single-CTA
 // tiles, SSB_TC_DEBUG=<bits> switches parts of the kernel off for tools/gemm_probe.py (results are then garbage).
 #pragma once
 #include <cuda.h>
@@ -84,6 +85,11 @@ int make_weight_maps(ConvTC* w);
 // TMA descriptor of an activation plane [rows, cols] fp16 (box 128 rows x 64 cols, 128B swizzle)
 int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols, int box_rows = 128);
 int conv_gemm_tc(Ctx& ctx, const GemmTC& p);
+// diagnostics: launches of one kernel variant ("tc2<128,GATE>", "tc<64,GENERIC>", ...), the variants seen so far,
+// and the activation-descriptor cache counters
+long long variant_launch_count(const char* name);
+int variant_names(char* buf, int cap);
+void tensor_map_cache_stats(long long* encodes, long long* hits);
 // x fp32 [rows, ld] -> hi/lo planes [rows, C] (all rows incl. guards; guards stay zero)
 int split_planes(Ctx& ctx, const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo);
 

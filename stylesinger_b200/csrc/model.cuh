@@ -40,6 +40,7 @@ struct DevicePool {
   ~DevicePool();
   float* upload(const std::vector<float>& h);
   float* alloc(size_t n);
+  void release(void* p);  // free one buffer of the pool early (schedule tables replaced by ssb_model_set_schedule)
 };
 
 struct TensorMap {

@@ -9,7 +9,7 @@
 
 namespace ssb {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
@@ -22,6 +22,16 @@ float* DevicePool::alloc(size_t n) {
   if (cudaMalloc(&p, (n ? n : 1) * sizeof(float)) != cudaSuccess) return nullptr;
   ptrs.push_back(p);
   return (float*)p;
+}
+void DevicePool::release(void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < ptrs.size(); ++i)
+    if (ptrs[i] == p) {
+      cudaFree(p);  // synchronises the device: no kernel can still be reading the buffer
+      ptrs[i] = ptrs.back();
+      ptrs.pop_back();
+      return;
+    }
 }
 float* DevicePool::upload(const std::vector<float>& h) {
   float* d = alloc(h.size());
@@ -613,18 +623,25 @@ int set_schedule(Model* m, int which, int T, const float* step_emb, const float*
   std::vector<float> g(gtab, gtab + (size_t)T * 8);
   if (which == 0) {
     Denoiser& d = m->melnet;
+    float *old_d = d.dtab, *old_g = d.gtab;  // a T sweep re-sets the schedule: the previous tables are released
     if (build_dtab(d, m->pool, T, step_emb, stream)) return -1;
     d.gtab = m->pool.upload(g);
     d.gtab_h = g;
+    m->pool.release(old_d);
+    m->pool.release(old_g);
   } else {
     SSB_CHECK(mtab != nullptr, "set_schedule: multinomial table required for the F0 nets");
     std::vector<float> mt(mtab, mtab + (size_t)T * 8);
     for (int i = 0; i < 2; ++i) {
       Denoiser& d = m->f0net[i];
+      float *old_d = d.dtab, *old_g = d.gtab, *old_m = d.mtab;
       if (build_dtab(d, m->pool, T, step_emb, stream)) return -1;
       d.gtab = m->pool.upload(g);
       d.mtab = m->pool.upload(mt);
       d.gtab_h = g;
+      m->pool.release(old_d);
+      m->pool.release(old_g);
+      m->pool.release(old_m);
     }
   }
   SSB_CUDA(cudaStreamSynchronize(stream));

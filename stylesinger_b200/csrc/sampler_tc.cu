@@ -15,6 +15,8 @@
 #include <string.h>
 
 #include "philox.cuh"
+#include <mutex>
+
 #include "sampler_tc.cuh"
 #include "tc_common.cuh"
 
@@ -449,12 +451,22 @@ int x80_planes(Ctx& ctx, const float* x, int64_t rows, __half* hi, __half* lo) {
 }
 
 int sampler_tc_max_clusters(int cs) {
-  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  // per device: the shared-memory attribute and the occupancy answer belong to the device that is current
+  static std::mutex mu;
+  static int cache_all[64][9];
+  static bool init[64];
   if (cs < 1 || cs > 8) return 0;
-  if (cache[cs] >= 0) return cache[cs];
-  cudaFuncSetAttribute(sampler_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  int* cache = cache_all[dev];
+  if (!init[dev]) {
+    for (int i = 0; i < 9; ++i) cache[i] = -1;
+    init[dev] = true;
+  }
+  if (cache[cs] >= 0) return cache[cs];
+  cudaFuncSetAttribute(sampler_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -25,6 +25,12 @@ def lpt_assign(lengths, world: int) -> List[List[int]]:
     return bins
 
 
+def empty_batch() -> PackedBatch:
+    """The shard of a rank that received no utterance (fewer utterances than ranks)."""
+    z = np.zeros(1, np.int32)
+    return PackedBatch(0, z, z.copy(), z.copy(), {}, False)
+
+
 def _p2p_device(device):
     return torch.device(device) if device is not None else torch.device("cpu")
 
@@ -38,8 +44,10 @@ def scatter_utterances(utts: Optional[List[dict]], src: int = 0, device=None, pi
     if rank == src:
         lens = [int(u["mel2ph"].shape[0]) if "mel2ph" in u else int(len(u["txt_tokens"])) for u in utts]
         bins = lpt_assign(lens, world)
-        packed = [pack_batch([utts[i] for i in b], use_mel2ph=all("mel2ph" in utts[i] for i in b)) for b in bins]
-        meta = [{"B": p.B, "ph": p.ph_offsets, "ref": p.ref_offsets, "fr": p.frame_offsets, "idx": b,
+        # fewer utterances than ranks leaves some bins empty: those ranks get an empty batch (B = 0) and skip the compute
+        packed = [pack_batch([utts[i] for i in b], use_mel2ph=all("mel2ph" in utts[i] for i in b)) if b else empty_batch()
+                  for b in bins]
+        meta = [{"B": p.B, "ph": p.ph_offsets, "ref": p.ref_offsets, "fr": p.frame_offsets, "idx": b, "pad": p.may_have_pad_frames,
                  "shapes": {k: (tuple(v.shape), str(v.dtype)) for k, v in p.t.items()}} for p, b in zip(packed, bins)]
     else:
         packed, meta = None, [None] * world
@@ -60,9 +68,10 @@ def scatter_utterances(utts: Optional[List[dict]], src: int = 0, device=None, pi
             buf = torch.empty(shape, dtype=getattr(torch, dt.replace("torch.", "")), device=dev)
             dist.recv(buf, src=src)
             t[k] = buf.cpu()
-        pb = PackedBatch(m["B"], m["ph"], m["ref"], m["fr"], t)
+        pb = PackedBatch(m["B"], m["ph"], m["ref"], m["fr"], t, m["pad"])
     if pin and torch.cuda.is_available():
-        pb = PackedBatch(pb.B, pb.ph_offsets, pb.ref_offsets, pb.frame_offsets, {k: v.pin_memory() for k, v in pb.t.items()})
+        pb = PackedBatch(pb.B, pb.ph_offsets, pb.ref_offsets, pb.frame_offsets, {k: v.pin_memory() for k, v in pb.t.items()},
+                         pb.may_have_pad_frames)
     return pb, m["idx"]
 
 

@@ -82,10 +82,12 @@ class PackedBatch:
     frame_offsets: Optional[np.ndarray]
     t: Dict[str, torch.Tensor] = field(default_factory=dict)  # txt_tokens, note, note_type (int32), note_dur,
     # spk_embed, emo_embed, ref_mels, ref_f0, [mel2ph int32], [f0], [uv]
+    may_have_pad_frames: bool = True  # False when the host knows every frame maps to a phone (mel2ph > 0 everywhere)
 
     def to(self, device, non_blocking=True):
         return PackedBatch(self.B, self.ph_offsets, self.ref_offsets, self.frame_offsets,
-                           {k: v.to(device, non_blocking=non_blocking) for k, v in self.t.items()})
+                           {k: v.to(device, non_blocking=non_blocking) for k, v in self.t.items()},
+                           self.may_have_pad_frames)
 
     def h2d_bytes(self):
         return int(sum(v.numel() * v.element_size() for v in self.t.values()))
@@ -110,11 +112,13 @@ def pack_batch(utts: List[dict], use_mel2ph=True, pin=False) -> PackedBatch:
          "spk_embed": torch.stack([u["spk_embed"] for u in utts]).float().contiguous(),
          "emo_embed": torch.stack([u["emo_embed"] for u in utts]).float().contiguous(),
          "ref_mels": cat("ref_mels", torch.float32), "ref_f0": cat("ref_f0", torch.float32)}
+    pad = False  # predicted durations: the length regulator never emits a zero entry inside an utterance
     if use_mel2ph:
         t["mel2ph"] = cat("mel2ph", torch.int32)
+        pad = bool((t["mel2ph"] <= 0).any())
     if pin and torch.cuda.is_available():
         t = {k: v.pin_memory() for k, v in t.items()}
-    return PackedBatch(B, po, ro, fo, t)
+    return PackedBatch(B, po, ro, fo, t, pad)
 
 
 class _Workspace:
@@ -261,7 +265,9 @@ class AcousticModel:
         o = AcousticOutputs()
         out = {}
         want = set(want)
-        if not skip_mel_diffusion:
+        if skip_mel_diffusion:
+            want.discard("mel_out")  # never written in that mode: do not hand back an uninitialised buffer
+        else:
             want.add("mel_out")
         for k in want:
             dt = torch.int32 if k in ("rq_codes", "mel2ph") else torch.float32

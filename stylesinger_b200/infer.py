@@ -6,6 +6,7 @@ batches.  Model + vocoder run in libstylesinger_b200.so; the mel / f0 hand-off b
 the device (the reference round-trips through numpy, inference/StyleSinger.py:54-63).
 """
 import ctypes as C
+import weakref
 from typing import List
 
 import numpy as np
@@ -13,6 +14,7 @@ import torch
 
 from ._lib import check, lib
 from .engine import AcousticModel, PackedBatch, Vocoder, pack_batch
+from .formats import norm_interp_f0
 from .hparams import resolve
 
 
@@ -29,14 +31,42 @@ class StyleSingerInfer:
         self.model = AcousticModel(model_state_dict, self.hparams, self.device)
         self.vocoder = Vocoder(vocoder_state_dict, vocoder_config, self.device)
         self._cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._pinned = []  # [(pinned tensor, weakref to the numpy array handed out last)]: see _host_out
+
+    def _host_out(self, n, dtype=torch.float32):
+        """A pinned host buffer of >= n elements for an asynchronous D2H copy.  Buffers are recycled only once the
+        caller has dropped every array sliced from them (tracked with a weakref), so results stay valid for as long as
+        they are referenced and a steady-state loop allocates nothing."""
+        for i, (t, ref) in enumerate(self._pinned):
+            if t.dtype == dtype and t.numel() >= n and (ref is None or ref() is None):
+                return i, t
+        t = torch.empty(max(int(n), 1), dtype=dtype).pin_memory()
+        self._pinned = [e for e in self._pinned if e[1] is None or e[1]() is not None or e[0].numel() >= n][-7:]
+        self._pinned.append((t, None))
+        return len(self._pinned) - 1, t
+
+    def _to_host(self, dev_tensor):
+        """device tensor -> numpy view of a pinned buffer (async copy on the current stream + one stream sync)."""
+        flat = dev_tensor.reshape(-1)
+        i, t = self._host_out(flat.numel(), flat.dtype)
+        t[:flat.numel()].copy_(flat, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        arr = t.numpy()[:flat.numel()].reshape(tuple(dev_tensor.shape))
+        self._pinned[i] = (t, weakref.ref(arr.base if arr.base is not None else arr))
+        return arr
 
     # ---- reference-compatible single-utterance path ------------------------------------------------
     def input_to_batch(self, item) -> PackedBatch:
-        """reference inference/StyleSinger.py:139-170 (B=1 assembly)."""
+        """reference inference/StyleSinger.py:139-170 (B=1 assembly).  ``item['f0']`` is the raw extractor output in Hz
+        (0 = unvoiced), exactly what ``preprocess_input`` produces: like the reference (:152) it goes through
+        ``norm_interp_f0`` (log2 Hz, unvoiced frames interpolated) before it becomes the style extractor's ``ref_f0``."""
+        hp = self.hparams
+        f0, _ = norm_interp_f0(np.asarray(item["f0"]), hp.get("pitch_norm", "log"), hp.get("use_uv", True),
+                               hp.get("f0_mean", 400.0), hp.get("f0_std", 100.0))
         u = {"txt_tokens": torch.as_tensor(item["ph_token"]).long(), "note": torch.as_tensor(item["note"]).long(),
              "note_dur": torch.as_tensor(item["note_dur"]).float(), "note_type": torch.as_tensor(item["note_type"]).long(),
              "spk_embed": torch.as_tensor(item["spk_embed"]).float(), "emo_embed": torch.as_tensor(item["emo_embed"]).float(),
-             "ref_mels": torch.as_tensor(item["mel"]).float(), "ref_f0": torch.as_tensor(item["f0"]).float()}
+             "ref_mels": torch.as_tensor(item["mel"]).float(), "ref_f0": torch.from_numpy(f0)}
         if item.get("mel2ph") is not None:
             u["mel2ph"] = torch.as_tensor(item["mel2ph"]).long()
         return pack_batch([u], use_mel2ph="mel2ph" in u)
@@ -70,7 +100,9 @@ class StyleSingerInfer:
                                       float(self.hparams["mel_vmax"]), C.c_void_p(self._cnt.data_ptr()), stream),
               "ssb_mel_postprocess")
         fo_v, f0_v = fo, f0
-        if int(self._cnt.item()) != n:  # rare: explicit mel2ph with zeros -> compact on the host side
+        # Frames whose mel is exactly zero only exist where an explicit mel2ph carries zeros (padding frames):
+        # pack_batch records that on the host, so the common case needs no device->host sync between model and vocoder.
+        if pb_dev.may_have_pad_frames and int(self._cnt.item()) != n:  # rare: compact on the host side
             keep = (mel.abs().sum(-1) > 0)
             k = keep.cpu().numpy()
             lens = [int(k[fo[i]:fo[i + 1]].sum()) for i in range(pb_dev.B)]
@@ -85,11 +117,11 @@ class StyleSingerInfer:
         """Host buffers in, host buffers out (H2D of the inputs, D2H of the waveform)."""
         pb_dev = pb.to(self.device)
         mel, f0, wav, fo_v = self.run_device(pb_dev, seed=seed, noise=noise, voc_noise=voc_noise)
-        wav_h = wav.cpu().numpy()
+        wav_h = self._to_host(wav)
         hop = self.vocoder.hop
         wavs = [wav_h[fo_v[i] * hop:fo_v[i + 1] * hop] for i in range(pb_dev.B)]
         if return_mel:
-            mel_h = mel.cpu().numpy()
+            mel_h = self._to_host(mel)
             fo = pb_dev.frame_offsets
             return wavs, [mel_h[fo[i]:fo[i + 1]] for i in range(pb_dev.B)]
         return wavs

@@ -16,13 +16,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, n=5):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from stylesinger_b200 import synth
     from stylesinger_b200.dist import gather_waveforms, scatter_utterances
-    n = 5
     utts = [synth.make_utterance(0.3 + 0.2 * i, utt_idx=i, ref_frames=20 + i) for i in range(n)] if rank == 0 else None
     pb, idx = scatter_utterances(utts, src=0)
     # every rank checks its shard against a local regeneration of the same utterances
@@ -61,6 +60,22 @@ def test_scatter_gather_world2_gloo():
     assert all(r[0] for r in res)
     all_idx = sorted(sum((r[2] for r in res), []))
     assert all_idx == [0, 1, 2, 3, 4]  # every utterance owned exactly once
+
+
+def test_scatter_gather_fewer_utterances_than_ranks():
+    """One utterance, two ranks: the rank without work gets an empty batch (B = 0) instead of hanging the collective."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, 1)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[0] for r in res)
+    assert sorted(sum((r[2] for r in res), [])) == [0]
 
 
 def test_lpt_balances_frames():

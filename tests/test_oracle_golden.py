@@ -1,11 +1,13 @@
 """Pin oracle/stylesinger_oracle.py against fixtures produced by the UNMODIFIED reference
 (tools/make_golden.py; the reference itself has no tests or golden vectors — SURVEY.md §4)."""
+import os
+
 import numpy as np
 import torch
 
 from oracle import stylesinger_oracle as O
 from stylesinger_b200.hparams import DEFAULT_VOCODER_CONFIG
-from tests.common import acoustic_sd, golden, hp_for, oracle_forward, utt_from_meta, vocoder_sd
+from tests.common import GOLDEN, acoustic_sd, golden, hp_for, oracle_forward, utt_from_meta, vocoder_sd
 
 TOL = 2e-5  # fp32 CPU, same op order up to BLAS blocking
 
@@ -81,3 +83,24 @@ def test_vocoder_matches_reference():
     assert [tuple(x[1]) for x in meta["noise_log"]] == [x[1] for x in ns.log][:3]
     assert _maxabs(w, g["wav"]) < TOL
     assert _maxabs(w2, g["wav_nof0"]) < TOL
+
+
+def test_schedules_match_reference_buffers_at_sweep_T():
+    """The oracle's and the product's schedule tables are written independently of each other; both must reproduce the
+    reference's registered buffers bit for bit at every T of BASELINE.json configs[4] (tools/make_golden.py sched)."""
+    from stylesinger_b200 import schedules as S
+    g = np.load(os.path.join(GOLDEN, "ref_schedules.npz"))
+    hp = hp_for(4)
+    for T in [int(t) for t in g["Ts"]]:
+        for net, mb in (("mel", hp["max_beta"]), ("f0", hp["f0_max_beta"])):
+            o = O._gauss_tables(T, mb)
+            p = S.gaussian_schedule(T, mb)
+            for k in p:
+                ref = g[f"{net}_T{T}_{k}"]
+                assert np.array_equal(o[k].numpy(), ref), (net, T, k, "oracle")
+                assert np.array_equal(p[k], ref), (net, T, k, "product")
+        om, pm = O._multi_tables(T, hp["f0_max_beta"]), S.multinomial_schedule(T, hp["f0_max_beta"])
+        for k in pm:
+            ref = g[f"f0_T{T}_{k}"]
+            assert np.array_equal(om[k].numpy(), ref), (T, k, "oracle")
+            assert np.array_equal(pm[k], ref), (T, k, "product")

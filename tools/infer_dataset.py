@@ -4,7 +4,10 @@ ragged batches and writes one wav per item.  Equivalent of `python tasks/run.py 
 (tasks/StyleSinger/stylesinger.py:168-275, which asserts B=1).
 
     python tools/infer_dataset.py --ckpt checkpoints/StyleSinger --vocoder checkpoints/hifigan --data data/binary/x/test \
-        --out infer_out [--batch 64] [--T 100] [--limit N] [--predict-durations]
+        --out infer_out [--batch 64] [--T 100] [--limit N] [--use-gt-dur]
+
+Like the reference's test_step (tasks/StyleSinger/stylesinger.py:177-180 with `use_gt_dur: false` in egs/stylesinger.yaml) the
+durations come from the duration predictor unless --use-gt-dur is given (then the items' ground-truth mel2ph is fed).
 """
 import argparse
 import os
@@ -25,7 +28,7 @@ def main():
     ap.add_argument("--T", type=int, default=100)
     ap.add_argument("--limit", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--predict-durations", action="store_true", help="ignore the items' mel2ph (use the duration predictor)")
+    ap.add_argument("--use-gt-dur", action="store_true", help="feed the items' ground-truth mel2ph (reference hparam use_gt_dur)")
     args = ap.parse_args()
 
     from scipy.io import wavfile
@@ -46,10 +49,10 @@ def main():
         order = sorted(range(n), key=lambda i: len(ds[i]["mel"]))
         for b0 in range(0, n, args.batch):
             idx = order[b0:b0 + args.batch]
-            utts = [formats.item_to_utterance(ds[i], hp, with_mel2ph=not args.predict_durations) for i in idx]
-            wavs = eng.infer_batch(utts, seed=args.seed + b0, use_mel2ph=not args.predict_durations)
-            for u, w in zip(utts, wavs):
-                name = str(u.get("item_name") or f"item{b0}")
+            utts = [formats.item_to_utterance(ds[i], hp, with_mel2ph=args.use_gt_dur) for i in idx]
+            wavs = eng.infer_batch(utts, seed=args.seed + b0, use_mel2ph=args.use_gt_dur)
+            for i, u, w in zip(idx, utts, wavs):
+                name = str(u.get("item_name") or f"item{i}")
                 wavfile.write(os.path.join(args.out, name + ".wav"), sr, np.asarray(w, np.float32))
             print(f"| {min(b0 + args.batch, n)}/{n} items", flush=True)
 

@@ -162,15 +162,37 @@ def case_vocoder(name, frames, seed):
     print("wrote", name, y.shape, float(y.abs().max()), float(y.std()))
 
 
+def case_schedules(name, Ts=(4, 25, 50, 100, 200, 500)):
+    """Registered schedule buffers of the reference's DiffusionDecoder / GaussianMultinomialDiffusion at several T
+    (shallow_diffusion_tts.py:86-119, gaussian_multinomial_diffusion.py:237-283): pins the oracle's and the product's
+    independently written schedule code, incl. the T values of BASELINE.json configs[4]."""
+    gk = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+          "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+          "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]
+    mk = ["log_alpha", "log_1_min_alpha", "log_cumprod_alpha", "log_1_min_cumprod_alpha"]
+    d = {"Ts": np.asarray(Ts, np.int64)}
+    for T in Ts:
+        model, hp, _ = build_reference_model(T)
+        for k in gk:
+            d[f"mel_T{T}_{k}"] = np32(getattr(model.postdiff, k))
+            d[f"f0_T{T}_{k}"] = np32(getattr(model.f0_gen, k))
+        for k in mk:
+            d[f"f0_T{T}_{k}"] = np32(getattr(model.f0_gen, k))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, len(d), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["small", "t25", "t100", "voc"]
+    which = sys.argv[1:] or ["small", "t25", "t100", "sched", "voc"]
     if "small" in which:
         case_model("ref_small_T4", T=4, frames=96, phones=12, ref_frames=64, seed=11, utt_idx=100)
     if "t25" in which:
         case_model("ref_f64_T25", T=25, frames=64, phones=8, ref_frames=48, seed=21, utt_idx=101, with_dur_case=False)
     if "t100" in which:  # the bench's step count (T=100 mel + 2 x 100 F0 steps) on a tiny utterance
         case_model("ref_f32_T100", T=100, frames=32, phones=4, ref_frames=32, seed=41, utt_idx=102, with_dur_case=False)
+    if "sched" in which:
+        case_schedules("ref_schedules")
     if "voc" in which:
         case_vocoder("ref_vocoder_f24", frames=24, seed=31)
