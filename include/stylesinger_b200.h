@@ -192,6 +192,11 @@ int ssb_vocoder_set_tensor_cores(ssb_vocoder_t* v, int32_t enable);
 /* 1 (default): small batches run the whole T-step mel sampler in ONE persistent cooperative kernel launch
  * (csrc/sampler_tc.cu); 0: one launch per GEMM (BASELINE.json configs[4] compares the two). */
 int ssb_model_set_persistent(ssb_model_t* m, int32_t enable);
+/* 0 (default): batches of more than 48 row tiles (~6 k frames) take the one-launch-per-GEMM path.  1: such batches are
+ * split into groups of consecutive utterances of <= 48 row tiles and every group runs the T-step mel sampler
+ * (shallow_diffusion_tts.py:303-304) as ONE persistent launch (production RNG mode only; each group draws from its own
+ * Philox stream).  This is the "persistent-kernel" arm of BASELINE.json configs[4] at batch 64. */
+int ssb_model_set_persistent_groups(ssb_model_t* m, int32_t enable);
 /* Decoder FFT blocks (modules/commons/transformer.py TransformerFFNLayer, conv k=9 -> gelu -> linear): run the FFN GEMMs
  * on the tcgen05 kernel for batches of >= 1024 frames (default on; 0 keeps them on the fp32 FFMA kernel). Returns the
  * new setting. */

@@ -515,6 +515,12 @@ int ssb_model_set_persistent(ssb_model_t* m, int32_t enable) {
   return m->m.persistent ? 1 : 0;
 }
 
+int ssb_model_set_persistent_groups(ssb_model_t* m, int32_t enable) {
+  SSB_CHECK(m, "null model");
+  m->m.persistent_groups = enable != 0;
+  return m->m.persistent_groups ? 1 : 0;
+}
+
 int ssb_op_conv1d_tc(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,
                      const float* b_host, int32_t N, int32_t k, int32_t dilation, float* out, void* stream) {
   SSB_CHECK(x && offsets && w_host && out, "null argument");

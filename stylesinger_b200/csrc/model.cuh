@@ -126,6 +126,7 @@ struct Model {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool persistent = true;  // single-launch persistent sampler for small batches (ssb_model_set_persistent)
+  bool persistent_groups = false;  // large batches: groups of <= 48 row tiles, one persistent launch each (mel sampler)
   bool use_tc = true;  // tcgen05 path for the denoiser layer GEMMs (ssb_model_set_tensor_cores)
   bool fft_tc = true;  // tcgen05 path for the decoder FFT blocks' FFN on long batches (ssb_model_set_fft_tensor_cores)
 };

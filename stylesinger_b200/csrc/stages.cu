@@ -568,22 +568,29 @@ int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond
                       const Seq* host_seq) {
   const Denoiser& d = m.melnet;
   SSB_CHECK(d.T > 0, "mel schedule not set: call ssb_model_set_schedule(which=0)");
-  // EXPERIMENTAL, off unless SSB_MEL_GROUP_FRAMES=<n> is set: utterances are independent,
-  // so the T x L loop can run per GROUP of utterances of ~n frames whose working set (x, skip, planes, cond:
-  // ~5 KB/frame) stays L2-resident across layers and steps.  A group of consecutive utterances is a contiguous slice
-  // of the guard-banded layout, so the sub-batch simply aliases the big buffers.  Production (Philox) mode only: the
-  // injected-noise tensors are strided by the whole batch; each group gets its own seed.
+  // Utterances are independent, so the T x L loop can run per GROUP of consecutive utterances (a contiguous slice of the
+  // guard-banded layout: the sub-batch simply aliases the big buffers).  Two users, production (Philox) mode only - the
+  // injected-noise tensors are strided by the whole batch; each group gets its own seed:
+  //  * SSB_MEL_GROUP_FRAMES=<n> (experiment): groups of ~n frames whose working set stays L2-resident;
+  //  * ssb_model_set_persistent_groups(1): groups of <= 48 row tiles, each run by the single-launch persistent kernel
+  //    (BASELINE.json configs[4]: persistent-kernel vs per-step-launch at batch 64).
   if (host_seq && !noise && !c.dry) {
     const char* ge = getenv("SSB_MEL_GROUP_FRAMES");
     const long gf = ge ? atol(ge) : 0;
-    if (gf > 0 && host_seq->total > gf + gf / 2) {
+    const bool by_tiles = m.persistent_groups && m.persistent && s.ntiles > 48;
+    if (by_tiles || (gf > 0 && host_seq->total > gf + gf / 2)) {
       int b0 = 0;
       int64_t tight0 = 0;
       int gi = 0;
+      auto tiles_of = [&](int b) { return (host_seq->len[b] + TILE_M - 1) / TILE_M; };
       while (b0 < host_seq->B) {
         int b1 = b0;
-        int64_t fr = 0;
-        while (b1 < host_seq->B && (b1 == b0 || fr + host_seq->len[b1] <= gf)) fr += host_seq->len[b1++];
+        int64_t fr = 0, nt = 0;
+        while (b1 < host_seq->B &&
+               (b1 == b0 || (by_tiles ? nt + tiles_of(b1) <= 48 : fr + host_seq->len[b1] <= gf))) {
+          nt += tiles_of(b1);
+          fr += host_seq->len[b1++];
+        }
         std::vector<int32_t> offs((size_t)(b1 - b0) + 1, 0);
         for (int b = b0; b < b1; ++b) offs[(size_t)(b - b0) + 1] = offs[(size_t)(b - b0)] + host_seq->len[b];
         Seq q;

@@ -11,18 +11,7 @@ import torch
 import torch.distributed as dist
 
 from .engine import PackedBatch, pack_batch
-
-
-def lpt_assign(lengths, world: int) -> List[List[int]]:
-    """Longest-processing-time-first assignment of utterances to ranks, balancing the total frame count
-    (cost is ~linear in frames x diffusion steps).  Returns, per rank, the utterance indices it owns."""
-    order = np.argsort(-np.asarray(lengths, dtype=np.float64), kind="stable")
-    loads, bins = [0.0] * world, [[] for _ in range(world)]
-    for i in order:
-        r = int(np.argmin(loads))
-        bins[r].append(int(i))
-        loads[r] += float(lengths[i])
-    return bins
+from .sharding import lpt_assign  # noqa: F401  (re-exported)
 
 
 def empty_batch() -> PackedBatch:
@@ -35,10 +24,12 @@ def _p2p_device(device):
     return torch.device(device) if device is not None else torch.device("cpu")
 
 
-def scatter_utterances(utts: Optional[List[dict]], src: int = 0, device=None, pin: bool = False):
+def scatter_utterances(utts: Optional[List[dict]], src: int = 0, device=None, pin: bool = False,
+                       keep_on_device: bool = False):
     """Rank `src` owns `utts` (list of per-utterance CPU tensors, see synth.make_utterance); every rank returns
-    (its PackedBatch on the host, the global indices of its utterances).  Metadata goes through
-    scatter_object_list, tensors through point-to-point send/recv (NCCL when `device` is a CUDA device)."""
+    (its PackedBatch, the global indices of its utterances).  Metadata goes through scatter_object_list, tensors
+    through point-to-point send/recv (NCCL over NVLink when `device` is a CUDA device, gloo on CPU).
+    `keep_on_device`: with a CUDA `device` the received shard stays in HBM (no host bounce before the engine call)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = _p2p_device(device)
     if rank == src:
@@ -61,15 +52,17 @@ def scatter_utterances(utts: Optional[List[dict]], src: int = 0, device=None, pi
             for k in sorted(packed[r].t.keys()):
                 dist.send(packed[r].t[k].to(dev), dst=r)
         pb = packed[src]
+        if keep_on_device and dev.type == "cuda":
+            pb = pb.to(dev)
     else:
         t = {}
         for k in sorted(m["shapes"].keys()):
             shape, dt = m["shapes"][k]
             buf = torch.empty(shape, dtype=getattr(torch, dt.replace("torch.", "")), device=dev)
             dist.recv(buf, src=src)
-            t[k] = buf.cpu()
+            t[k] = buf if (keep_on_device and dev.type == "cuda") else buf.cpu()
         pb = PackedBatch(m["B"], m["ph"], m["ref"], m["fr"], t, m["pad"])
-    if pin and torch.cuda.is_available():
+    if pin and torch.cuda.is_available() and not (keep_on_device and dev.type == "cuda"):
         pb = PackedBatch(pb.B, pb.ph_offsets, pb.ref_offsets, pb.frame_offsets, {k: v.pin_memory() for k, v in pb.t.items()},
                          pb.may_have_pad_frames)
     return pb, m["idx"]
@@ -103,3 +96,38 @@ def gather_waveforms(wavs: List[np.ndarray], idx: List[int], n_total: int, dst: 
     if flat.size:
         dist.send(torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float32)).to(dev), dst=dst)
     return None
+
+
+def gather_waveforms_device(wav: torch.Tensor, frame_offsets, hop: int, idx: List[int], n_total: int, dst: int = 0):
+    """Gather for device-resident results: `wav` is this rank's tight waveform tensor [sum_frames * hop] on its GPU
+    (utterance j of the shard = global utterance idx[j]); shards travel GPU -> GPU over NCCL and rank `dst` copies them
+    to pinned host memory once.  Rank `dst` returns the list of all waveforms (numpy views) in the original utterance
+    order, other ranks return None."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    fo = np.asarray(frame_offsets, np.int64)
+    lens = [int(fo[j + 1] - fo[j]) * hop for j in range(len(idx))]
+    metas = [None] * world
+    dist.all_gather_object(metas, {"idx": list(idx), "lens": lens})
+    if rank != dst:
+        if wav.numel():
+            dist.send(wav.contiguous(), dst=dst)
+        return None
+    total = int(sum(sum(m["lens"]) for m in metas))
+    host = torch.empty(max(total, 1), dtype=torch.float32).pin_memory() if wav.is_cuda else torch.empty(max(total, 1))
+    out, o = [None] * n_total, 0
+    for r in range(world):
+        tot = int(sum(metas[r]["lens"]))
+        if r == dst:
+            buf = wav.reshape(-1)
+        else:
+            buf = torch.empty(tot, dtype=torch.float32, device=wav.device)
+            if tot:
+                dist.recv(buf, src=r)
+        host[o:o + tot].copy_(buf[:tot], non_blocking=True)
+        for i, n in zip(metas[r]["idx"], metas[r]["lens"]):
+            out[i] = (o, n)
+            o += n
+    if wav.is_cuda:
+        torch.cuda.current_stream(wav.device).synchronize()
+    h = host.numpy()
+    return [h[a:a + n] for a, n in out]

@@ -175,6 +175,10 @@ class AcousticModel:
         """Single-launch persistent sampler kernel for small batches (True) vs one launch per GEMM (False)."""
         return bool(lib.ssb_model_set_persistent(self._h, 1 if enable else 0))
 
+    def set_persistent_groups(self, enable=True):
+        """Large batches: run the mel sampler as one persistent launch per group of <= 48 row tiles (default off)."""
+        return bool(lib.ssb_model_set_persistent_groups(self._h, 1 if enable else 0))
+
     def set_fft_tensor_cores(self, enable: bool) -> bool:
         """Decoder FFT-block FFN GEMMs on the tcgen05 kernel for batches of >= 1024 frames (default on)."""
         return bool(lib.ssb_model_set_fft_tensor_cores(self._h, 1 if enable else 0))

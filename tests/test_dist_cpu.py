@@ -37,8 +37,13 @@ def _worker(rank, world, port, q, n=5):
     # fake "waveforms": utterance index encoded in the samples
     wavs = [np.full(int(pb.frame_offsets[j + 1] - pb.frame_offsets[j]) * 4, float(i), np.float32) for j, i in enumerate(idx)]
     out = gather_waveforms(wavs, idx, n, dst=0)
+    # the device-tensor variant (NCCL on the GPU box) follows the same protocol: exercise it with CPU tensors over gloo
+    from stylesinger_b200.dist import gather_waveforms_device
+    flat = torch.from_numpy(np.concatenate(wavs)) if wavs else torch.zeros(0)
+    out2 = gather_waveforms_device(flat, pb.frame_offsets, 4, idx, n, dst=0)
     if rank == 0:
         ok = all(o is not None and np.all(o == float(i)) for i, o in enumerate(out))
+        ok = ok and all(np.array_equal(a, b) for a, b in zip(out, out2))
         lens = [len(o) for o in out]
         q.put((ok, lens, sorted(idx)))
     else:

@@ -1,39 +1,86 @@
-"""Import shim for the UNMODIFIED reference at /root/reference (build container only).
+"""Import shim for the UNMODIFIED reference (never for the product path).
 
-Used exclusively by tools/make_golden.py to generate the fixtures under tests/golden/.
-Nothing in tests/, bench.py or the package imports this at run time on the GPU box
-(the reference does not travel there).  Shims follow SURVEY.md §8(c): they only satisfy
-import-time dependencies that are unused on the hot path; no hot-path arithmetic is touched.
+The reference lives at /root/reference in the build container and - staged byte for byte by tools/stage_reference.py -
+under baseline/_ref/StyleSinger on the GPU box.  Users: tools/make_golden.py (fixtures), baseline/ref_harness.py (the
+reference arms of bench.py and tools/baseline_arms.py) and tests/test_gpu_reference_dropin.py.  Shims follow SURVEY.md
+§8(c): they only satisfy import-time dependencies that are unused on the hot path (librosa, matplotlib, resemblyzer,
+parselmouth, skimage, webrtcvad, ... are imported by reference files but never called between `ph` tokens and the
+waveform); no hot-path arithmetic is touched.
 """
+import importlib.abc
+import importlib.machinery
 import os
 import sys
 import types
 
-REF = os.environ.get("STYLESINGER_REF", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _stub(name, **attrs):
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
-    sys.modules[name] = m
-    return m
+def find_reference():
+    for c in (os.environ.get("STYLESINGER_REF"), "/root/reference", os.path.join(_REPO, "baseline", "_ref", "StyleSinger")):
+        if c and os.path.isdir(os.path.join(c, "modules", "StyleSinger")):
+            return c
+    return None
 
 
-def install(T=100, f0_T=None):
-    """chdir to the reference, stub unused imports, load hparams. Returns the hparams dict."""
-    if not os.path.isdir(REF):
-        raise RuntimeError(f"reference not present at {REF}")
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    os.chdir(REF)
-    for n in ["librosa", "librosa.filters", "pycwt", "pycwt.wavelet", "chardet", "pyloudnorm",
-              "matplotlib", "matplotlib.pyplot", "resemblyzer", "parselmouth"]:
-        if n not in sys.modules:
-            _stub(n)
-    sys.modules["librosa"].filters = sys.modules["librosa.filters"]
-    sys.modules["pycwt"].wavelet = sys.modules["pycwt.wavelet"]
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.modules["matplotlib"].use = lambda *a, **k: None
+REF = find_reference()
+
+
+class _Dummy:
+    """Stands in for any attribute of a stubbed third-party module (classes, functions, constants)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Dummy()
+
+    def __getattr__(self, n):
+        if n.startswith("__"):
+            raise AttributeError(n)
+        return _Dummy()
+
+
+# third-party packages the reference imports at module level but never uses on the ph -> mel -> wav path
+_STUBBED = ("librosa", "pycwt", "chardet", "pyloudnorm", "matplotlib", "resemblyzer", "parselmouth", "skimage",
+            "webrtcvad", "tensorboardX", "g2p_en", "pypinyin", "jieba", "textgrid", "praatio", "pyworld", "soundfile",
+            "torchaudio", "nltk", "inflect", "unidecode", "pretty_midi", "miditoolkit", "h5py", "numba", "sklearn",
+            "Levenshtein", "editdistance", "textdistance")
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, name, path=None, target=None):
+        # last finder on sys.meta_path: only consulted for names no real finder could resolve
+        if name.split(".")[0] in _STUBBED:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = types.ModuleType(spec.name)
+        m.__path__ = []
+        m.__getattr__ = lambda attr: (_ for _ in ()).throw(AttributeError(attr)) if attr.startswith("__") else _Dummy
+        return m
+
+    def exec_module(self, module):
+        if module.__name__ == "matplotlib":
+            module.use = lambda *a, **k: None
+
+
+_finder = None
+
+
+def install(T=100, f0_T=None, overrides=None):
+    """chdir to the reference, stub unused imports, load hparams. Returns the reference's global hparams dict."""
+    global _finder
+    ref = find_reference()
+    if ref is None:
+        raise RuntimeError("reference not found (STYLESINGER_REF, /root/reference or baseline/_ref/StyleSinger)")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    os.chdir(ref)
+    if _finder is None:
+        _finder = _StubFinder()
+        sys.meta_path.append(_finder)  # after the real finders: only names nothing else can import are stubbed
     import scipy.signal
     import scipy.signal.windows
     if not hasattr(scipy.signal, "kaiser"):
@@ -47,4 +94,6 @@ def install(T=100, f0_T=None):
         sys.argv = saved
     hparams["timesteps"] = hparams["K_step"] = T
     hparams["f0_timesteps"] = f0_T if f0_T is not None else T
+    if overrides:
+        hparams.update(overrides)
     return hparams
