@@ -163,6 +163,25 @@ int ssb_f0_diffusion_sample(const ssb_model_t* m, int32_t which, const float* co
                             const float* unif_noise, uint64_t seed, float* f0_norm_out, int32_t* uv_out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-registry drop-ins.  The reference dispatches through FS_ENCODERS / FS_DECODERS
+ * (modules/fastspeech/fs2.py:9-18,30-31) and calls StyleSinger.get_style (modules/StyleSinger/stylesinger.py:189-214):
+ *  ssb_fft_encoder  = FastspeechEncoder.forward(txt_tokens) (tts_modules.py:326-346): tokens int32 [sumP] -> [sumP,256]
+ *                     (embedding * sqrt(H) + sinusoidal positions, FFT blocks, final LayerNorm, padding rows zero);
+ *  ssb_fft_decoder  = FastspeechDecoder.forward(x) (tts_modules.py:349-355, FFTBlocks.forward :281-306): x [sumF,256]
+ *                     -> [sumF,256], padding mask = rows of x that are all zero;
+ *  ssb_get_style    = get_style(decoder_inp, ref_mels, ...) with ret['ref_f0'] (LocalStyleAdaptor + RVQ + l1 +
+ *                     ProsodyAligner, lse.py:103-129,59-81): -> style [sumF,256], codes int32 [sumR,depth] (optional).
+ * which (workspace query): 0 encoder (offsets = ph_offsets), 1 decoder (offsets = frame_offsets). */
+size_t ssb_fft_workspace_bytes(const ssb_model_t* m, int32_t which, const int32_t* offsets, int32_t B);
+int ssb_fft_encoder(const ssb_model_t* m, const int32_t* txt_tokens, const int32_t* ph_offsets, int32_t B, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int ssb_fft_decoder(const ssb_model_t* m, const float* x, const int32_t* frame_offsets, int32_t B, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t ssb_get_style_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, const int32_t* ref_offsets, int32_t B);
+int ssb_get_style(const ssb_model_t* m, const float* decoder_inp, const int32_t* frame_offsets, const float* ref_mels,
+                  const float* ref_f0, const int32_t* ref_offsets, int32_t B, float* style_out, int32_t* codes_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* RQBottleneck.forward / VQEmbedding.find_nearest_embedding (modules/StyleSinger/RQ.py:262-270,29-55). */
 int ssb_rvq_lookup(const ssb_model_t* m, const float* x /*[sumR,256]*/, const int32_t* ref_offsets, int32_t B,
                    float* quant_out /*[sumR,256]*/, int32_t* codes_out /*[sumR,depth]*/, void* workspace,

@@ -56,7 +56,8 @@ EXPORTS = [
     "ssb_op_conv1d", "ssb_op_attention", "ssb_mel_postprocess", "ssb_launch_count",
     "ssb_model_set_tensor_cores", "ssb_op_conv1d_tc", "ssb_model_set_persistent", "ssb_model_set_fft_tensor_cores",
     "ssb_vocoder_set_tensor_cores", "ssb_variant_launch_count", "ssb_variant_names", "ssb_tensor_map_cache_stats",
-    "ssb_model_set_persistent_groups",
+    "ssb_model_set_persistent_groups", "ssb_fft_workspace_bytes", "ssb_fft_encoder", "ssb_fft_decoder",
+    "ssb_get_style_workspace_bytes", "ssb_get_style",
 ]
 
 
@@ -96,6 +97,11 @@ def _load():
         "ssb_model_set_fft_tensor_cores": (C.c_int, [vp, i32]),
         "ssb_vocoder_set_tensor_cores": (C.c_int, [vp, i32]),
         "ssb_op_conv1d_tc": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
+        "ssb_fft_workspace_bytes": (sz, [vp, i32, vp, i32]),
+        "ssb_fft_encoder": (C.c_int, [vp, vp, vp, i32, vp, vp, sz, vp]),
+        "ssb_fft_decoder": (C.c_int, [vp, vp, vp, i32, vp, vp, sz, vp]),
+        "ssb_get_style_workspace_bytes": (sz, [vp, vp, vp, i32]),
+        "ssb_get_style": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, sz, vp]),
         "ssb_variant_launch_count": (C.c_int64, [C.c_char_p]),
         "ssb_variant_names": (i32, [C.c_char_p, i32]),
         "ssb_tensor_map_cache_stats": (None, [P(C.c_int64), P(C.c_int64)]),

@@ -221,23 +221,10 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
   {
     const size_t mk = c.mark();
     float* xd = alloc_rows(c, sf, H);
-    float* keep = alloc_rows(c, sf, 1);
-    float* c0 = alloc_rows(c, sf, 1);
-    int32_t* pos = alloc_rows_i32(c, sf);
     WS_OK(c);
-    if (!c.dry) SSB_CUDA(cudaMemcpyAsync(xd, dec, (size_t)sf.rows * H * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
-    RUN(row_nonzero_mask(c, sf, dec, H, H, keep));
-    RUN(col0_nonzero_mask(c, sf, dec, H, c0));
-    RUN(positions_from_mask(c, sf, c0, pos));
-    RUN(add_positional(c, sf, xd, H, H, pos, m.pos_table, m.pos_rows, m.dec.pos_alpha));
-    {
-      CombineArgs a;
-      a.m[0] = xd; a.ldm[0] = H; a.rowmask = keep; a.out = xd; a.ldo = H; a.C = H;
-      RUN(combine_rows(c, sf, a));
-    }
     // long batches: the decoder's FFN GEMMs on the tcgen05 kernel (short ones stay on the fp32 FFMA path, which is
     // what the reference-golden parity tests pin)
-    RUN(fft_blocks(c, m.dec, sf, xd, keep, m.use_tc && m.fft_tc && tc_available() && sf.ntiles >= 8));
+    RUN(run_fft_decoder(c, m, sf, dec, xd, m.use_tc && m.fft_tc && tc_available() && sf.ntiles >= 8));
     {
       ConvGemm g = make_gemm(m.mel_out, sf, xd, H);
       g.e.rowmask = tgt; g.e.out = coarse; g.e.ldo = 80;
@@ -438,6 +425,89 @@ int ssb_f0_diffusion_sample(const ssb_model_t* m, int32_t which, const float* co
   RUN(unpack_rows(c, s, z, 1, f0_norm_out, 1, 1));
   RUN(unpack_rows_i32(c, s, uv, uv_out));
   return 0;
+}
+
+// ---- per-registry drop-ins (FS_ENCODERS / FS_DECODERS 'fft', StyleSinger.get_style) ------------------------------------
+static int fft_encoder_impl(Ctx& c, const Model& m, const int32_t* tokens, const int32_t* offs, int B, float* out) {
+  Seq q;
+  q.build(offs, B);
+  SSB_CHECK(q.maxlen + 2 <= m.pos_rows, "sequence longer than __pos_table");
+  SeqDev sp;
+  RUN(upload_layout(c, q, 1, &sp));
+  int32_t* tok = alloc_rows_i32(c, sp);
+  float* srcmask = alloc_rows(c, sp, 1);
+  float* enc = alloc_rows(c, sp, 256);
+  WS_OK(c);
+  RUN(pack_rows_i32(c, sp, tokens, tok));
+  RUN(run_encoder(c, m, sp, tok, nullptr, nullptr, nullptr, srcmask, enc));
+  return unpack_rows(c, sp, enc, 256, out, 256, 256);
+}
+static int fft_decoder_impl(Ctx& c, const Model& m, const float* x, const int32_t* offs, int B, float* out) {
+  Seq q;
+  q.build(offs, B);
+  SSB_CHECK(q.maxlen + 2 <= m.pos_rows, "frame sequence longer than __pos_table");
+  SeqDev sf;
+  RUN(upload_layout(c, q, 1, &sf));
+  float* xin = alloc_rows(c, sf, 256);
+  float* xd = alloc_rows(c, sf, 256);
+  WS_OK(c);
+  RUN(pack_rows(c, sf, x, 256, xin, 256, 256));
+  RUN(run_fft_decoder(c, m, sf, xin, xd, m.use_tc && m.fft_tc && tc_available() && sf.ntiles >= 8));
+  return unpack_rows(c, sf, xd, 256, out, 256, 256);
+}
+static int get_style_impl(Ctx& c, const Model& m, const float* dec_inp, const int32_t* foffs, const float* ref_mels,
+                          const float* ref_f0, const int32_t* roffs, int B, float* style_out, int32_t* codes_out) {
+  Seq qf, qr;
+  qf.build(foffs, B);
+  qr.build(roffs, B);
+  SSB_CHECK(qf.maxlen + 2 <= m.pos_rows && qr.maxlen + 2 <= m.pos_rows, "sequence longer than __pos_table");
+  SeqDev sf, sr;
+  RUN(upload_layout(c, qf, 1, &sf));
+  RUN(upload_layout(c, qr, 1, &sr));
+  float* dec0 = alloc_rows(c, sf, 256);
+  float* style = alloc_rows(c, sf, 256);
+  float* ref = alloc_rows(c, sr, 80);
+  float* reff0 = alloc_rows(c, sr, 1);
+  int32_t* codes = alloc_rows_i32(c, sr, m.hp.rq_depth);
+  WS_OK(c);
+  RUN(pack_rows(c, sf, dec_inp, 256, dec0, 256, 256));
+  RUN(pack_rows(c, sr, ref_mels, 80, ref, 80, 80));
+  RUN(pack_rows(c, sr, ref_f0, 1, reff0, 1, 1));
+  RUN(run_style(c, m, sf, sr, dec0, ref, reff0, style, codes, nullptr));
+  RUN(unpack_rows(c, sf, style, 256, style_out, 256, 256));
+  if (codes_out)
+    for (int d = 0; d < m.hp.rq_depth; ++d) RUN(unpack_cols_i32(c, sr, codes, m.hp.rq_depth, d, codes_out));
+  return 0;
+}
+
+size_t ssb_fft_workspace_bytes(const ssb_model_t* m, int32_t which, const int32_t* offsets, int32_t B) {
+  Ctx c = make_ctx(nullptr, 0, nullptr, true);
+  const int rc = which == 0 ? fft_encoder_impl(c, m->m, nullptr, offsets, B, nullptr)
+                            : fft_decoder_impl(c, m->m, nullptr, offsets, B, nullptr);
+  return rc == 0 ? c.high + 4096 : 0;
+}
+int ssb_fft_encoder(const ssb_model_t* m, const int32_t* txt_tokens, const int32_t* ph_offsets, int32_t B, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && txt_tokens && ph_offsets && out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  return fft_encoder_impl(c, m->m, txt_tokens, ph_offsets, B, out);
+}
+int ssb_fft_decoder(const ssb_model_t* m, const float* x, const int32_t* frame_offsets, int32_t B, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && x && frame_offsets && out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  return fft_decoder_impl(c, m->m, x, frame_offsets, B, out);
+}
+size_t ssb_get_style_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, const int32_t* ref_offsets, int32_t B) {
+  Ctx c = make_ctx(nullptr, 0, nullptr, true);
+  return get_style_impl(c, m->m, nullptr, frame_offsets, nullptr, nullptr, ref_offsets, B, nullptr, nullptr) == 0 ? c.high + 4096 : 0;
+}
+int ssb_get_style(const ssb_model_t* m, const float* decoder_inp, const int32_t* frame_offsets, const float* ref_mels,
+                  const float* ref_f0, const int32_t* ref_offsets, int32_t B, float* style_out, int32_t* codes_out,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && decoder_inp && frame_offsets && ref_mels && ref_f0 && ref_offsets && style_out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  return get_style_impl(c, m->m, decoder_inp, frame_offsets, ref_mels, ref_f0, ref_offsets, B, style_out, codes_out);
 }
 
 int ssb_rvq_lookup(const ssb_model_t* m, const float* x, const int32_t* ref_offsets, int32_t B, float* quant_out,

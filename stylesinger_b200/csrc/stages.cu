@@ -154,7 +154,34 @@ int run_encoder(Ctx& c, const Model& m, const SeqDev& sp, const int32_t* tok_g, 
     RUN(combine_rows(c, sp, a));
   }
   RUN(fft_blocks(c, m.enc, sp, enc_out, srcmask));
-  RUN(note_encoder(c, sp, note_g, type_g, ndur_g, m.note_emb, m.type_emb, m.dur_w, m.dur_b, 16.0f, enc_out, H, H, 1));
+  // StyleSinger.forward: encoder_out + note_encoder(note, note_dur, note_type) (stylesinger.py:124-126); a null note_g
+  // stops at FastspeechEncoder.forward (the FS_ENCODERS['fft'] drop-in, ssb_fft_encoder)
+  if (note_g) RUN(note_encoder(c, sp, note_g, type_g, ndur_g, m.note_emb, m.type_emb, m.dur_w, m.dur_b, 16.0f, enc_out, H, H, 1));
+  c.release(mk);
+  return 0;
+}
+
+// a16 body: FastspeechDecoder.forward = FFTBlocks.forward(x) with the padding mask taken from x itself
+// (tts_modules.py:281-306): xd [rows,256] in/out
+int run_fft_decoder(Ctx& c, const Model& m, const SeqDev& sf, const float* dec_in, float* xd, bool tc) {
+  const int H = 256;
+  const size_t mk = c.mark();
+  float* keep = alloc_rows(c, sf, 1);
+  float* c0 = alloc_rows(c, sf, 1);
+  int32_t* pos = alloc_rows_i32(c, sf);
+  WS_OK(c);
+  if (!c.dry && xd != dec_in)
+    SSB_CUDA(cudaMemcpyAsync(xd, dec_in, (size_t)sf.rows * H * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  RUN(row_nonzero_mask(c, sf, dec_in, H, H, keep));
+  RUN(col0_nonzero_mask(c, sf, dec_in, H, c0));
+  RUN(positions_from_mask(c, sf, c0, pos));
+  RUN(add_positional(c, sf, xd, H, H, pos, m.pos_table, m.pos_rows, m.dec.pos_alpha));
+  {
+    CombineArgs a;
+    a.m[0] = xd; a.ldm[0] = H; a.rowmask = keep; a.out = xd; a.ldo = H; a.C = H;
+    RUN(combine_rows(c, sf, a));
+  }
+  RUN(fft_blocks(c, m.dec, sf, xd, keep, tc));
   c.release(mk);
   return 0;
 }

@@ -322,6 +322,47 @@ class AcousticModel:
                                           ws.numel(), self._stream()), "ssb_f0_diffusion_sample")
         return z, uv
 
+    def fft_encoder(self, txt_tokens, ph_offsets):
+        """FastspeechEncoder.forward: int32 tokens [sumP] (device) -> [sumP,256]."""
+        po = np.ascontiguousarray(ph_offsets, np.int32)
+        B = len(po) - 1
+        n = lib.ssb_fft_workspace_bytes(self._h, 0, po.ctypes.data, B)
+        if n == 0:
+            check(-1, "ssb_fft_workspace_bytes")
+        ws = self._ws.get(n)
+        out = torch.empty((int(po[-1]), 256), dtype=torch.float32, device=self.device)
+        check(lib.ssb_fft_encoder(self._h, _ptr(txt_tokens), po.ctypes.data, B, _ptr(out), _ptr(ws), ws.numel(), self._stream()),
+              "ssb_fft_encoder")
+        return out
+
+    def fft_decoder(self, x, frame_offsets):
+        """FastspeechDecoder.forward: x [sumF,256] (device) -> [sumF,256]."""
+        fo = np.ascontiguousarray(frame_offsets, np.int32)
+        B = len(fo) - 1
+        n = lib.ssb_fft_workspace_bytes(self._h, 1, fo.ctypes.data, B)
+        if n == 0:
+            check(-1, "ssb_fft_workspace_bytes")
+        ws = self._ws.get(n)
+        out = torch.empty((int(fo[-1]), 256), dtype=torch.float32, device=self.device)
+        check(lib.ssb_fft_decoder(self._h, _ptr(x), fo.ctypes.data, B, _ptr(out), _ptr(ws), ws.numel(), self._stream()),
+              "ssb_fft_decoder")
+        return out
+
+    def get_style(self, decoder_inp, frame_offsets, ref_mels, ref_f0, ref_offsets):
+        """StyleSinger.get_style: (decoder_inp [sumF,256], ref_mels [sumR,80], ref_f0 [sumR]) -> (style [sumF,256], codes)."""
+        fo = np.ascontiguousarray(frame_offsets, np.int32)
+        ro = np.ascontiguousarray(ref_offsets, np.int32)
+        B = len(fo) - 1
+        n = lib.ssb_get_style_workspace_bytes(self._h, fo.ctypes.data, ro.ctypes.data, B)
+        if n == 0:
+            check(-1, "ssb_get_style_workspace_bytes")
+        ws = self._ws.get(n)
+        style = torch.empty((int(fo[-1]), 256), dtype=torch.float32, device=self.device)
+        codes = torch.empty((int(ro[-1]), self.hp["rq_depth"]), dtype=torch.int32, device=self.device)
+        check(lib.ssb_get_style(self._h, _ptr(decoder_inp), fo.ctypes.data, _ptr(ref_mels), _ptr(ref_f0), ro.ctypes.data, B,
+                                _ptr(style), _ptr(codes), _ptr(ws), ws.numel(), self._stream()), "ssb_get_style")
+        return style, codes
+
     def rvq(self, x, ref_offsets):
         ro = np.ascontiguousarray(ref_offsets, np.int32)
         B, Rs = len(ro) - 1, int(ro[-1])

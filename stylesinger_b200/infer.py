@@ -71,9 +71,11 @@ class StyleSingerInfer:
             u["mel2ph"] = torch.as_tensor(item["mel2ph"]).long()
         return pack_batch([u], use_mel2ph="mel2ph" in u)
 
-    def forward_model(self, inp, seed=0):
-        """reference inference/StyleSinger.py:41-64: returns the waveform (np.float32 [T*hop])."""
-        return self.infer_packed(self.input_to_batch(inp), seed=seed)[0]
+    def forward_model(self, inp, seed=0, noise=None, voc_noise=None, return_mel=False):
+        """reference inference/StyleSinger.py:41-64: returns the waveform (np.float32 [T*hop]).
+        `noise` / `voc_noise` inject the reference's random draws (parity tests); `return_mel` adds the raw mel_out."""
+        r = self.infer_packed(self.input_to_batch(inp), seed=seed, noise=noise, voc_noise=voc_noise, return_mel=return_mel)
+        return (r[0][0], r[1][0]) if return_mel else r[0]
 
     # ---- batched path --------------------------------------------------------------------------------
     def infer_batch(self, utts: List[dict], seed=0, use_mel2ph=True, return_mel=False):

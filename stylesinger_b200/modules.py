@@ -83,8 +83,30 @@ class StyleSinger:
     def eval(self):
         return self
 
+    def to(self, *a, **k):  # the reference driver calls model.to(device); the engine already lives on its GPU
+        return self
+
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)
+
+    def get_style(self, encoder_out, ref_mels, ret, infer=False, global_steps=0):
+        """modules/StyleSinger/stylesinger.py:189-214 with padded tensors (ret['ref_f0'] as there)."""
+        dev = self.engine.device
+        fl = _true_lengths(encoder_out)
+        rl = [max(int(v), 1) for v in (ref_mels.abs().sum(-1) > 0).sum(1).tolist()]
+        fo = np.concatenate([[0], np.cumsum(fl)]).astype(np.int32)
+        ro = np.concatenate([[0], np.cumsum(rl)]).astype(np.int32)
+        rf0 = ret["ref_f0"]
+        rf0 = rf0[None] if rf0.dim() == 1 else rf0
+        dec = torch.cat([encoder_out[i, :n] for i, n in enumerate(fl)]).to(dev, torch.float32).contiguous()
+        rm = torch.cat([ref_mels[i, :n] for i, n in enumerate(rl)]).to(dev, torch.float32).contiguous()
+        rf = torch.cat([rf0[i, :n] for i, n in enumerate(rl)]).to(dev, torch.float32).contiguous()
+        style, _ = self.engine.get_style(dec, fo, rm, rf, ro)
+        ret["rq_loss"], ret["gloss"] = 0.0, 0.0
+        out = packed_to_padded(style, fo)
+        if out.shape[1] < encoder_out.shape[1]:
+            out = torch.cat([out, out.new_zeros(out.shape[0], encoder_out.shape[1] - out.shape[1], out.shape[2])], 1)
+        return out
 
     def forward(self, txt_tokens, mel2ph=None, spk_embed=None, emo_embed=None, ref_mels=None, ref_f0=None,
                 f0=None, uv=None, skip_decoder=False, global_steps=0, infer=False, note=None, note_dur=None,
@@ -115,6 +137,8 @@ class StyleSinger:
         want = ["f0_denorm", "mel2ph", "decoder_inp", "style", "pitch_pred", "spk_proj", "emo_proj"]
         if not skip_decoder:
             want.append("mel_out" if run_diff else "coarse_mel")
+        if callable(noise):  # parity hooks: the injected draws depend on the (possibly predicted) frame count
+            noise = noise(pb.frame_offsets)
         out = self.engine.forward(pb, noise=noise, seed=seed, skip_mel_diffusion=not run_diff, dur=dur, want=tuple(want))
         fo = pb.frame_offsets
         m2p = packed_to_padded(out["mel2ph"].long(), fo)
@@ -132,6 +156,91 @@ class StyleSinger:
         for k in ("gdiff1", "gdiff2", "mdiff1", "mdiff2", "diff", "rq_loss", "gloss"):
             ret[k] = 0.0
         return ret
+
+
+def _true_lengths(x: torch.Tensor):
+    """Per batch element, the index after the last row that is not all zero (the reference's padding rows are zero)."""
+    nz = (x.abs().sum(-1) > 0)
+    L = x.shape[1]
+    idx = torch.arange(1, L + 1, device=x.device)[None, :] * nz
+    return [max(int(v), 1) for v in idx.max(dim=1).values.tolist()]
+
+
+class _Registered(torch.nn.Module):
+    """Common shell of the per-registry drop-ins: parameter-free nn.Modules (the reference assigns them where it holds
+    child modules, and calls .eval() / .to(device) on the tree); the weights live in the engine's packed model."""
+
+    def __init__(self, engine: AcousticModel):
+        super().__init__()
+        object.__setattr__(self, "engine", engine)
+
+
+class FastspeechEncoder(_Registered):
+    """FS_ENCODERS['fft'] drop-in (modules/fastspeech/fs2.py:9-13): ``forward(txt_tokens [B,T]) -> [B,T,256]``."""
+
+    def forward(self, txt_tokens):
+        dev = self.engine.device
+        lens = [max(int(v), 1) for v in (txt_tokens > 0).sum(1).tolist()]  # pad id 0 only ever trails (dictionary.pad())
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        tight = torch.cat([txt_tokens[i, :n] for i, n in enumerate(lens)]).to(dev, torch.int32).contiguous()
+        out = self.engine.fft_encoder(tight, offs)
+        pad = packed_to_padded(out, offs)
+        if pad.shape[1] < txt_tokens.shape[1]:
+            pad = torch.cat([pad, pad.new_zeros(pad.shape[0], txt_tokens.shape[1] - pad.shape[1], pad.shape[2])], 1)
+        return pad
+
+
+class FastspeechDecoder(_Registered):
+    """FS_DECODERS['fft'] drop-in (modules/fastspeech/fs2.py:15-18): ``forward(x [B,T,256]) -> [B,T,256]``."""
+
+    def forward(self, x, padding_mask=None, attn_mask=None, return_hiddens=False):
+        if padding_mask is not None or attn_mask is not None or return_hiddens:
+            raise NotImplementedError("FastspeechDecoder drop-in: only forward(x) (the call the StyleSinger path makes)")
+        dev = self.engine.device
+        lens = _true_lengths(x)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        tight = torch.cat([x[i, :n] for i, n in enumerate(lens)]).to(dev, torch.float32).contiguous()
+        out = packed_to_padded(self.engine.fft_decoder(tight, offs), offs)
+        if out.shape[1] < x.shape[1]:
+            out = torch.cat([out, out.new_zeros(out.shape[0], x.shape[1] - out.shape[1], out.shape[2])], 1)
+        return out
+
+
+class DiffNet(_Registered):
+    """DIFF_DECODERS['wavenet'] drop-in (modules/StyleSinger/stylesinger.py:38-40), called by the reference's sampler as
+    ``denoise_fn(spec [B,1,M,F], diffusion_step [B], cond [B,H,F]) -> [B,1,M,F]`` (shallow_diffusion_tts.py:146)."""
+
+    def forward(self, spec, diffusion_step, cond):
+        B, _, M, Fr = spec.shape
+        t = int(diffusion_step.reshape(-1)[0])
+        offs = (np.arange(B + 1) * Fr).astype(np.int32)
+        x = spec[:, 0].transpose(1, 2).reshape(B * Fr, M).to(self.engine.device, torch.float32).contiguous()
+        c = cond.transpose(1, 2).reshape(B * Fr, cond.shape[1]).to(self.engine.device, torch.float32).contiguous()
+        out = self.engine.denoiser_eval(0, x, None, t, c, offs)
+        return out.reshape(B, Fr, M).transpose(1, 2)[:, None].contiguous()
+
+
+class DDiffNet(_Registered):
+    """Drop-in for the two F0/UV denoisers (modules/diff/net.py:215-266), called from
+    GaussianMultinomialDiffusion.sample (gaussian_multinomial_diffusion.py:930-935) as
+    ``denoise_fn(f0 [B,1,F], uv [B,F] long, diffusion_step [B], cond [B,H,F], nonpadding [B,F]) -> [B,3,F]``.
+    which: 1 = gm_diffnet (domain-agnostic), 2 = gm_diffnet_inpainte (domain-specific)."""
+
+    def __init__(self, engine: AcousticModel, which: int):
+        super().__init__(engine)
+        self.which = which
+
+    def forward(self, f0, uv, diffusion_step, cond, nonpadding=None):
+        B, _, Fr = f0.shape
+        t = int(diffusion_step.reshape(-1)[0])
+        offs = (np.arange(B + 1) * Fr).astype(np.int32)
+        dev = self.engine.device
+        x = f0.reshape(B * Fr).to(dev, torch.float32).contiguous()
+        u = uv.reshape(B * Fr).to(dev, torch.int32).contiguous()
+        c = cond.transpose(1, 2).reshape(B * Fr, cond.shape[1]).to(dev, torch.float32).contiguous()
+        out = self.engine.denoiser_eval(self.which, x, u, t, c, offs)  # [B*F, 3]
+        out = out.reshape(B, Fr, 3).transpose(1, 2).contiguous()
+        return out if nonpadding is None else out * nonpadding[:, None, :].to(out.device)
 
 
 class HifiGAN:
