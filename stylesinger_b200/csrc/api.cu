@@ -256,7 +256,7 @@ int denoiser_eval_api(Ctx& c, const Model& m, int which, const SeqDev& s, const 
   SSB_CHECK(d.T > 0, "denoiser_eval: schedule not set");
   float* cond = alloc_rows(c, s, 256);
   DenoiserBufs b;
-  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
+  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b, false));  // a single evaluation: nothing to amortise a hoist over
   RUN(pack_rows(c, s, cond_tight, 256, cond, 256, 256));
   RUN(prepare_cond(c, d, s, cond, b));
   if (which == 0) {
@@ -271,7 +271,7 @@ int denoiser_eval_api(Ctx& c, const Model& m, int which, const SeqDev& s, const 
     RUN(pack_rows(c, s, x_tight, 1, z, 1, 1));
     RUN(pack_rows_i32(c, s, uv_tight, uv));
     const float* dt = d.dtab + (size_t)t * d.L * d.C;
-    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.x, b.y, d.C, b.yh, b.yl));
+    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.tc ? nullptr : b.x, b.y, d.C, b.yh, b.yl));
     RUN(denoiser_stack(c, d, s, t, b));
   }
   RUN(unpack_rows(c, s, b.head, b.ld_head, out_tight, d.out_dims, d.out_dims));
@@ -583,6 +583,12 @@ int ssb_model_set_persistent(ssb_model_t* m, int32_t enable) {
   SSB_CHECK(m, "null model");
   m->m.persistent = enable != 0;
   return m->m.persistent ? 1 : 0;
+}
+
+int ssb_model_set_cond_hoist(ssb_model_t* m, int32_t enable) {
+  SSB_CHECK(m, "null model");
+  m->m.cond_hoist = enable != 0;
+  return m->m.cond_hoist ? 1 : 0;
 }
 
 int ssb_model_set_persistent_groups(ssb_model_t* m, int32_t enable) {

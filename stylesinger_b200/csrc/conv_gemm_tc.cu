@@ -69,17 +69,33 @@ __device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int n
     if (!e.res) return;
     src = e.res + n; ld = e.ld_res;
   } else if constexpr (MODE == EPI_RES_SKIP) {
-    if (n < e.C) { src = e.res + n; ld = e.ld_res; }
-    else if (!e.skip_init) { src = e.skip + (n - e.C); ld = e.ld_skip; }
+    if (n < e.C) {
+      if (e.rh) {  // residual stream carried as fp16 hi/lo planes: 4 columns = 8 bytes per plane, packed into one float4
+        const __half* ph = e.rh + n + (lane & 7) * 4;
+        const __half* pl = e.rl + n + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          if (rr < nrows) {
+            const uint2 h = *reinterpret_cast<const uint2*>(ph + (r0 + rr) * e.ld_rh);
+            const uint2 l = *reinterpret_cast<const uint2*>(pl + (r0 + rr) * e.ld_rh);
+            p.a[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
+          }
+        }
+        return;
+      }
+      src = e.res + n; ld = e.ld_res;
+    } else if (!e.skip_init) { src = e.skip + (n - e.C); ld = e.ld_skip; }
     else return;
-  } else {
-    return;
+  } else {  // EPI_GATE: the hoisted conditioner projection of this layer
+    if (!e.add) return;
+    src = e.add + n; ld = e.ld_add;
   }
   src += (lane & 7) * 4;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rr = 4 * i + (lane >> 3);
-    if (rr < nrows) p.a[i] = *reinterpret_cast<const float4*>(src + (r0 + rr) * ld);
+    if (rr < nrows) p.a[i] = *reinterpret_cast<const float4*>(src + (int64_t)(r0 + rr) * ld);
   }
 }
 
@@ -107,20 +123,31 @@ __device__ __forceinline__ void split_store2(__half* hi, __half* lo, float a, fl
 template <int MODE>
 __device__ __forceinline__ void prefetch_tile_l2(const EpiTC& e, int2 t, int n0, int bn, int lane) {
   if (e.n_valid > 0 && n0 >= e.n_valid) return;
-  const float* s1 = nullptr;
-  const float* s2 = nullptr;
-  int ld1 = 0, ld2 = 0;
+  const char* s1 = nullptr;
+  const char* s2 = nullptr;
+  int64_t st1 = 0, st2 = 0;       // row strides in bytes
+  uint32_t b1 = 0, b2 = 0;        // bytes per row (multiples of 16)
   if constexpr (MODE == EPI_GENERIC) {
-    if (e.res) { s1 = e.res + n0; ld1 = e.ld_res; }
-    if (e.accum && e.out) { s2 = e.out + n0; ld2 = e.ldo; }
+    if (e.res) { s1 = reinterpret_cast<const char*>(e.res + n0); st1 = 4 * (int64_t)e.ld_res; b1 = (uint32_t)bn * 4u; }
+    if (e.accum && e.out) { s2 = reinterpret_cast<const char*>(e.out + n0); st2 = 4 * (int64_t)e.ldo; b2 = (uint32_t)bn * 4u; }
   } else if constexpr (MODE == EPI_RES_SKIP) {
-    if (n0 < e.C) { s1 = e.res + n0; ld1 = e.ld_res; }
-    else if (!e.skip_init) { s1 = e.skip + (n0 - e.C); ld1 = e.ld_skip; }
+    if (n0 < e.C) {
+      if (e.rh) {
+        s1 = reinterpret_cast<const char*>(e.rh + n0); s2 = reinterpret_cast<const char*>(e.rl + n0);
+        st1 = st2 = 2 * (int64_t)e.ld_rh; b1 = b2 = (uint32_t)bn * 2u;
+      } else {
+        s1 = reinterpret_cast<const char*>(e.res + n0); st1 = 4 * (int64_t)e.ld_res; b1 = (uint32_t)bn * 4u;
+      }
+    } else if (!e.skip_init) {
+      s1 = reinterpret_cast<const char*>(e.skip + (n0 - e.C)); st1 = 4 * (int64_t)e.ld_skip; b1 = (uint32_t)bn * 4u;
+    }
+  } else {  // EPI_GATE
+    if (e.add) { s1 = reinterpret_cast<const char*>(e.add + n0); st1 = 4 * (int64_t)e.ld_add; b1 = (uint32_t)bn * 4u; }
   }
-  const uint32_t bytes = (uint32_t)bn * 4u;
+  if (!s1 && !s2) return;
   for (int rr = lane; rr < t.y; rr += 32) {
-    if (s1) bulk_prefetch_l2(s1 + (int64_t)(t.x + rr) * ld1, bytes);
-    if (s2) bulk_prefetch_l2(s2 + (int64_t)(t.x + rr) * ld2, bytes);
+    if (s1) bulk_prefetch_l2(s1 + (int64_t)(t.x + rr) * st1, b1);
+    if (s2) bulk_prefetch_l2(s2 + (int64_t)(t.x + rr) * st2, b2);
   }
 }
 
@@ -154,11 +181,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     __half* ph = e.oh + rb * e.ldh + (n4 >> 1);
     __half* pl = e.ol + rb * e.ldh + (n4 >> 1);
 #pragma unroll
+    const bool has_add = e.add != nullptr;
     for (int i = 0; i < 8; ++i) {
       if (i < nsteps) {
         const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
-        const float z0 = sigmoidf_(acc.x + b0) * tanhf(acc.y + b1), z1 = sigmoidf_(acc.z + b2) * tanhf(acc.w + b3);
-        split_store2(ph + i * st, pl + i * st, z0, z1);
+        float g0 = acc.x + b0, f0 = acc.y + b1, g1 = acc.z + b2, f1 = acc.w + b3;
+        if (has_add) {
+          const float4 ad = pre.a[i];
+          g0 += ad.x; f0 += ad.y; g1 += ad.z; f1 += ad.w;
+        }
+        split_store2(ph + i * st, pl + i * st, sigmoidf_(g0) * tanhf(f0), sigmoidf_(g1) * tanhf(f1));
       }
     }
   } else if constexpr (MODE == EPI_RES_SKIP) {
@@ -167,7 +199,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       const bool planes = e.oh != nullptr;
       if (planes && e.vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
-      float* po = e.out + rb * e.ldo + n4;
+      const bool res_planes = e.rh != nullptr, has_out = e.out != nullptr;
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;  // step bias of the current layer: x = (hi + lo) - c
+      if (res_planes && e.vec1) { c0 = __ldg(e.vec1 + n4); c1 = __ldg(e.vec1 + n4 + 1); c2 = __ldg(e.vec1 + n4 + 2); c3 = __ldg(e.vec1 + n4 + 3); }
+      float* po = has_out ? e.out + rb * e.ldo + n4 : nullptr;
       const int64_t sto = 4 * (int64_t)e.ldo, sth = 4 * (int64_t)e.ldh;
       __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
       __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
@@ -175,10 +210,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
       for (int i = 0; i < 8; ++i) {
         if (i < nsteps) {
           const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
-          const float4 x0 = pre.a[i];
+          float4 x0 = pre.a[i];
+          if (res_planes) {  // (hi0 hi1 | hi2 hi3 | lo0 lo1 | lo2 lo3) as raw half2 bits
+            const uint32_t u0 = __float_as_uint(x0.x), u1 = __float_as_uint(x0.y), u2 = __float_as_uint(x0.z), u3 = __float_as_uint(x0.w);
+            const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&u0)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+            const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&u2)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&u3));
+            x0 = make_float4((h01.x + l01.x) - c0, (h01.y + l01.y) - c1, (h23.x + l23.x) - c2, (h23.y + l23.y) - c3);
+          }
           const float v0 = (acc.x + b0 + x0.x) * beta, v1 = (acc.y + b1 + x0.y) * beta;
           const float v2 = (acc.z + b2 + x0.z) * beta, v3 = (acc.w + b3 + x0.w) * beta;
-          *reinterpret_cast<float4*>(po + i * sto) = make_float4(v0, v1, v2, v3);
+          if (has_out) *reinterpret_cast<float4*>(po + i * sto) = make_float4(v0, v1, v2, v3);
           if (planes) split_store4(ph + i * sth, pl + i * sth, v0 + s0, v1 + s1, v2 + s2, v3 + s3);
         }
       }
@@ -367,18 +408,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
     }
   } else if (warp == 3) {
-    if constexpr (MODE != EPI_GATE) {
-      if ((int)blockIdx.x < total) {
-        const int mt = (int)blockIdx.x / p.NT, nt = (int)blockIdx.x - mt * p.NT;
-        prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
-      }
+    if ((int)blockIdx.x < total) {
+      const int mt = (int)blockIdx.x / p.NT, nt = (int)blockIdx.x - mt * p.NT;
+      prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int a = it & 1;
       if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);  // pace: one tile ahead of the epilogue
       __syncwarp();
-      if constexpr (MODE != EPI_GATE) {
+      {
         const int nx = tile + gridDim.x;
         if (nx < total) {
           const int mt = nx / p.NT, nt = nx - mt * p.NT;
@@ -571,17 +610,13 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int mt = 2 * mp + (int)rank;
       if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
     };
-    if constexpr (MODE != EPI_GATE) {
-      if (cid < total) pf(cid);
-    }
+    if (cid < total) pf(cid);
     int it = 0;
     for (int tile = cid; tile < total; tile += ncl, ++it) {
       const int a = it & 1;
       if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
       __syncwarp();
-      if constexpr (MODE != EPI_GATE) {
-        if (tile + ncl < total) pf(tile + ncl);
-      }
+      if (tile + ncl < total) pf(tile + ncl);
       if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
     }
   } else if (warp >= 4) {
@@ -941,6 +976,7 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
             "conv_gemm_tc: unsupported epilogue activation");
   SSB_CHECK(p.e.plane_act == ACT_NONE || p.e.plane_act == ACT_LRELU, "conv_gemm_tc: unsupported plane activation");
   SSB_CHECK(p.e.mode != EPI_GENERIC || p.e.out || p.e.oh, "conv_gemm_tc: GENERIC epilogue without an output");
+  SSB_CHECK(p.e.mode != EPI_RES_SKIP || p.e.res || (p.e.rh && p.e.rl), "conv_gemm_tc: RES_SKIP epilogue without a residual source");
   const int num_sms = device_sms();
   TCParams tp;
   tp.tiles = p.tiles; tp.ntiles = p.ntiles; tp.taps = w.taps; tp.kchunks = w.Cin / BK;

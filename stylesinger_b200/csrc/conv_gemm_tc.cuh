@@ -45,8 +45,14 @@ struct EpiTC {
   __half* oh = nullptr;          // GATE: z planes [rows, C];  RES_SKIP: y = x_new + vec2 planes [rows, C] (may be null)
   __half* ol = nullptr;
   int ldh = 0;
+  const float* add = nullptr;    // GATE: pre-activation addend [rows, ld_add] in packed (sigmoid, tanh) column order - the
+  int ld_add = 0;                //   hoisted, step-invariant conditioner projection of this layer (stages.cu prepare_cond)
   const float* res = nullptr;    // RES_SKIP: x [rows, ld_res]
   int ld_res = 0;
+  const __half* rh = nullptr;    // RES_SKIP, planes-only residual stream: x = (rh + rl) - vec1 is read from the fp16 hi/lo
+  const __half* rl = nullptr;    //   planes of y = x + step bias (the GATE GEMM's own A operand); no fp32 x is read or written
+  int ld_rh = 0;
+  const float* vec1 = nullptr;   //   step bias of the CURRENT layer [C]
   float beta = 1.0f;
   const float* vec2 = nullptr;   // RES_SKIP: step bias of the next layer [C]
   float* skip = nullptr;         // RES_SKIP: [rows, ld_skip]

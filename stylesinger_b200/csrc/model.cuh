@@ -77,6 +77,7 @@ struct Denoiser {
   Conv mlp0, mlp2;
   std::vector<DenoiserLayer> layers;
   Conv cond_all;                // 256 -> L*2C, gate-interleaved per layer
+  ConvTC cond_all_tc;           // the same stacked projection for the tcgen05 kernel (hoisted out of the T loop; no bias)
   Conv skip_proj, out_proj;
   // schedule-dependent (set by ssb_model_set_schedule)
   int T = 0;
@@ -126,6 +127,8 @@ struct Model {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool persistent = true;  // single-launch persistent sampler for small batches (ssb_model_set_persistent)
+  bool cond_hoist = true;   // tcgen05 per-launch path: conditioner projection computed once per call ([rows, L*2C] fp32) and
+                            // added in the GATE epilogue, instead of being contracted inside every layer GEMM of every step
   bool persistent_groups = false;  // large batches: groups of <= 48 row tiles, one persistent launch each (mel sampler)
   bool use_tc = true;  // tcgen05 path for the denoiser layer GEMMs (ssb_model_set_tensor_cores)
   bool fft_tc = true;  // tcgen05 path for the decoder FFT blocks' FFN on long batches (ssb_model_set_fft_tensor_cores)

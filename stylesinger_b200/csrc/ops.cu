@@ -364,7 +364,7 @@ __global__ void k_ddiff_input(const int4* utt, const float* z, const int32_t* uv
   const int cls = uv[r];
   for (int c = threadIdx.x; c < C; c += 32) {
     const float v = c < h ? (f * w[c] + bb[c]) : Euv[cls * h + (c - h)];
-    x[r * C + c] = v;
+    if (x) x[r * C + c] = v;
     const float yy = v + d0[c];
     if (y) y[r * C + c] = yy;
     if (yh) {

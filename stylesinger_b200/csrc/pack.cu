@@ -327,6 +327,16 @@ static int build_denoiser(TensorMap& tm, DevicePool& pool, const std::string& p,
       if (pack_conv_tc(pool, cw, 1, PACK_GATE_SIG_TANH, d->layers[i].bias_gate_tc, &d->layers[i].cond_tc)) return -1;
     }
   }
+  {  // tensor-core packing of the SAME stacked projection (no bias: bias_gate_tc already carries dil + conditioner bias):
+     // hoisted out of the T loop, its [rows, L*2C] output is the per-layer addend of the GATE epilogue (EpiTC::add)
+    std::vector<float> wt((size_t)L * N2 * H);  // torch layout [N = L*2C][Cin = 256][1], rows in packed column order
+    for (int pn = 0; pn < L * N2; ++pn)
+      for (int c = 0; c < H; ++c) wt[(size_t)pn * H + c] = Wc[(size_t)c * L * N2 + pn];
+    HostTensor ht;
+    ht.data = wt.data();
+    ht.shape = {L * N2, H, 1};
+    if (pack_conv_tc(pool, &ht, 1, PACK_PLAIN, nullptr, &d->cond_all_tc)) return -1;
+  }
   d->cond_all.W = pool.upload(Wc);
   d->cond_all.bias = pool.upload(Bc);
   d->cond_all.taps = 1; d->cond_all.Cin = H; d->cond_all.N = L * N2; d->cond_all.Npad = L * N2; d->cond_all.dil = 1; d->cond_all.center = 0;

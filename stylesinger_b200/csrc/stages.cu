@@ -357,7 +357,11 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
       {
         GemmTC g;
         g.A_hi = b.yh; g.A_lo = b.yl; g.rows_total = s.rows; g.w = &d.layers[l].dil_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
-        g.A2_hi = b.ch; g.A2_lo = b.cl; g.w2 = &d.layers[l].cond_tc;  // K = 3*C (taps of y) + 256 (cond)
+        if (b.condpre) {  // conditioner hoisted: K = 3*C only, the projection arrives as an epilogue addend
+          g.e.add = b.condpre + (size_t)l * 2 * C; g.e.ld_add = L * 2 * C;
+        } else {
+          g.A2_hi = b.ch; g.A2_lo = b.cl; g.w2 = &d.layers[l].cond_tc;  // K = 3*C (taps of y) + 256 (cond)
+        }
         g.e.mode = EPI_GATE; g.e.bias = d.layers[l].bias_gate_tc;
         g.e.oh = b.zh; g.e.ol = b.zl; g.e.ldh = C;
         RUN(conv_gemm_tc(c, g));
@@ -365,8 +369,10 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
       {
         GemmTC g;
         g.A_hi = b.zh; g.A_lo = b.zl; g.rows_total = s.rows; g.w = &d.layers[l].outp_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
-        g.e.mode = EPI_RES_SKIP; g.e.C = C; g.e.res = b.x; g.e.ld_res = C; g.e.beta = 0.70710678118654752440f;
-        g.e.out = b.x; g.e.ldo = C;
+        // residual stream carried ONLY as the fp16 hi/lo planes of y = x + step bias (in place: this epilogue reads
+        // y_l[row] and writes y_{l+1}[row] for the same rows/columns): no fp32 x is read or written in the T x L loop
+        g.e.mode = EPI_RES_SKIP; g.e.C = C; g.e.beta = 0.70710678118654752440f;
+        g.e.rh = b.yh; g.e.rl = b.yl; g.e.ld_rh = C; g.e.vec1 = dt + (size_t)l * C;
         if (l + 1 < L) { g.e.oh = b.yh; g.e.ol = b.yl; g.e.ldh = C; g.e.vec2 = dt + (size_t)(l + 1) * C; }
         g.e.skip = b.skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
         if (b.tc_heads && l == L - 1) { g.e.sh = b.skh; g.e.sl = b.skl; }
@@ -430,8 +436,9 @@ bool denoiser_tc_ok(const Model& m, const Denoiser& d) {
     if (!l.dil_tc.ok || !l.outp_tc.ok || !l.cond_tc.ok) return false;
   return true;
 }
-int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b) {
+int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b, bool hoist) {
   b->tc = tc;
+  b->condpre = nullptr;
   b->x = alloc_rows(c, s, d.C);
   b->y = b->zg = nullptr;
   b->yh = b->yl = b->zh = b->zl = b->ch = b->cl = nullptr;
@@ -455,6 +462,8 @@ int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, Denoiser
     b->zl = alloc_half_rows(c, s, d.C);
     b->ch = alloc_half_rows(c, s, 256);
     b->cl = alloc_half_rows(c, s, 256);
+    // only valid rows are ever written or read (epilogues are row-bounded): no 4.6 GB memset for batch64
+    if (hoist && d.cond_all_tc.ok) b->condpre = alloc_rows(c, s, d.L * 2 * d.C, false);
   } else {
     b->y = alloc_rows(c, s, d.C);
     b->zg = alloc_rows(c, s, d.C);
@@ -470,7 +479,14 @@ int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, Denoiser
 // Conditioner: tensor-core path -> fp16 hi/lo planes of cond (contracted inside every layer GEMM);
 // SIMT path -> the step-invariant projection of all L layers hoisted into one [rows, L*2C] buffer.
 int prepare_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, DenoiserBufs& b) {
-  if (b.tc) return split_planes(c, cond_g, 256, s.rows, 256, 1.0f, b.ch, b.cl);
+  if (b.tc) {
+    RUN(split_planes(c, cond_g, 256, s.rows, 256, 1.0f, b.ch, b.cl));
+    if (!b.condpre) return 0;
+    GemmTC g;  // all L conditioner projections at once: [rows, 256] x [256, L*2C], once per sampler call
+    g.A_hi = b.ch; g.A_lo = b.cl; g.rows_total = s.rows; g.w = &d.cond_all_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+    g.e.mode = EPI_GENERIC; g.e.out = b.condpre; g.e.ldo = d.L * 2 * d.C;
+    return conv_gemm_tc(c, g);
+  }
   ConvGemm g = make_gemm(d.cond_all, s, cond_g, 256);
   g.e.out = b.condall; g.e.ldo = d.L * 2 * d.C;
   return conv_gemm(c, g);
@@ -482,7 +498,7 @@ int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const f
     RUN(x80_planes(c, x80, s.rows, b.x80h, b.x80l));
     GemmTC g;
     g.A_hi = b.x80h; g.A_lo = b.x80l; g.rows_total = s.rows; g.w = &d.in_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
-    g.e.mode = EPI_GENERIC; g.e.bias = d.in_proj.bias; g.e.act = ACT_RELU; g.e.out = b.x; g.e.ldo = d.C;
+    g.e.mode = EPI_GENERIC; g.e.bias = d.in_proj.bias; g.e.act = ACT_RELU;  // planes of y = relu(in_proj) + step bias only
     g.e.oh = b.yh; g.e.ol = b.yl; g.e.ldh = d.C; g.e.vec2 = d.dtab + (size_t)t * d.L * d.C;
     RUN(conv_gemm_tc(c, g));
     return denoiser_stack(c, d, s, t, b);
@@ -641,7 +657,7 @@ int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond
     return run_mel_diffusion_persistent(c, m, s, cond_g, coarse_g, noise, seed, mel_tight);
   const size_t mk = c.mark();
   DenoiserBufs b;
-  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
+  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b, m.cond_hoist));
   float* xm = alloc_rows(c, s, 80);
   WS_OK(c);
   RUN(prepare_cond(c, d, s, cond_g, b));
@@ -819,7 +835,7 @@ int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const f
   }
   const size_t mk = c.mark();
   DenoiserBufs b;
-  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b));
+  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b, m.cond_hoist));
   RUN(prepare_cond(c, d, s, cond_g, b));
   const int T = d.T;
   const size_t per = (size_t)s.total;
@@ -827,7 +843,7 @@ int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const f
   RUN(f0_init(c, s, z, uv, gnoise, seed, sbase));
   for (int t = T - 1; t >= 0; --t) {
     const float* dt = d.dtab + (size_t)t * d.L * d.C;
-    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.x, b.y, d.C, b.yh, b.yl));
+    RUN(ddiff_input(c, s, z, uv, d.in_w, d.in_b, d.uv_emb, dt, b.tc ? nullptr : b.x, b.y, d.C, b.yh, b.yl));
     RUN(denoiser_stack(c, d, s, t, b));
     F0StepArgs a;
     a.z = z; a.uv = uv; a.out3 = b.head; a.ld3 = b.ld_head; a.lo = lo; a.hi = hi;

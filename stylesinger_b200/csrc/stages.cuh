@@ -13,6 +13,7 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
               const float* reff0_g, float* style, int32_t* codes, float* rq_in_out);
 struct DenoiserBufs {
   float *x, *y, *zg, *skip, *sbuf, *head, *condall;
+  float* condpre;             // tensor-core path with the hoisted conditioner: [rows, L*2C] fp32 pre-activation addends
   __half *yh, *yl, *zh, *zl;  // tensor-core path: fp16 hi/lo planes of y = x + step bias and of the gate output
   __half *ch, *cl;            // tensor-core path: fp16 hi/lo planes of the conditioner [rows,256]
   __half *skh, *skl, *sh, *sl;  // tensor-core heads: planes of the skip sum and of relu(skip_proj)
@@ -22,7 +23,7 @@ struct DenoiserBufs {
   bool tc;
 };
 bool denoiser_tc_ok(const Model& m, const Denoiser& d);
-int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b);
+int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, DenoiserBufs* b, bool hoist = false);
 int prepare_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g, DenoiserBufs& b);
 int mel_denoiser_eval(Ctx& c, const Denoiser& d, const SeqDev& s, int t, const float* x80, DenoiserBufs& b);
 int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBufs& b);

@@ -175,6 +175,10 @@ class AcousticModel:
         """Single-launch persistent sampler kernel for small batches (True) vs one launch per GEMM (False)."""
         return bool(lib.ssb_model_set_persistent(self._h, 1 if enable else 0))
 
+    def set_cond_hoist(self, enable=True):
+        """Conditioner projection hoisted out of the T loop (default) vs contracted inside every layer GEMM."""
+        return bool(lib.ssb_model_set_cond_hoist(self._h, 1 if enable else 0))
+
     def set_persistent_groups(self, enable=True):
         """Large batches: run the mel sampler as one persistent launch per group of <= 48 row tiles (default off)."""
         return bool(lib.ssb_model_set_persistent_groups(self._h, 1 if enable else 0))
@@ -303,7 +307,7 @@ class AcousticModel:
         C_ = self.hp["residual_channels"] if which == 0 else self.hp["f0_residual_channels"]
         L_ = self.hp["residual_layers"] if which == 0 else self.hp["f0_residual_layers"]
         rows = Fs + 16 * (B + 1) + 512
-        ws = self._ws.get(rows * (6 * C_ + 2 * C_ * L_ + 512) * 4 + (1 << 20))
+        ws = self._ws.get(rows * (12 * C_ + 2 * C_ * L_ + 1024) * 4 + (1 << 20))
         out = torch.empty((Fs, 80 if which == 0 else 3), dtype=torch.float32, device=self.device)
         check(lib.ssb_denoiser_eval(self._h, which, _ptr(x), _ptr(uv), int(t), _ptr(cond), fo.ctypes.data, B, _ptr(out),
                                     _ptr(ws), ws.numel(), self._stream()), "ssb_denoiser_eval")
@@ -314,7 +318,7 @@ class AcousticModel:
         B, Fs = len(fo) - 1, int(fo[-1])
         C_, L_ = self.hp["f0_residual_channels"], self.hp["f0_residual_layers"]
         rows = Fs + 16 * (B + 1) + 512
-        ws = self._ws.get(rows * (6 * C_ + 2 * C_ * L_ + 300) * 4 + (1 << 20))
+        ws = self._ws.get(rows * (12 * C_ + 2 * C_ * L_ + 1024) * 4 + (1 << 20))
         z = torch.empty(Fs, dtype=torch.float32, device=self.device)
         uv = torch.empty(Fs, dtype=torch.int32, device=self.device)
         check(lib.ssb_f0_diffusion_sample(self._h, which, _ptr(cond), _ptr(lo), _ptr(hi), fo.ctypes.data, B,
