@@ -111,6 +111,9 @@ typedef struct {
   const float* mel_noise;         /* dev [(T+1), sumF, 80]: q_sample then one per step */
   uint64_t seed;
   int32_t skip_mel_diffusion;     /* 1: stop after the coarse mel / diff_cond */
+  int32_t pndm_speedup;           /* 0: DDPM ancestral sampling, T steps (the StyleSinger default, DiffusionDecoder.forward);
+                                   * k > 0: PLMS with iteration interval k (hparams['pndm_speedup'],
+                                   * modules/diff/shallow_diffusion_tts.py:164-197,254-260): T / k (+1) denoiser evaluations */
 } ssb_acoustic_inputs;
 
 /* Outputs (all optional except mel_out/f0_denorm when diffusion runs); device, tight packed. */
@@ -147,6 +150,14 @@ size_t ssb_mel_diffusion_workspace_bytes(const ssb_model_t* m, const int32_t* fr
 int ssb_mel_diffusion_sample(const ssb_model_t* m, const float* cond, const float* coarse_mel,
                              const int32_t* frame_offsets, int32_t B, const float* noise, uint64_t seed,
                              float* mel_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* PLMS / PNDM sampler over the same DiffNet: GaussianDiffusion.p_sample_plms driven by the
+ * `pndm_speedup` loop of GaussianDiffusion.forward (modules/diff/shallow_diffusion_tts.py:164-197,254-260).
+ * interval = hparams['pndm_speedup']; q_noise [sumF,80] (tight) is the single q_sample draw, NULL = in-kernel Philox. */
+size_t ssb_mel_diffusion_plms_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, int32_t B);
+int ssb_mel_diffusion_sample_plms(const ssb_model_t* m, const float* cond, const float* coarse_mel,
+                                  const int32_t* frame_offsets, int32_t B, const float* q_noise, uint64_t seed,
+                                  int32_t interval, float* mel_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* One denoiser evaluation, DiffNet.forward / DDiffNet.forward (modules/diff/net.py:107-130,242-266).
  * which: 0 mel (x [sumF,80] -> eps [sumF,80]); 1 / 2 F0 agnostic / specific (x = f0 [sumF], uv int32 [sumF]

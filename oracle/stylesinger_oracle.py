@@ -438,6 +438,48 @@ def mel_diffusion_sample(cond, coarse_mel, sd, hp, noise, return_steps=False):
     return (mel, steps) if return_steps else mel
 
 
+def mel_diffusion_sample_plms(cond, coarse_mel, sd, hp, noise, interval):
+    """PLMS / PNDM sampler over the same DiffNet: GaussianDiffusion.p_sample_plms
+    (shallow_diffusion_tts.py:164-197) driven by the `pndm_speedup` loop of GaussianDiffusion.forward (:254-260):
+    T // interval denoiser evaluations (+1 for the first, second-order, step) instead of T; deterministic after q_sample.
+    cond [B,F,256], coarse_mel [B,F,80] -> mel [B,F,80]."""
+    T = hp["timesteps"]
+    s = _gauss_tables(T, hp["max_beta"])
+    ac = s["alphas_cumprod"]
+    smin = torch.tensor(hp["spec_min"], dtype=torch.float32)[None, None, :hp["keep_bins"]]
+    smax = torch.tensor(hp["spec_max"], dtype=torch.float32)[None, None, :hp["keep_bins"]]
+    c = cond.transpose(1, 2)
+    x0 = ((coarse_mel - smin) / (smax - smin) * 2 - 1).transpose(1, 2)[:, None]
+    x = s["sqrt_alphas_cumprod"][T - 1] * x0 + s["sqrt_one_minus_alphas_cumprod"][T - 1] * noise.randn(x0.shape)
+    B = x.shape[0]
+
+    def x_pred(x, eps, i):  # get_x_pred (:170-178), fp32 like the reference's registered buffers
+        a_t, a_prev = ac[i], ac[max(i - interval, 0)]
+        a_t_sq, a_prev_sq = a_t.sqrt(), a_prev.sqrt()
+        delta = (a_prev - a_t) * ((1 / (a_t_sq * (a_t_sq + a_prev_sq))) * x
+                                  - 1 / (a_t_sq * (((1 - a_prev) * a_t).sqrt() + ((1 - a_t) * a_prev).sqrt())) * eps)
+        return x + delta
+
+    hist = []  # deque(maxlen=4) in the reference; only the last three entries are ever read
+    for i in reversed(range(0, T, interval)):
+        t = torch.full((B,), i, dtype=torch.long)
+        eps = diffnet(x, t, c, sd, hp)
+        if len(hist) == 0:
+            xp = x_pred(x, eps, i)
+            eps_prev = diffnet(xp, torch.full((B,), max(i - interval, 0), dtype=torch.long), c, sd, hp)
+            prime = (eps + eps_prev) / 2
+        elif len(hist) == 1:
+            prime = (3 * eps - hist[-1]) / 2
+        elif len(hist) == 2:
+            prime = (23 * eps - 16 * hist[-1] + 5 * hist[-2]) / 12
+        else:
+            prime = (55 * eps - 59 * hist[-1] + 37 * hist[-2] - 9 * hist[-3]) / 24
+        x = x_pred(x, prime, i)
+        hist.append(eps)
+        hist = hist[-4:]
+    return (x[:, 0].transpose(1, 2) + 1) / 2 * (smax - smin) + smin
+
+
 def _log_add_exp(a, b):
     m = torch.max(a, b)
     return m + torch.log(torch.exp(a - m) + torch.exp(b - m))

@@ -38,7 +38,7 @@ class AcousticInputs(C.Structure):
                 ("spk_embed", C.c_void_p), ("emo_embed", C.c_void_p), ("ref_mels", C.c_void_p), ("ref_f0", C.c_void_p),
                 ("mel2ph", C.c_void_p), ("dur", C.c_void_p), ("f0", C.c_void_p), ("uv", C.c_void_p),
                 ("f0_gauss_noise", C.c_void_p * 2), ("f0_unif_noise", C.c_void_p * 2), ("mel_noise", C.c_void_p),
-                ("seed", C.c_uint64), ("skip_mel_diffusion", C.c_int32)]
+                ("seed", C.c_uint64), ("skip_mel_diffusion", C.c_int32), ("pndm_speedup", C.c_int32)]
 
 
 class AcousticOutputs(C.Structure):
@@ -56,7 +56,8 @@ EXPORTS = [
     "ssb_op_conv1d", "ssb_op_attention", "ssb_mel_postprocess", "ssb_launch_count",
     "ssb_model_set_tensor_cores", "ssb_op_conv1d_tc", "ssb_model_set_persistent", "ssb_model_set_fft_tensor_cores",
     "ssb_vocoder_set_tensor_cores", "ssb_variant_launch_count", "ssb_variant_names", "ssb_tensor_map_cache_stats",
-    "ssb_model_set_persistent_groups", "ssb_model_set_cond_hoist", "ssb_fft_workspace_bytes", "ssb_fft_encoder", "ssb_fft_decoder",
+    "ssb_model_set_persistent_groups", "ssb_model_set_cond_hoist", "ssb_mel_diffusion_plms_workspace_bytes",
+    "ssb_mel_diffusion_sample_plms", "ssb_fft_workspace_bytes", "ssb_fft_encoder", "ssb_fft_decoder",
     "ssb_get_style_workspace_bytes", "ssb_get_style",
 ]
 
@@ -80,6 +81,8 @@ def _load():
         "ssb_acoustic_forward": (C.c_int, [vp, P(AcousticInputs), P(AcousticOutputs), vp, sz, vp]),
         "ssb_mel_diffusion_workspace_bytes": (sz, [vp, vp, i32]),
         "ssb_mel_diffusion_sample": (C.c_int, [vp, vp, vp, vp, i32, vp, u64, vp, vp, sz, vp]),
+        "ssb_mel_diffusion_plms_workspace_bytes": (sz, [vp, vp, i32]),
+        "ssb_mel_diffusion_sample_plms": (C.c_int, [vp, vp, vp, vp, i32, vp, u64, i32, vp, vp, sz, vp]),
         "ssb_denoiser_eval": (C.c_int, [vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, sz, vp]),
         "ssb_f0_diffusion_sample": (C.c_int, [vp, i32, vp, vp, vp, vp, i32, vp, vp, u64, vp, vp, vp, sz, vp]),
         "ssb_rvq_lookup": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, sz, vp]),

@@ -245,7 +245,10 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
   if (out.diff_cond) RUN(unpack_rows(c, sf, cond, H, out.diff_cond, H, H));
   if (!in.skip_mel_diffusion) {
     SSB_CHECK(out.mel_out != nullptr, "acoustic: mel_out required");
-    RUN(run_mel_diffusion(c, m, sf, cond, coarse, in.mel_noise, in.seed, out.mel_out, &qf));
+    if (in.pndm_speedup > 0)  // PLMS: mel_noise, when given, supplies only the q_sample draw (its first [sumF, 80] block)
+      RUN(run_mel_diffusion_plms(c, m, sf, cond, coarse, in.mel_noise, in.seed, in.pndm_speedup, out.mel_out));
+    else
+      RUN(run_mel_diffusion(c, m, sf, cond, coarse, in.mel_noise, in.seed, out.mel_out, &qf));
   }
   return 0;
 }
@@ -375,6 +378,31 @@ static int mel_diff_impl(Ctx& c, const Model& m, const float* cond, const float*
   RUN(pack_rows(c, s, cond, 256, cg, 256, 256));
   RUN(pack_rows(c, s, coarse, 80, co, 80, 80));
   return run_mel_diffusion(c, m, s, cg, co, noise, seed, mel_out, &q);
+}
+static int mel_plms_impl(Ctx& c, const Model& m, const float* cond, const float* coarse, const int32_t* offs, int B,
+                         const float* q_noise, uint64_t seed, int interval, float* mel_out) {
+  Seq q;
+  q.build(offs, B);
+  SeqDev s;
+  RUN(upload_layout(c, q, 1, &s));
+  float* cg = alloc_rows(c, s, 256);
+  float* co = alloc_rows(c, s, 80);
+  WS_OK(c);
+  RUN(pack_rows(c, s, cond, 256, cg, 256, 256));
+  RUN(pack_rows(c, s, coarse, 80, co, 80, 80));
+  return run_mel_diffusion_plms(c, m, s, cg, co, q_noise, seed, interval, mel_out);
+}
+size_t ssb_mel_diffusion_plms_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, int32_t B) {
+  Ctx c = make_ctx(nullptr, 0, nullptr, true);
+  if (mel_plms_impl(c, m->m, nullptr, nullptr, frame_offsets, B, nullptr, 0, 1, nullptr) != 0) return 0;
+  return c.high + 4096;
+}
+int ssb_mel_diffusion_sample_plms(const ssb_model_t* m, const float* cond, const float* coarse_mel,
+                                  const int32_t* frame_offsets, int32_t B, const float* q_noise, uint64_t seed,
+                                  int32_t interval, float* mel_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && cond && coarse_mel && frame_offsets && mel_out && workspace, "null argument");
+  Ctx c = make_ctx(workspace, workspace_bytes, stream);
+  return mel_plms_impl(c, m->m, cond, coarse_mel, frame_offsets, B, q_noise, seed, interval, mel_out);
 }
 size_t ssb_mel_diffusion_workspace_bytes(const ssb_model_t* m, const int32_t* frame_offsets, int32_t B) {
   Ctx c = make_ctx(nullptr, 0, nullptr, true);

@@ -302,6 +302,29 @@ __global__ void k_mel_p_sample(const int4* utt, float* x, int ldx, const float* 
     x[r * ldx + c] = mean + sig * noise_n(noise, ti * 80 + c, seed, sid);
   }
 }
+// PLMS update (shallow_diffusion_tts.py:164-197).  prime = (w0*eps + w1*h1 + w2*h2 + w3*h3) / den; x_out = x + x_delta with
+//   x_delta = (a_prev - a_t) * (x / (sqrt(a_t) * (sqrt(a_t) + sqrt(a_prev)))
+//                               - prime / (sqrt(a_t) * (sqrt((1 - a_prev) * a_t) + sqrt((1 - a_t) * a_prev))))     (get_x_pred)
+// and, when hist_out is given, hist_out <- eps (the un-extrapolated prediction joins the history, :194).
+__global__ void k_plms_update(const int4* utt, PlmsArgs a) {
+  ROW_SETUP();
+  const float a_t = a.a_t, a_prev = a.a_prev;
+  const float a_t_sq = sqrtf(a_t), a_prev_sq = sqrtf(a_prev);
+  const float kx = 1.0f / (a_t_sq * (a_t_sq + a_prev_sq));
+  const float ke = 1.0f / (a_t_sq * (sqrtf((1.0f - a_prev) * a_t) + sqrtf((1.0f - a_t) * a_prev)));
+  const float da = a_prev - a_t;
+  for (int c = threadIdx.x; c < 80; c += 32) {
+    const float e = a.eps[r * a.lde + c];
+    float pr = a.w0 * e;
+    if (a.h1) pr += a.w1 * a.h1[r * 80 + c];
+    if (a.h2) pr += a.w2 * a.h2[r * 80 + c];
+    if (a.h3) pr += a.w3 * a.h3[r * 80 + c];
+    pr = pr / a.den;
+    const float xt = a.x[r * 80 + c];
+    a.x_out[r * 80 + c] = xt + da * (kx * xt - ke * pr);
+    if (a.hist_out) a.hist_out[r * 80 + c] = e;
+  }
+}
 __global__ void k_mel_denorm(const int4* utt, const float* x, int ldx, const float* smin, const float* smax,
                              const float* rowmask, float* mel, int ld) {
   ROW_SETUP();
@@ -705,6 +728,10 @@ int mel_q_sample(Ctx& ctx, const SeqDev& s, const float* coarse, int ldc, const 
 int mel_p_sample(Ctx& ctx, const SeqDev& s, float* x, int ldx, const float* eps, int lde, const float* noise,
                  const float* tab, uint64_t seed, uint64_t sid) {
   LAUNCH_ROWS(k_mel_p_sample, s, x, ldx, eps, lde, noise, tab, seed, sid);
+  return 0;
+}
+int plms_update(Ctx& ctx, const SeqDev& s, const PlmsArgs& a) {
+  LAUNCH_ROWS(k_plms_update, s, a);
   return 0;
 }
 int mel_denorm(Ctx& ctx, const SeqDev& s, const float* x, int ldx, const float* smin, const float* smax,

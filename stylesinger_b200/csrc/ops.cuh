@@ -83,6 +83,17 @@ int mel_q_sample(Ctx&, const SeqDev&, const float* coarse, int ldc, const float*
                  const float* spec_min, const float* spec_max, float sa, float s1a, float* x, int ldx,
                  uint64_t seed, uint64_t stream_id);
 // one reverse step: x <- c1*clamp(a*x - b*eps) + c2*x + sigma*noise
+struct PlmsArgs {  // one PLMS update over [rows, 80] guarded buffers (see k_plms_update)
+  const float* x = nullptr;      // x_t
+  float* x_out = nullptr;        // x_{t - interval} (may alias x)
+  const float* eps = nullptr;    // current prediction [rows, lde]
+  int lde = 0;
+  const float *h1 = nullptr, *h2 = nullptr, *h3 = nullptr;  // previous predictions, newest first (null: unused)
+  float w0 = 1.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, den = 1.f;
+  float a_t = 0.f, a_prev = 0.f;  // alphas_cumprod[t], alphas_cumprod[max(t - interval, 0)]
+  float* hist_out = nullptr;     // receives eps (null: the update is the first step's trial x_pred)
+};
+int plms_update(Ctx&, const SeqDev&, const PlmsArgs&);
 int mel_p_sample(Ctx&, const SeqDev&, float* x, int ldx, const float* eps, int lde, const float* noise,
                  const float* tab /*dev ptr to 8 floats for this t*/, uint64_t seed, uint64_t stream_id);
 int mel_denorm(Ctx&, const SeqDev&, const float* x, int ldx, const float* spec_min, const float* spec_max,

@@ -675,6 +675,64 @@ int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond
   return 0;
 }
 
+// f2: PLMS / PNDM sampler over the same denoiser (GaussianDiffusion.p_sample_plms + the pndm_speedup loop of
+// GaussianDiffusion.forward, shallow_diffusion_tts.py:164-197,254-260): T / interval evaluations (+1 for the first step).
+int run_mel_diffusion_plms(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
+                           const float* q_noise /*tight [total, 80] or null*/, uint64_t seed, int interval, float* mel_tight) {
+  const Denoiser& d = m.melnet;
+  SSB_CHECK(d.T > 0, "mel schedule not set: call ssb_model_set_schedule(which=0)");
+  SSB_CHECK(interval >= 1 && interval < d.T, "plms: interval (pndm_speedup) must be in [1, T)");
+  const size_t mk = c.mark();
+  DenoiserBufs b;
+  RUN(alloc_denoiser(c, d, s, denoiser_tc_ok(m, d), &b, m.cond_hoist));
+  float* xm = alloc_rows(c, s, 80);
+  float* xp = alloc_rows(c, s, 80);
+  float* hist[3] = {alloc_rows(c, s, 80), alloc_rows(c, s, 80), alloc_rows(c, s, 80)};
+  WS_OK(c);
+  RUN(prepare_cond(c, d, s, cond_g, b));
+  const int T = d.T;
+  auto acp = [&](int t) { return c.dry ? 0.5f : d.gtab_h[(size_t)t * 8 + 7]; };
+  const float sa = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 5], s1a = c.dry ? 0.f : d.gtab_h[(size_t)(T - 1) * 8 + 6];
+  RUN(mel_q_sample(c, s, coarse_g, 80, q_noise, m.spec_min, m.spec_max, sa, s1a, xm, 80, seed, 1000));
+  int nh = 0;  // predictions in the history; hist[(head + k) % 3] is the k-th newest
+  int head = 0;
+  int t0 = 0;
+  for (int t = 0; t < T; t += interval) t0 = t;  // reversed(range(0, T, interval)) starts at the largest multiple
+  for (int t = t0; t >= 0; t -= interval) {
+    const int tp = t - interval > 0 ? t - interval : 0;
+    RUN(mel_denoiser_eval(c, d, s, t, xm, b));
+    PlmsArgs a;
+    a.x = xm; a.eps = b.head; a.lde = b.ld_head; a.a_t = acp(t); a.a_prev = acp(tp);
+    const int slot = (head + 2) % 3;  // overwritten by this step's eps: the oldest entry
+    if (nh == 0) {
+      // second-order start: trial step with eps, second evaluation at the trial point, average (:182-185)
+      PlmsArgs p1 = a;
+      p1.x_out = xp; p1.hist_out = hist[slot];  // eps is saved before the head buffer is overwritten by the 2nd evaluation
+      RUN(plms_update(c, s, p1));
+      RUN(mel_denoiser_eval(c, d, s, tp, xp, b));
+      a.h1 = hist[slot]; a.w0 = 1.f; a.w1 = 1.f; a.den = 2.f;  // (eps + eps_prev) / 2 with eps_prev = current head
+      a.x_out = xm; a.hist_out = nullptr;
+      RUN(plms_update(c, s, a));
+    } else {
+      const float* h1 = hist[head];
+      const float* h2 = hist[(head + 1) % 3];
+      const float* h3 = hist[(head + 2) % 3];
+      if (nh == 1) { a.h1 = h1; a.w0 = 3.f; a.w1 = -1.f; a.den = 2.f; }
+      else if (nh == 2) { a.h1 = h1; a.h2 = h2; a.w0 = 23.f; a.w1 = -16.f; a.w2 = 5.f; a.den = 12.f; }
+      else { a.h1 = h1; a.h2 = h2; a.h3 = h3; a.w0 = 55.f; a.w1 = -59.f; a.w2 = 37.f; a.w3 = -9.f; a.den = 24.f; }
+      a.x_out = xm;
+      // the oldest entry (h3's slot) receives eps; with nh >= 3 the same element is read (h3) and then written by one thread
+      a.hist_out = hist[slot];
+      RUN(plms_update(c, s, a));
+    }
+    head = slot;
+    if (nh < 3) ++nh;
+  }
+  RUN(mel_denorm(c, s, xm, 80, m.spec_min, m.spec_max, nullptr, mel_tight, 80));
+  c.release(mk);
+  return 0;
+}
+
 // a13+a14 for BOTH F0 nets in one persistent launch: the agnostic and the specific sampler are independent
 // (stylesinger.py:223-225), so each phase of the table carries two entries (one per net, no barrier between them).
 int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, const float* cond0, const float* cond1,

@@ -30,6 +30,8 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
 // host_seq (optional): the host-side layout of `s`; enables the experimental utterance grouping (SSB_MEL_GROUP_FRAMES)
 int run_mel_diffusion(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
                       const float* noise, uint64_t seed, float* mel_tight, const Seq* host_seq = nullptr);
+int run_mel_diffusion_plms(Ctx& c, const Model& m, const SeqDev& s, const float* cond_g, const float* coarse_g,
+                           const float* q_noise, uint64_t seed, int interval, float* mel_tight);
 int run_f0_diffusion(Ctx& c, const Model& m, int which, const SeqDev& s, const float* cond_g, const float* lo,
                      const float* hi, const float* gnoise, const float* unoise, uint64_t seed, float* z, int32_t* uv,
                      const Seq* host_seq = nullptr);  // host_seq: see run_mel_diffusion (SSB_F0_GROUP_FRAMES)

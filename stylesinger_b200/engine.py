@@ -242,6 +242,7 @@ class AcousticModel:
                 a.mel_noise = noise["mel"].data_ptr()
         a.seed = int(seed)
         a.skip_mel_diffusion = 1 if skip_mel else 0
+        a.pndm_speedup = int(self.hp.get("pndm_speedup") or 0)  # reference hparam: 0 / absent = DDPM (the StyleSinger default)
         return a
 
     # -- entry points ------------------------------------------------------------------------------
@@ -299,6 +300,20 @@ class AcousticModel:
         mel = torch.empty((int(fo[-1]), 80), dtype=torch.float32, device=self.device)
         check(lib.ssb_mel_diffusion_sample(self._h, _ptr(cond), _ptr(coarse), fo.ctypes.data, B, _ptr(noise), int(seed),
                                            _ptr(mel), _ptr(ws), ws.numel(), self._stream()), "ssb_mel_diffusion_sample")
+        return mel
+
+    def mel_diffusion_plms(self, cond, coarse, frame_offsets, interval, q_noise=None, seed=0):
+        """PLMS sampler (hparams['pndm_speedup'] = interval) over the mel denoiser: T / interval (+1) evaluations."""
+        fo = np.ascontiguousarray(frame_offsets, np.int32)
+        B = len(fo) - 1
+        n = lib.ssb_mel_diffusion_plms_workspace_bytes(self._h, fo.ctypes.data, B)
+        if n == 0:
+            check(-1, "ssb_mel_diffusion_plms_workspace_bytes")
+        ws = self._ws.get(n)
+        mel = torch.empty((int(fo[-1]), 80), dtype=torch.float32, device=self.device)
+        check(lib.ssb_mel_diffusion_sample_plms(self._h, _ptr(cond), _ptr(coarse), fo.ctypes.data, B, _ptr(q_noise), int(seed),
+                                                int(interval), _ptr(mel), _ptr(ws), ws.numel(), self._stream()),
+              "ssb_mel_diffusion_sample_plms")
         return mel
 
     def denoiser_eval(self, which, x, uv, t, cond, frame_offsets):

@@ -101,8 +101,10 @@ def _check_supported(hp):
             raise NotImplementedError(
                 f"stylesinger_b200 implements the egs/stylesinger.yaml configuration only: "
                 f"hparams[{k!r}]={hp.get(k)!r}, required {v!r}")
-    if hp.get("pndm_speedup"):
-        raise NotImplementedError("pndm_speedup (PLMS sampler) is out of scope (SURVEY.md §8 f2)")
+    if hp.get("pndm_speedup"):  # PLMS sampler over the mel denoiser (ssb_mel_diffusion_sample_plms)
+        k = int(hp["pndm_speedup"])
+        if not (1 <= k < int(hp["timesteps"])):
+            raise ValueError(f"pndm_speedup must be in [1, timesteps), got {k}")
     if hp.get("rel_pos"):
         raise NotImplementedError("rel_pos is not selected by egs/stylesinger.yaml")
     if hp["K_step"] != hp["timesteps"]:

@@ -45,7 +45,7 @@ def sampler_table(T, max_beta):
     """Per-step scalars the sampler kernels consume, [T, 8] fp32:
     0 sqrt_recip_alphas_cumprod, 1 sqrt_recipm1_alphas_cumprod, 2 posterior_mean_coef1,
     3 posterior_mean_coef2, 4 sigma = [t>0]*exp(0.5*posterior_log_variance_clipped) (fp32 arithmetic),
-    5 sqrt_alphas_cumprod, 6 sqrt_one_minus_alphas_cumprod, 7 unused."""
+    5 sqrt_alphas_cumprod, 6 sqrt_one_minus_alphas_cumprod, 7 alphas_cumprod (PLMS sampler, get_x_pred)."""
     s = gaussian_schedule(T, max_beta)
     tab = np.zeros((T, 8), np.float32)
     tab[:, 0] = s["sqrt_recip_alphas_cumprod"]
@@ -57,6 +57,7 @@ def sampler_table(T, max_beta):
     tab[:, 4] = sig
     tab[:, 5] = s["sqrt_alphas_cumprod"]
     tab[:, 6] = s["sqrt_one_minus_alphas_cumprod"]
+    tab[:, 7] = s["alphas_cumprod"]
     return tab
 
 

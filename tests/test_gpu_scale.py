@@ -335,3 +335,59 @@ def test_encoder_out_matches_oracle():
     err = _maxabs(out["encoder_out"], r["encoder_out"][0])
     print("encoder_out L-inf", err)
     assert err < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# f2: PLMS sampler (pndm_speedup) on the same kernels
+def test_plms_sampler_matches_reference_golden_and_oracle():
+    from tests.common import golden
+    g, meta = golden("ref_plms_T100_i10")
+    T, k = meta["T"], meta["interval"]
+    m = acoustic_engine(T, 4)
+    Fr = g["cond"].shape[0]
+    ns = O.NoiseSource(meta["seed"] + 1)
+    q = ns.randn((1, 1, 80, Fr))[0, 0].t().contiguous()
+    offs = np.array([0, Fr], np.int32)
+    scale = float(np.abs(g["mel"]).max())
+    errs = {}
+    try:
+        for tc in (True, False):
+            m.set_tensor_cores(tc)
+            mel = m.mel_diffusion_plms(torch.from_numpy(g["cond"]).to(DEV), torch.from_numpy(g["coarse"]).to(DEV), offs, k, q.to(DEV))
+            errs[tc] = _maxabs(mel, g["mel"])
+    finally:
+        m.set_tensor_cores(True)
+    print(f"PLMS T={T} interval={k}: L-inf vs reference golden tc {errs[True]:.3e}, fp32 FFMA {errs[False]:.3e} (max |mel| {scale:.1f})")
+    assert errs[False] < 1e-4 * max(1.0, scale) and errs[True] < 1e-3 * max(1.0, scale)
+
+
+def test_plms_on_a_ragged_batch_vs_oracle_and_through_forward():
+    """Batch of 3 through ssb_mel_diffusion_sample_plms against the B=1 oracle, and hparams['pndm_speedup'] through the whole
+    acoustic forward (Philox mode: runs, finite, differs from the DDPM result)."""
+    from stylesinger_b200 import synth
+    from stylesinger_b200.engine import AcousticModel, pack_batch
+    T, k = 20, 5
+    hp = hp_for(T)
+    m = acoustic_engine(T, 4)
+    gen = torch.Generator().manual_seed(8)
+    lens = [130, 70, 257]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n = int(offs[-1])
+    cond = torch.randn(n, 256, generator=gen)
+    coarse = (-3 + 0.8 * torch.randn(n, 80, generator=gen)).clamp(-6, 0.5)
+    q = torch.randn(n, 80, generator=gen)
+    mel = m.mel_diffusion_plms(cond.to(DEV), coarse.to(DEV), offs, k, q.to(DEV))
+    for b in range(3):
+        a, e = int(offs[b]), int(offs[b + 1])
+        with torch.no_grad():
+            ref = O.mel_diffusion_sample_plms(cond[None, a:e], coarse[None, a:e], acoustic_sd(), hp,
+                                              ListNoise([q[a:e].t().contiguous()[None, None]]), k)
+        sc = max(1.0, float(ref.abs().max()))
+        assert _maxabs(mel[a:e], ref[0]) < 1e-3 * sc
+    hp2 = dict(hp, pndm_speedup=k)
+    m2 = AcousticModel(acoustic_sd(), hp2, DEV)
+    u = synth.make_utterance(0.5, utt_idx=5, ref_frames=40, frames=90, phones=8)
+    pb = pack_batch([u]).to(DEV)
+    a = m2.forward(pb, seed=3)["mel_out"].clone()
+    b_ = m.forward(pb, seed=3)["mel_out"].clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, b_)

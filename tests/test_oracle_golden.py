@@ -104,3 +104,17 @@ def test_schedules_match_reference_buffers_at_sweep_T():
             ref = g[f"f0_T{T}_{k}"]
             assert np.array_equal(om[k].numpy(), ref), (T, k, "oracle")
             assert np.array_equal(pm[k], ref), (T, k, "product")
+
+
+def test_plms_sampler_matches_reference():
+    """f2: oracle restatement of p_sample_plms + the pndm_speedup loop vs the reference run (tools/make_golden.py plms)."""
+    g, meta = golden("ref_plms_T100_i10")
+    hp = hp_for(meta["T"])
+    ns = O.NoiseSource(meta["seed"] + 1)
+    with torch.no_grad():
+        mel = O.mel_diffusion_sample_plms(torch.from_numpy(g["cond"])[None], torch.from_numpy(g["coarse"])[None], acoustic_sd(), hp,
+                                          ns, meta["interval"])
+    assert [[k, list(sh)] for k, sh in ns.log] == meta["noise_log"]
+    err = _maxabs(mel[0].numpy(), g["mel"])
+    scale = float(np.abs(g["mel"]).max())  # the extrapolating multistep update amplifies the synthetic denoiser's output
+    assert err < TOL * max(1.0, scale), (err, scale)

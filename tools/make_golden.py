@@ -162,6 +162,31 @@ def case_vocoder(name, frames, seed):
     print("wrote", name, y.shape, float(y.abs().max()), float(y.std()))
 
 
+def case_plms(name, T=100, interval=10, frames=48, seed=61):
+    """f2: the reference's PLMS sampler (GaussianDiffusion.p_sample_plms, shallow_diffusion_tts.py:164-197) driven exactly
+    as GaussianDiffusion.forward does under hparams['pndm_speedup'] (:254-260), on the StyleSinger mel denoiser (the
+    DiffusionDecoder instance inherits the method)."""
+    from collections import deque
+    model, hp, sd = build_reference_model(T)
+    pd = model.postdiff
+    g = torch.Generator().manual_seed(seed)
+    cond = torch.randn(1, frames, 256, generator=g)
+    coarse = (-3 + 0.8 * torch.randn(1, frames, 80, generator=g)).clamp(-6, 0.5)
+    ns = NoiseSource(seed + 1)
+    with torch.no_grad(), patched_rng(ns):
+        c = cond.transpose(1, 2)
+        fs2 = pd.norm_spec(coarse).transpose(1, 2)[:, None, :, :]
+        x = pd.q_sample(x_start=fs2, t=torch.tensor([T - 1]).long())
+        pd.noise_list = deque(maxlen=4)
+        for i in reversed(range(0, T, interval)):
+            x = pd.p_sample_plms(x, torch.full((1,), i, dtype=torch.long), interval, c)
+        mel = pd.denorm_spec(x[:, 0].transpose(1, 2))
+    d = {"meta": json.dumps({"T": T, "interval": interval, "frames": frames, "seed": seed, "noise_log": ns.log}),
+         "cond": np32(cond[0]), "coarse": np32(coarse[0]), "mel": np32(mel[0])}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, mel.shape, float(mel.abs().max()))
+
+
 def case_schedules(name, Ts=(4, 25, 50, 100, 200, 500)):
     """Registered schedule buffers of the reference's DiffusionDecoder / GaussianMultinomialDiffusion at several T
     (shallow_diffusion_tts.py:86-119, gaussian_multinomial_diffusion.py:237-283): pins the oracle's and the product's
@@ -185,13 +210,15 @@ def case_schedules(name, Ts=(4, 25, 50, 100, 200, 500)):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["small", "t25", "t100", "sched", "voc"]
+    which = sys.argv[1:] or ["small", "t25", "t100", "plms", "sched", "voc"]
     if "small" in which:
         case_model("ref_small_T4", T=4, frames=96, phones=12, ref_frames=64, seed=11, utt_idx=100)
     if "t25" in which:
         case_model("ref_f64_T25", T=25, frames=64, phones=8, ref_frames=48, seed=21, utt_idx=101, with_dur_case=False)
     if "t100" in which:  # the bench's step count (T=100 mel + 2 x 100 F0 steps) on a tiny utterance
         case_model("ref_f32_T100", T=100, frames=32, phones=4, ref_frames=32, seed=41, utt_idx=102, with_dur_case=False)
+    if "plms" in which:
+        case_plms("ref_plms_T100_i10")
     if "sched" in which:
         case_schedules("ref_schedules")
     if "voc" in which:
