@@ -53,6 +53,7 @@ struct FFTLayer {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   Conv qkv, out, ffn1, ffn2;
   ConvTC ffn1_tc, ffn2_tc;  // the FFN (92 % of the block's FLOPs) on the tcgen05 path, used for long sequences
+  ConvTC qkv_tc, out_tc;    // self-attention in/out projections on the same path
 };
 struct FFT {
   std::vector<FFTLayer> layers;
@@ -95,6 +96,7 @@ struct Denoiser {
 
 struct AlignLayer {
   Conv q, kv, out, lin1, lin2;
+  ConvTC q_tc, kv_tc, out_tc, lin1_tc, lin2_tc;  // tcgen05 packing of the same projections (long batches)
   float *n1_g, *n1_b, *n2_g, *n2_b;
 };
 

@@ -271,6 +271,14 @@ static int build_fft(TensorMap& tm, DevicePool& pool, const std::string& p, int 
     if (pack_conv(pool, tm.get(q + "ffn.ffn_1.weight"), tm.get(q + "ffn.ffn_1.bias"), 1, PACK_PLAIN, &L.ffn1)) return -1;
     if (pack_linear(pool, tm.get(q + "ffn.ffn_2.weight"), tm.get(q + "ffn.ffn_2.bias"), &L.ffn2)) return -1;
     if (pack_conv_tc(pool, tm.get(q + "ffn.ffn_1.weight"), 1, PACK_PLAIN, L.ffn1.bias, &L.ffn1_tc)) return -1;
+    for (int which = 0; which < 2; ++which) {  // in_proj [3H, H] / out_proj [H, H], bias-free (common_layers.py:200-205)
+      const HostTensor* w = tm.get(q + (which == 0 ? "self_attn.in_proj_weight" : "self_attn.out_proj.weight"));
+      if (!w) return -1;
+      HostTensor ht;
+      ht.data = w->data;
+      ht.shape = {w->shape[0], w->shape[1], 1};
+      if (pack_conv_tc(pool, &ht, 1, PACK_PLAIN, nullptr, which == 0 ? &L.qkv_tc : &L.out_tc)) return -1;
+    }
     {
       const HostTensor* w2 = tm.get(q + "ffn.ffn_2.weight");  // Linear [H, 4H] as a 1-tap conv
       if (!w2) return -1;
@@ -462,6 +470,23 @@ int build_model(TensorMap& tm, const ssb_hparams& hp, Model* m) {
     PK(pack_linear(pool, tm.get(q + "multihead_attn.out_proj.weight"), tm.get(q + "multihead_attn.out_proj.bias"), &a.out));
     PK(pack_linear(pool, tm.get(q + "linear1.weight"), tm.get(q + "linear1.bias"), &a.lin1));
     PK(pack_linear(pool, tm.get(q + "linear2.weight"), tm.get(q + "linear2.bias"), &a.lin2));
+    {  // the same five projections for the tcgen05 kernel (biases: the packed fp32 vectors above)
+      auto lin_tc = [&](const float* data, int64_t n, int64_t k, const float* bias, ConvTC* out) {
+        HostTensor ht;
+        ht.data = data;
+        ht.shape = {n, k, 1};
+        return pack_conv_tc(pool, &ht, 1, PACK_PLAIN, bias, out);
+      };
+      const HostTensor* ow = tm.get(q + "multihead_attn.out_proj.weight");
+      const HostTensor* w1 = tm.get(q + "linear1.weight");
+      const HostTensor* w2 = tm.get(q + "linear2.weight");
+      if (!iw || !ow || !w1 || !w2) goto fail;
+      PK(lin_tc(iw->data, H, H, a.q.bias, &a.q_tc));
+      PK(lin_tc(iw->data + (size_t)H * H, 2 * H, H, a.kv.bias, &a.kv_tc));
+      PK(lin_tc(ow->data, ow->shape[0], ow->shape[1], a.out.bias, &a.out_tc));
+      PK(lin_tc(w1->data, w1->shape[0], w1->shape[1], a.lin1.bias, &a.lin1_tc));
+      PK(lin_tc(w2->data, w2->shape[0], w2->shape[1], a.lin2.bias, &a.lin2_tc));
+    }
     a.n1_g = upload_tensor(pool, tm.get(q + "norm1.weight"));
     a.n1_b = upload_tensor(pool, tm.get(q + "norm1.bias"));
     a.n2_g = upload_tensor(pool, tm.get(q + "norm2.weight"));

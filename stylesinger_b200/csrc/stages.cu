@@ -72,7 +72,7 @@ static __half* alloc_half_rows(Ctx& c, const SeqDev& s, int C);
 int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* keep, bool tc) {
   const int H = 256;
   const size_t mk = c.mark();
-  for (auto& L : f.layers) tc = tc && L.ffn1_tc.ok && L.ffn2_tc.ok;
+  for (auto& L : f.layers) tc = tc && L.ffn1_tc.ok && L.ffn2_tc.ok && L.qkv_tc.ok && L.out_tc.ok;
   float* h = alloc_rows(c, s, H);
   float* qkv = alloc_rows(c, s, 3 * H);
   float* att = alloc_rows(c, s, H);
@@ -86,7 +86,13 @@ int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* kee
   for (size_t i = 0; i < f.layers.size(); ++i) {
     const FFTLayer& L = f.layers[i];
     RUN(layernorm_rows(c, s, x, H, h, H, H, L.ln1_g, L.ln1_b, 1e-5f, nullptr));
-    {
+    if (tc) {
+      RUN(split_planes(c, h, H, s.rows, H, 1.0f, hh, hl));
+      GemmTC g;
+      g.A_hi = hh; g.A_lo = hl; g.rows_total = s.rows; g.w = &L.qkv_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+      g.e.mode = EPI_GENERIC; g.e.out = qkv; g.e.ldo = 3 * H;
+      RUN(conv_gemm_tc(c, g));
+    } else {
       ConvGemm g = make_gemm(L.qkv, s, h, H);
       g.e.out = qkv; g.e.ldo = 3 * H;
       RUN(conv_gemm(c, g));
@@ -99,7 +105,13 @@ int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* kee
       a.out = att; a.ldo = H;
       RUN(attention(c, a));
     }
-    {
+    if (tc) {
+      RUN(split_planes(c, att, H, s.rows, H, 1.0f, hh, hl));
+      GemmTC g;
+      g.A_hi = hh; g.A_lo = hl; g.rows_total = s.rows; g.w = &L.out_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+      g.e.mode = EPI_GENERIC; g.e.res = x; g.e.ld_res = H; g.e.rowmask = keep; g.e.out = x; g.e.ldo = H;
+      RUN(conv_gemm_tc(c, g));
+    } else {
       ConvGemm g = make_gemm(L.out, s, att, H);
       g.e.res = x; g.e.ld_res = H; g.e.rowmask = keep; g.e.out = x; g.e.ldo = H;
       RUN(conv_gemm(c, g));
@@ -236,7 +248,12 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
   float* q = alloc_rows(c, sf, H);
   float* att = alloc_rows(c, sf, H);
   float* tmp = alloc_rows(c, sf, H);
-  float* hid = alloc_rows(c, sf, 2048);
+  // long batches: the aligner's five projections per layer on the tcgen05 kernel (the 256 -> 2048 -> 256 feed-forward is
+  // 90 % of its FLOPs; its hidden activation then only exists as fp16 hi/lo planes); attention itself stays fp32
+  bool tc = m.use_tc && m.fft_tc && tc_available() && sf.ntiles >= 8;
+  for (int i = 0; i < 2; ++i)
+    tc = tc && m.align[i].q_tc.ok && m.align[i].kv_tc.ok && m.align[i].out_tc.ok && m.align[i].lin1_tc.ok && m.align[i].lin2_tc.ok;
+  float* hid = tc ? nullptr : alloc_rows(c, sf, 2048);
   WS_OK(c);
   // LocalStyleAdaptor.forward (lse.py:103-129)
   RUN(col0_nonzero_mask(c, sr, ref_g, 80, rmask));
@@ -303,17 +320,41 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
   RUN(col0_nonzero_mask(c, sr, zl, H, kmask));  // style_key_padding_mask = zl[:,:,0].eq(0) (:204) -> attend where != 0
   // ProsodyAligner (lse.py:59-81), forcing=False
   if (!c.dry) SSB_CUDA(cudaMemcpyAsync(style, dec0, (size_t)sf.rows * H * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  __half *sth = nullptr, *stl = nullptr, *zlh = nullptr, *zll = nullptr, *hdh = nullptr, *hdl = nullptr;
+  if (tc) {
+    sth = alloc_half_rows(c, sf, H); stl = alloc_half_rows(c, sf, H);
+    zlh = alloc_half_rows(c, sr, H); zll = alloc_half_rows(c, sr, H);
+    hdh = alloc_half_rows(c, sf, 2048); hdl = alloc_half_rows(c, sf, 2048);
+    WS_OK(c);
+    RUN(split_planes(c, zl, H, sr.rows, H, 1.0f, zlh, zll));
+  }
+  auto tcg = [&](const SeqDev& sq, const __half* ah, const __half* al, const ConvTC& w) {
+    GemmTC g;
+    g.A_hi = ah; g.A_lo = al; g.rows_total = sq.rows; g.w = &w; g.tiles = sq.tiles; g.ntiles = sq.ntiles;
+    g.e.mode = EPI_GENERIC;
+    return g;
+  };
   for (int i = 0; i < 2; ++i) {
     const AlignLayer& L = m.align[i];
-    {
-      ConvGemm g = make_gemm(L.q, sf, style, H);
-      g.e.out = q; g.e.ldo = H;
-      RUN(conv_gemm(c, g));
-    }
-    {
-      ConvGemm g = make_gemm(L.kv, sr, zl, H);
-      g.e.out = kv; g.e.ldo = 2 * H;
-      RUN(conv_gemm(c, g));
+    if (tc) {
+      RUN(split_planes(c, style, H, sf.rows, H, 1.0f, sth, stl));
+      GemmTC gq = tcg(sf, sth, stl, L.q_tc);
+      gq.e.out = q; gq.e.ldo = H;
+      RUN(conv_gemm_tc(c, gq));
+      GemmTC gk = tcg(sr, zlh, zll, L.kv_tc);
+      gk.e.out = kv; gk.e.ldo = 2 * H;
+      RUN(conv_gemm_tc(c, gk));
+    } else {
+      {
+        ConvGemm g = make_gemm(L.q, sf, style, H);
+        g.e.out = q; g.e.ldo = H;
+        RUN(conv_gemm(c, g));
+      }
+      {
+        ConvGemm g = make_gemm(L.kv, sr, zl, H);
+        g.e.out = kv; g.e.ldo = 2 * H;
+        RUN(conv_gemm(c, g));
+      }
     }
     {
       AttnArgs a;
@@ -322,21 +363,36 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
       a.keymask = kmask; a.scale = 0.08838834764831845f; a.out = att; a.ldo = H;
       RUN(attention(c, a));
     }
-    {
+    if (tc) {
+      RUN(split_planes(c, att, H, sf.rows, H, 1.0f, sth, stl));
+      GemmTC g = tcg(sf, sth, stl, L.out_tc);
+      g.e.res = style; g.e.ld_res = H; g.e.out = tmp; g.e.ldo = H;
+      RUN(conv_gemm_tc(c, g));
+    } else {
       ConvGemm g = make_gemm(L.out, sf, att, H);
       g.e.res = style; g.e.ld_res = H; g.e.out = tmp; g.e.ldo = H;
       RUN(conv_gemm(c, g));
     }
     RUN(layernorm_rows(c, sf, tmp, H, style, H, H, L.n1_g, L.n1_b, 1e-5f, nullptr));
-    {
-      ConvGemm g = make_gemm(L.lin1, sf, style, H);
-      g.e.act = ACT_RELU; g.e.out = hid; g.e.ldo = 2048;
-      RUN(conv_gemm(c, g));
-    }
-    {
-      ConvGemm g = make_gemm(L.lin2, sf, hid, 2048);
-      g.e.res = style; g.e.ld_res = H; g.e.out = tmp; g.e.ldo = H;
-      RUN(conv_gemm(c, g));
+    if (tc) {
+      RUN(split_planes(c, style, H, sf.rows, H, 1.0f, sth, stl));
+      GemmTC g1 = tcg(sf, sth, stl, L.lin1_tc);
+      g1.e.act = ACT_RELU; g1.e.oh = hdh; g1.e.ol = hdl; g1.e.ldh = 2048;
+      RUN(conv_gemm_tc(c, g1));
+      GemmTC g2 = tcg(sf, hdh, hdl, L.lin2_tc);
+      g2.e.res = style; g2.e.ld_res = H; g2.e.out = tmp; g2.e.ldo = H;
+      RUN(conv_gemm_tc(c, g2));
+    } else {
+      {
+        ConvGemm g = make_gemm(L.lin1, sf, style, H);
+        g.e.act = ACT_RELU; g.e.out = hid; g.e.ldo = 2048;
+        RUN(conv_gemm(c, g));
+      }
+      {
+        ConvGemm g = make_gemm(L.lin2, sf, hid, 2048);
+        g.e.res = style; g.e.ld_res = H; g.e.out = tmp; g.e.ldo = H;
+        RUN(conv_gemm(c, g));
+      }
     }
     RUN(layernorm_rows(c, sf, tmp, H, style, H, H, L.n2_g, L.n2_b, 1e-5f, nullptr));
   }

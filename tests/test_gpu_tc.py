@@ -185,24 +185,34 @@ def test_f0_pair_persistent_matches_oracle_and_per_launch():
 
 
 def test_decoder_fft_ffn_tensor_cores_match_ffma():
-    """A 12 s utterance (2250 frames) puts the decoder's FFN GEMMs (conv k=9 -> gelu -> linear, 92 % of the FFT block's
-    FLOPs) on the tcgen05 kernel; the same pass with that switch off keeps them on the fp32 FFMA kernel. Everything
-    upstream is identical (same Philox streams), so decoder_inp must agree exactly and coarse_mel to fp32 rounding."""
+    """A 12 s utterance (2250 frames) puts the decoder's GEMMs (QKV / out projections, FFN conv k=9 -> gelu -> linear) and
+    the style aligner's five projections per layer on the tcgen05 kernel; the same pass with that switch off keeps them on
+    the fp32 FFMA kernel.  Same Philox streams, so style / decoder_inp / coarse_mel must agree to fp32 rounding."""
     from stylesinger_b200 import synth
     from stylesinger_b200.engine import pack_batch
     T = 4
     u = synth.make_utterance(12.0, utt_idx=77)
     m = acoustic_engine(T)
     pb = pack_batch([u]).to(DEV)
-    out = {}
+    out, ran = {}, {}
+    from stylesinger_b200._lib import variant_launches
     try:
         for on in (True, False):
             assert m.set_fft_tensor_cores(on) == on
-            o = m.forward(pb, seed=11, skip_mel_diffusion=True, want=("decoder_inp", "coarse_mel"))
+            before = variant_launches()
+            o = m.forward(pb, seed=11, skip_mel_diffusion=True, want=("decoder_inp", "coarse_mel", "style"))
+            after = variant_launches()
+            ran[on] = {k: v - before.get(k, 0) for k, v in after.items() if "GENERIC" in k and v - before.get(k, 0) > 0}
             out[on] = {k: v.clone() for k, v in o.items()}
     finally:
         m.set_fft_tensor_cores(True)
-    assert torch.equal(out[True]["decoder_inp"], out[False]["decoder_inp"])
+    # 2 aligner layers x 5 projections + 4 decoder layers x (qkv, out, ffn1, ffn2) GENERIC tcgen05 GEMMs more than with the switch off
+    assert sum(ran[True].values()) - sum(ran[False].values()) == 2 * 5 + 4 * 4, ran
+    for k in ("style", "decoder_inp"):
+        e = _maxabs(out[True][k], out[False][k])
+        sc = float(out[False][k].abs().max())
+        print(f"{k}: tcgen05 vs FFMA max |diff| {e:.3e} (max |value| {sc:.2f})")
+        assert e < 1e-4 * max(1.0, sc), k
     err = _maxabs(out[True]["coarse_mel"], out[False]["coarse_mel"])
     scale = float(out[False]["coarse_mel"].abs().max())
     print(f"decoder FFN tcgen05 vs FFMA: coarse_mel max |diff| {err:.3e} (max |value| {scale:.2f})")
