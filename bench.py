@@ -14,6 +14,7 @@ the inputs resident in HBM; `e2e` = the same pass through StyleSingerInfer.infer
 inputs (H2D inside the timed region) and the waveform copied back to the host (D2H inside).
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -110,7 +111,8 @@ class CpuArm:
             import ref_harness
             if ref_harness.available():
                 cwd = os.getcwd()
-                self.runner = ref_harness.ReferenceRunner(T=T, device="cpu", threads=threads)
+                with contextlib.redirect_stdout(sys.stderr):  # the reference prints while loading: keep stdout to the JSON line
+                    self.runner = ref_harness.ReferenceRunner(T=T, device="cpu", threads=threads)
                 os.chdir(cwd)
         except Exception as e:  # staged copy broken: say so and fall back to the port
             print(f"[bench] reference harness unavailable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
@@ -123,7 +125,8 @@ class CpuArm:
 
     def one_pass(self, seconds, utt_idx=0):
         if self.runner is not None:
-            return self.runner.timed_pass(seconds, utt_idx=utt_idx)
+            with contextlib.redirect_stdout(sys.stderr):
+                return self.runner.timed_pass(seconds, utt_idx=utt_idx)
         return self._port_pass(seconds, utt_idx)
 
     def _port_pass(self, seconds, utt_idx):
@@ -349,10 +352,11 @@ def run_b200(args, rank, world, local_rank):
             if arm.kind == "reference" and not args.no_torch_gpu_baseline:
                 try:
                     import ref_harness
-                    g = ref_harness.ReferenceRunner(T=T, device="cuda")
-                    g.timed_pass(1.0)
-                    passes = [g.timed_pass(10.0) for _ in range(3)]
-                    g.close()
+                    with contextlib.redirect_stdout(sys.stderr):
+                        g = ref_harness.ReferenceRunner(T=T, device="cuda")
+                        g.timed_pass(1.0)
+                        passes = [g.timed_pass(10.0) for _ in range(3)]
+                        g.close()
                     fg = passes[0][0]
                     tg = float(np.median([p_[1] for p_ in passes]))
                     gpu_ref = {"value": fg / tg, "unit": UNIT, "ms": 1000.0 * tg, "kind": "reference",

@@ -1,4 +1,5 @@
 // extern "C" boundary (include/stylesinger_b200.h) + the whole-model driver.
+#include <stdlib.h>
 #include <string.h>
 
 #include "stages.cuh"
@@ -169,7 +170,9 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
       // Two streams only for small batches (latency-bound chains).  From ~8k frames on every GEMM fills the GPU on its
       // own, and the CTA-pair (cluster) kernels used there must not run concurrently with each other from two streams:
       // that combination hung on B200 (gpurun diag, round 1; root cause open - see DESIGN.md "known issues").
-      const bool fork = !c.dry && m.aux_stream != nullptr && sf.ntiles <= 64;
+      // SSB_F0_FORK_ALWAYS=1 (diagnosis only): fork at any size, i.e. the round-1 configuration that hung with CTA-pair kernels
+      static const bool fork_always = getenv("SSB_F0_FORK_ALWAYS") != nullptr;
+      const bool fork = !c.dry && m.aux_stream != nullptr && (sf.ntiles <= 64 || fork_always);
       if (fork) {
         SSB_CUDA(cudaEventRecord(m.ev_fork, c.stream));
         SSB_CUDA(cudaStreamWaitEvent(m.aux_stream, m.ev_fork, 0));

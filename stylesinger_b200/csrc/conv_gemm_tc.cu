@@ -660,6 +660,197 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tap-reuse variant of the CTA-pair kernel for 3-tap (dilated) convs without a second K segment: the DiffNet / DDiffNet
+// gate GEMM once the conditioner is hoisted.  The round-2 ncu captures show that GEMM moving ~1.4 GB of operands from L2
+// to shared memory per launch at ~8-10 TB/s - the chip-wide L2 -> SM throughput cap (B300_MICROARCH.md "LTS throughput
+// cap") - i.e. it is bound by operand traffic, not by the tensor pipe.  Half of that traffic is the SAME activation
+// rows loaded three times, once per tap, shifted by the dilation.  Here each K block's activation tile is loaded ONCE with
+// a halo (rows [row0 - 8, row0 + 136), one TMA box of 144 rows) and the three taps address it through UMMA descriptors
+// whose start address is advanced by whole 128-byte rows: in the K-major SWIZZLE_128B layout row m of the operand sits at
+// start + 128*m and the 16-byte-chunk XOR is a function of the absolute shared-memory address bits [7:9], so a descriptor
+// that starts s rows later reads exactly the rows TMA wrote for box rows s .. s+127.  Activation bytes per tile drop from
+// 3 x 32 KB to 36 KB per K block (-31 % of all operand traffic of the GEMM).
+// Rings: A (2 slots of 36 KB, one per K block, freed after its third tap), B (3-4 slots, one per (K block, tap)).
+constexpr int HALO = 8;                     // largest dilation served (DiffNet: 1, 2, 4, 8)
+constexpr int A3_ROWS = BM + 2 * HALO;      // 144
+constexpr int A3_TILE = A3_ROWS * BK * 2;   // 18 KB per plane (a multiple of 1024: swizzle pattern alignment)
+
+template <int HB>
+struct Cfg3 {
+  static constexpr int BN = 2 * HB;
+  static constexpr int B_TILE = HB * BK * 2;
+  static constexpr int ASLOT = 2 * A3_TILE, BSLOT = 2 * B_TILE;
+  static constexpr int ASLOTS = 2, BSLOTS = HB >= 128 ? 3 : 4;
+  static constexpr int RING = ASLOTS * ASLOT + BSLOTS * BSLOT;
+  static constexpr int SMEM = RING + XPOSE_BYTES + 1024 + 256;
+  static constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+};
+
+template <int HB, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TCParams p) {
+  using K = Cfg3<HB>;
+  constexpr int BN = K::BN, AS = K::ASLOTS, BS = K::BSLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float4* xpose = reinterpret_cast<float4*>(smem + K::RING);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::RING + XPOSE_BYTES);
+  // bars: afull[AS], aempty[AS], bfull[BS], bempty[BS], tfull[2], tempty[2]; then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AS + 2 * BS + 4);
+  const uint32_t abase = smem_u32(smem), bbase = abase + AS * K::ASLOT;
+  const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * AS, bfull0 = aempty0 + 8 * AS, bempty0 = bfull0 + 8 * BS;
+  const uint32_t tfull0 = bempty0 + 8 * BS, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * AS + 2 * BS; ++s) mbar_init(afull0 + 8 * s, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int npairs = (p.ntiles + 1) >> 1;
+  const int total = npairs * p.NT;
+  const int nkc = p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t lafull0 = mapa_u32(afull0, 0), lbfull0 = mapa_u32(bfull0, 0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = cid; tile < total; tile += ncl) {
+        const int mp = tile / p.NT, nt = tile - mp * p.NT;
+        int mt = 2 * mp + (int)rank;
+        if (mt >= p.ntiles) mt = 2 * mp;
+        const int row0 = p.tiles[mt].x;
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(aempty0 + 8 * as, aph ^ 1);
+          if (rank == 0) mbar_expect_tx(afull0 + 8 * as, 2 * K::ASLOT);
+          const uint32_t sa = abase + as * K::ASLOT;
+          tma_load_2d_pair(sa, &tmA_hi, lafull0 + 8 * as, kc * BK, row0 - HALO);
+          tma_load_2d_pair(sa + A3_TILE, &tmA_lo, lafull0 + 8 * as, kc * BK, row0 - HALO);
+          if (++as == AS) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 3; ++tap) {
+            mbar_wait(bempty0 + 8 * bs, bph ^ 1);
+            if (rank == 0) mbar_expect_tx(bfull0 + 8 * bs, 2 * K::BSLOT);
+            const uint32_t sb = bbase + bs * K::BSLOT;
+            const int brow = tap * p.N + nt * BN + (int)rank * HB;
+            tma_load_2d_pair(sb, &tmB_hi, lbfull0 + 8 * bs, kc * BK, brow);
+            tma_load_2d_pair(sb + K::B_TILE, &tmB_lo, lbfull0 + 8 * bs, kc * BK, brow);
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int as = 0, bs = 0, it = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = cid; tile < total; tile += ncl, ++it) {
+        const int a = it & 1;
+        mbar_wait(tempty0 + 8 * a, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * K::ACC_STRIDE;
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(afull0 + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t sa = abase + as * K::ASLOT;
+          for (int tap = 0; tap < 3; ++tap) {
+            mbar_wait(bfull0 + 8 * bs, bph);
+            tc_fence_after();
+            const uint32_t sh = (uint32_t)(HALO + (tap - 1) * p.dil) * 128u;  // whole rows: the swizzle phase follows the address
+            const uint32_t sb = bbase + bs * K::BSLOT;
+            const uint64_t dah = make_sdesc(sa + sh), dal = make_sdesc(sa + A3_TILE + sh);
+            const uint64_t dbh = make_sdesc(sb), dbl = make_sdesc(sb + K::B_TILE);
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t off = (uint64_t)((ks * 32) >> 4);
+              tc_mma_pair(d_tmem, dah + off, dbh + off, idesc, (kc | tap | ks) != 0 ? 1u : 0u);
+              tc_mma_pair(d_tmem, dah + off, dbl + off, idesc, 1u);
+              tc_mma_pair(d_tmem, dal + off, dbh + off, idesc, 1u);
+            }
+            tc_commit_pair(bempty0 + 8 * bs);
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          tc_commit_pair(aempty0 + 8 * as);  // the halo tile is free once its third tap has been consumed
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+        tc_commit_pair(tfull0 + 8 * a);
+      }
+    }
+  } else if (warp == 3) {
+    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
+    auto pf = [&](int tile) {
+      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      const int mt = 2 * mp + (int)rank;
+      if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+    };
+    if (cid < total) pf(cid);
+    int it = 0;
+    for (int tile = cid; tile < total; tile += ncl, ++it) {
+      const int a = it & 1;
+      if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
+      __syncwarp();
+      if (tile + ncl < total) pf(tile + ncl);
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    const int eg = (warp - 4) >> 2;
+    constexpr int NCH = BN / 32;
+    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
+    int it = 0;
+    for (int tile = cid; tile < total; tile += ncl, ++it) {
+      const int a = it & 1;
+      const uint32_t tph = (it >> 1) & 1;
+      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      const int mt = 2 * mp + (int)rank;
+      const bool have = mt < p.ntiles;
+      const int2 t = have ? p.tiles[mt] : make_int2(0, 0);
+      const int64_t r0 = (int64_t)t.x + ew * 32;
+      const int nrows = min(32, max(0, t.y - ew * 32));
+      float4* xb = xpose + (warp - 4) * 256;
+      Pre cur, nxt;
+      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + eg * 32, lane, cur);
+      mbar_wait(tfull0 + 8 * a, tph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = eg; ch < NCH; ch += 2) {
+        if (ch + 2 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * K::ACC_STRIDE + (uint32_t)(ch * 32), v);
+        if (nrows > 0) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
+        cur = nxt;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS) : "memory");
+  }
+}
+
 __global__ void k_split_planes(const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
@@ -900,6 +1091,48 @@ int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
   counter->fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
+template <int HB, int MODE>
+int launch_pair_reuse_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
+  using KCfg = Cfg3<HB>;
+  const ConvTC& w = *p.w;
+  static std::atomic<bool> configured[MAX_DEV];
+  if (configure_once(conv_gemm_tc2r_kernel<HB, MODE>, configured, KCfg::SMEM)) return -2;
+  static std::atomic<long long>* const counter = [] {
+    static char name[48];
+    snprintf(name, sizeof(name), "tc2r<%d,%s>", HB, mode_name(MODE));
+    return variant_counter(name);
+  }();
+  CUtensorMap ta_hi, ta_lo;  // activation boxes of BM + 2 * HALO rows
+  if (cached_act_map(&ta_hi, p.A_hi, (uint64_t)p.rows_total, (uint64_t)w.Cin, A3_ROWS)) return -1;
+  if (cached_act_map(&ta_lo, p.A_lo, (uint64_t)p.rows_total, (uint64_t)w.Cin, A3_ROWS)) return -1;
+  tp.NT = w.N / (2 * HB);
+  const int total = ((tp.ntiles + 1) / 2) * tp.NT;
+  const int ncl = total < num_sms / 2 ? total : num_sms / 2;
+  {
+    const bool guard = pair_guard_enabled();
+    const int dev = guard ? current_device() : 0;
+    std::unique_lock<std::mutex> lk(g_pair_mu, std::defer_lock);
+    if (guard) {
+      lk.lock();
+      pair_guard_begin(dev, ctx.stream);
+    }
+    conv_gemm_tc2r_kernel<HB, MODE><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, tp);
+    const cudaError_t le = cudaGetLastError();
+    if (guard) pair_guard_end(dev, ctx.stream);
+    SSB_CUDA(le);
+  }
+  ++g_launches;
+  counter->fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+// the tap-reuse kernel serves 3-tap convs with wide N: the gate GEMMs of the two denoisers (hb 128 / 96), the vocoder's
+// transposed convs (3-tap, N = u * C) and its k = 3 ResBlock convs; everything else keeps the general kernel
+bool tap_reuse_eligible(const GemmTC& p, const ConvTC& w) {
+  static const bool off = getenv("SSB_TC_NO_TAP_REUSE") != nullptr;
+  return !off && !p.w2 && w.taps == 3 && w.center == 1 && w.dil >= 1 && w.dil <= HALO &&
+         (p.e.mode == EPI_GATE || p.e.mode == EPI_GENERIC) && (w.hb == 128 || w.hb == 96);
+}
+
 template <int HB>
 int launch_pair(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   switch (tp.e.mode) {
@@ -991,6 +1224,11 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   const bool pair_off = getenv("SSB_TC_NO_PAIR") != nullptr;
   if (!pair_off && w.hb > 0 && (!p.w2 || p.w2->hb == w.hb) &&
       (int64_t)((p.ntiles + 1) / 2) * (w.N / (2 * w.hb)) >= (int64_t)num_sms) {
+    if (tap_reuse_eligible(p, w)) {
+      if (p.e.mode == EPI_GATE)
+        return w.hb == 128 ? launch_pair_reuse_m<128, EPI_GATE>(ctx, p, tp, num_sms) : launch_pair_reuse_m<96, EPI_GATE>(ctx, p, tp, num_sms);
+      return w.hb == 128 ? launch_pair_reuse_m<128, EPI_GENERIC>(ctx, p, tp, num_sms) : launch_pair_reuse_m<96, EPI_GENERIC>(ctx, p, tp, num_sms);
+    }
     switch (w.hb) {
       case 128: return launch_pair<128>(ctx, p, tp, num_sms);
       case 96: return launch_pair<96>(ctx, p, tp, num_sms);
