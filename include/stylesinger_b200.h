@@ -257,6 +257,13 @@ int64_t ssb_variant_launch_count(const char* variant);
 int32_t ssb_variant_names(char* buf, int32_t cap);
 void ssb_tensor_map_cache_stats(int64_t* encodes, int64_t* hits);
 
+/* Process-wide switch (default 1) of the interleaved residual-layer schedule of the large-batch samplers: the gate conv of
+ * one group of utterances (or of one F0 net) and the 1x1 residual/skip conv of the other group share one launch and
+ * alternate tile by tile inside every SM (kernel variant "tc2d<HB,GATE+RES_SKIP>"; reference loop net.py:66-78 inside
+ * shallow_diffusion_tts.py:303-304 / gaussian_multinomial_diffusion.py:928-939).  0 restores one launch per GEMM.
+ * Results are identical either way (same kernels' arithmetic); tests use it for A/B checks.  Returns the new state. */
+int32_t ssb_set_interleaved_layers(int32_t enable);
+
 /* Unit-test granularity: one Conv1d over ragged rows with torch-layout HOST weights [N,Cin,k]
  * (packs on the fly with cudaMalloc; not for production use).  act: 0 none 1 relu 2 gelu 3 leaky(0.1) 4 tanh. */
 int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,

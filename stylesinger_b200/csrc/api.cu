@@ -166,6 +166,11 @@ int run_acoustic(Ctx& c, const Model& m, const ssb_acoustic_inputs& in, const ss
         float* zz[2] = {za, zs};
         int32_t* uu[2] = {uva, uvs};
         RUN(run_f0_diffusion_pair_persistent(c, m, sf, cond, cond2, lo, hi, in.f0_gauss_noise, in.f0_unif_noise, in.seed, zz, uu));
+      } else if (f0_dual_ok(m, sf)) {
+        // large batches: both nets in lock step, their gate / residual GEMMs interleaved on the dual kernel
+        float* zz[2] = {za, zs};
+        int32_t* uu[2] = {uva, uvs};
+        RUN(run_f0_diffusion_dual(c, m, sf, cond, cond2, lo, hi, in.f0_gauss_noise, in.f0_unif_noise, in.seed, zz, uu));
       } else {
       // Two streams only for small batches (latency-bound chains).  From ~8k frames on every GEMM fills the GPU on its
       // own, and the CTA-pair (cluster) kernels used there must not run concurrently with each other from two streams:
@@ -677,6 +682,7 @@ int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, in
   return mel_postprocess_flat((cudaStream_t)stream, mel, n_frames, vmin, vmax, nonzero_frames);
 }
 int64_t ssb_launch_count(void) { return (int64_t)ssb::g_launches.load(); }
+int32_t ssb_set_interleaved_layers(int32_t enable) { return ssb::set_dual_enabled(enable); }
 int64_t ssb_variant_launch_count(const char* variant) { return variant ? (int64_t)ssb::variant_launch_count(variant) : 0; }
 int32_t ssb_variant_names(char* buf, int32_t cap) { return buf && cap > 0 ? ssb::variant_names(buf, cap) : 0; }
 void ssb_tensor_map_cache_stats(int64_t* encodes, int64_t* hits) {

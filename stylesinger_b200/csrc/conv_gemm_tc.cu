@@ -851,6 +851,229 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Interleaved two-problem CTA-pair kernel ("dual"): ONE launch works through the tiles of two independent GEMMs,
+//   problem 0 = a gate conv  (3 taps x C -> 2C, EPI_GATE:     tensor-pipe bound, ~15 us of MMAs per 256 x 256 tile),
+//   problem 1 = a 1x1 conv   (C -> 2C,         EPI_RES_SKIP:  bound by its epilogue's HBM streams, ~5 us of MMAs),
+// and every cluster ALTERNATES between them.  With the double-buffered TMEM accumulators the MMA warp runs one tile
+// ahead of the epilogue warps, so the long MMA phase of a gate tile hides the long epilogue of the 1x1 tile before it
+// and vice versa: the two kernels that ran back to back at 78 % / 22 % tensor-pipe activity (profiles/r01_ncu_full_pair_v2)
+// overlap inside every SM instead.  The two problems must be independent: the sampler drivers (stages.cu) pair the gate
+// conv of one half of the utterances (or of one F0 net) with the residual conv of the other half (other net).
+// Tile s of the interleaved sequence belongs to cluster s % ncl in its iteration s / ncl; while both problems have tiles
+// left, (s, s ^ 1) are the same tile index of the two problems and the problem alternates per cluster and iteration.
+struct TCProb {
+  const int2* tiles;
+  int ntiles, NT, taps, kchunks, dil, center, N;
+  EpiTC e;
+};
+struct TCDual {
+  TCProb q[2];
+  int n0, n1;  // tiles (row-tile pairs x NT) of problem 0 / 1
+};
+__device__ __forceinline__ bool dual_decode(int i, int cid, int ncl, int n0, int n1, int& p, int& t) {
+  const int s = i * ncl + cid;
+  if (s >= n0 + n1) return false;
+  const int m = n0 < n1 ? n0 : n1;
+  if (s < 2 * m) {
+    p = (ncl & 1) ? (s & 1) : ((i + cid) & 1);
+    t = s >> 1;
+  } else {
+    p = n0 > n1 ? 0 : 1;
+    t = m + (s - 2 * m);
+  }
+  return true;
+}
+#define DQ(field) (p ? P.q[1].field : P.q[0].field)
+
+template <int HB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
+                      const __grid_constant__ CUtensorMap tmB0_hi, const __grid_constant__ CUtensorMap tmB0_lo,
+                      const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
+                      const __grid_constant__ CUtensorMap tmB1_hi, const __grid_constant__ CUtensorMap tmB1_lo,
+                      const __grid_constant__ TCDual P) {
+  using K = Cfg2<HB>;
+  constexpr int STAGES = K::STAGES;
+  constexpr int BN = K::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float4* xpose = reinterpret_cast<float4*>(smem + STAGES * K::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * K::STAGE + XPOSE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int n0 = P.n0, n1 = P.n1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t lfull0 = mapa_u32(full0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int p, t;
+      for (int i = 0; dual_decode(i, cid, ncl, n0, n1, p, t); ++i) {
+        const int NT = DQ(NT), ntl = DQ(ntiles), kch = DQ(kchunks), taps = DQ(taps), dil = DQ(dil), center = DQ(center), N = DQ(N);
+        const int2* tiles = DQ(tiles);
+        const CUtensorMap* mAh = p ? &tmA1_hi : &tmA0_hi;
+        const CUtensorMap* mAl = p ? &tmA1_lo : &tmA0_lo;
+        const CUtensorMap* mBh = p ? &tmB1_hi : &tmB0_hi;
+        const CUtensorMap* mBl = p ? &tmB1_lo : &tmB0_lo;
+        const int mp = t / NT, nt = t - mp * NT;
+        int mt = 2 * mp + (int)rank;
+        if (mt >= ntl) mt = 2 * mp;
+        const int row0 = tiles[mt].x;
+        const int nk = taps * kch;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * K::STAGE);
+          const uint32_t fb = lfull0 + 8 * stage;
+          const uint32_t sa = sbase + stage * K::STAGE;
+          const int tap = kb / kch;
+          const int c0 = (kb - tap * kch) * BK;
+          const int arow = row0 + (tap - center) * dil;
+          const int brow = tap * N + nt * BN + (int)rank * HB;
+          tma_load_2d_pair(sa, mAh, fb, c0, arow);
+          tma_load_2d_pair(sa + A_TILE, mAl, fb, c0, arow);
+          tma_load_2d_pair(sa + 2 * A_TILE, mBh, fb, c0, brow);
+          tma_load_2d_pair(sa + 2 * A_TILE + K::B_TILE, mBl, fb, c0, brow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int p, t;
+      for (int it = 0; dual_decode(it, cid, ncl, n0, n1, p, t); ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        const int nk = DQ(taps) * DQ(kchunks);
+        mbar_wait(tempty0 + 8 * a, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * K::ACC_STRIDE;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * K::STAGE;
+          const uint64_t dah = make_sdesc(sa), dal = make_sdesc(sa + A_TILE);
+          const uint64_t dbh = make_sdesc(sa + 2 * A_TILE), dbl = make_sdesc(sa + 2 * A_TILE + K::B_TILE);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t off = (uint64_t)((ks * 32) >> 4);
+            tc_mma_pair(d_tmem, dah + off, dbh + off, idesc, (kb | ks) != 0 ? 1u : 0u);
+            tc_mma_pair(d_tmem, dah + off, dbl + off, idesc, 1u);
+            tc_mma_pair(d_tmem, dal + off, dbh + off, idesc, 1u);
+          }
+          tc_commit_pair(empty0 + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(tfull0 + 8 * a);
+      }
+    }
+  } else if (warp == 3) {
+    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
+    auto pf = [&](int i) {
+      int p, t;
+      if (!dual_decode(i, cid, ncl, n0, n1, p, t)) return;
+      const int NT = DQ(NT);
+      const int mp = t / NT, nt = t - mp * NT;
+      const int mt = 2 * mp + (int)rank;
+      if (mt >= DQ(ntiles)) return;
+      if (p == 0) prefetch_tile_l2<EPI_GATE>(P.q[0].e, P.q[0].tiles[mt], nt * BN, BN, lane);
+      else prefetch_tile_l2<EPI_RES_SKIP>(P.q[1].e, P.q[1].tiles[mt], nt * BN, BN, lane);
+    };
+    pf(0);
+    int p, t;
+    for (int it = 0; dual_decode(it, cid, ncl, n0, n1, p, t); ++it) {
+      const int a = it & 1;
+      if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
+      __syncwarp();
+      pf(it + 1);
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    const int eg = (warp - 4) >> 2;
+    constexpr int NCH = BN / 32;
+    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
+    float4* xb = xpose + (warp - 4) * 256;
+    int p, t;
+    for (int it = 0; dual_decode(it, cid, ncl, n0, n1, p, t); ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int NT = DQ(NT);
+      const int mp = t / NT, nt = t - mp * NT;
+      const int mt = 2 * mp + (int)rank;
+      const bool have = mt < DQ(ntiles);
+      const int2 tl = have ? DQ(tiles)[mt] : make_int2(0, 0);
+      const int64_t r0 = (int64_t)tl.x + ew * 32;
+      const int nrows = min(32, max(0, tl.y - ew * 32));
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * K::ACC_STRIDE;
+      Pre cur, nxt;
+      if (p == 0) {
+        prefetch_chunk<EPI_GATE>(P.q[0].e, r0, nrows, nt * BN + eg * 32, lane, cur);
+        mbar_wait(tfull0 + 8 * a, aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = eg; ch < NCH; ch += 2) {
+          if (ch + 2 < NCH) prefetch_chunk<EPI_GATE>(P.q[0].e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)(ch * 32), v);
+          if (nrows > 0) epilogue_chunk<EPI_GATE>(P.q[0].e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
+          cur = nxt;
+        }
+      } else {
+        prefetch_chunk<EPI_RES_SKIP>(P.q[1].e, r0, nrows, nt * BN + eg * 32, lane, cur);
+        mbar_wait(tfull0 + 8 * a, aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = eg; ch < NCH; ch += 2) {
+          if (ch + 2 < NCH) prefetch_chunk<EPI_RES_SKIP>(P.q[1].e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)(ch * 32), v);
+          if (nrows > 0) epilogue_chunk<EPI_RES_SKIP>(P.q[1].e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
+          cur = nxt;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS) : "memory");
+  }
+}
+#undef DQ
+
 __global__ void k_split_planes(const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
@@ -1252,6 +1475,89 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   }
   tp.NT = w.N / 128;
   return launch<128>(ctx, p, tp, num_sms);
+}
+
+namespace {
+template <int HB>
+int launch_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r, int num_sms) {
+  using KCfg = Cfg2<HB>;
+  static std::atomic<bool> configured[MAX_DEV];
+  if (configure_once(conv_gemm_tc2d_kernel<HB>, configured, KCfg::SMEM)) return -2;
+  static std::atomic<long long>* const counter = [] {
+    static char name[48];
+    snprintf(name, sizeof(name), "tc2d<%d,GATE+RES_SKIP>", HB);
+    return variant_counter(name);
+  }();
+  const GemmTC* gs[2] = {&g, &r};
+  CUtensorMap ta[2][2];
+  TCDual P;
+  for (int i = 0; i < 2; ++i) {
+    const GemmTC& q = *gs[i];
+    const ConvTC& w = *q.w;
+    if (cached_act_map(&ta[i][0], q.A_hi, (uint64_t)q.rows_total, (uint64_t)w.Cin, BM)) return -1;
+    if (cached_act_map(&ta[i][1], q.A_lo, (uint64_t)q.rows_total, (uint64_t)w.Cin, BM)) return -1;
+    TCProb& t = P.q[i];
+    t.tiles = q.tiles; t.ntiles = q.ntiles; t.NT = w.N / (2 * HB); t.taps = w.taps; t.kchunks = w.Cin / BK;
+    t.dil = w.dil; t.center = w.center; t.N = w.N; t.e = q.e;
+    if (!t.e.bias) t.e.bias = w.bias;
+  }
+  P.n0 = ((g.ntiles + 1) / 2) * P.q[0].NT;
+  P.n1 = ((r.ntiles + 1) / 2) * P.q[1].NT;
+  const int total = P.n0 + P.n1;
+  const int ncl = total < num_sms / 2 ? total : num_sms / 2;
+  {
+    const bool guard = pair_guard_enabled();
+    const int dev = guard ? current_device() : 0;
+    std::unique_lock<std::mutex> lk(g_pair_mu, std::defer_lock);
+    if (guard) {
+      lk.lock();
+      pair_guard_begin(dev, ctx.stream);
+    }
+    conv_gemm_tc2d_kernel<HB><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
+                                                                         r.w->tm2_hi, r.w->tm2_lo, P);
+    const cudaError_t le = cudaGetLastError();
+    if (guard) pair_guard_end(dev, ctx.stream);
+    SSB_CUDA(le);
+  }
+  ++g_launches;
+  counter->fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+}  // namespace
+
+static std::atomic<int> g_dual_on{-1};  // -1: not decided yet (environment), 0 / 1: off / on
+bool dual_enabled() {
+  int v = g_dual_on.load(std::memory_order_relaxed);
+  if (v < 0) {
+    v = getenv("SSB_TC_NO_DUAL") ? 0 : 1;
+    g_dual_on.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+int set_dual_enabled(int on) {
+  g_dual_on.store(on ? 1 : 0, std::memory_order_relaxed);
+  return on ? 1 : 0;
+}
+
+// gate conv (EPI_GATE, no second K segment) of one independent sub-problem + 1x1 residual conv (EPI_RES_SKIP) of another,
+// interleaved tile by tile in one launch (conv_gemm_tc2d_kernel).  Falls back to two launches when the shapes do not qualify.
+int conv_gemm_tc_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r) {
+  if (ctx.dry) return 0;
+  if (g.ntiles == 0) return conv_gemm_tc(ctx, r);
+  if (r.ntiles == 0) return conv_gemm_tc(ctx, g);
+  const ConvTC& wg = *g.w;
+  const ConvTC& wr = *r.w;
+  const int num_sms = device_sms();
+  const bool pair_off = getenv("SSB_TC_NO_PAIR") != nullptr;
+  const bool ok = dual_enabled() && !pair_off && wg.ok && wr.ok && !g.w2 && !r.w2 && g.e.mode == EPI_GATE && r.e.mode == EPI_RES_SKIP &&
+                  wg.hb == wr.hb && (wg.hb == 128 || wg.hb == 96) && wg.taps == 3 && wr.taps == 1 &&
+                  (r.e.res || (r.e.rh && r.e.rl)) &&
+                  (int64_t)((g.ntiles + 1) / 2) * (wg.N / (2 * wg.hb)) + (int64_t)((r.ntiles + 1) / 2) * (wr.N / (2 * wr.hb)) >= (int64_t)num_sms;
+  if (!ok) {
+    if (int rc = conv_gemm_tc(ctx, g)) return rc;
+    return conv_gemm_tc(ctx, r);
+  }
+  return wg.hb == 128 ? launch_dual<128>(ctx, g, r, num_sms) : launch_dual<96>(ctx, g, r, num_sms);
 }
 
 int split_planes(Ctx& ctx, const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {

@@ -111,7 +111,14 @@ def _batch_inputs(seed):
     return offs, n, cond, coarse
 
 
+def _interleaved(on):
+    from stylesinger_b200._lib import lib
+    return lib.ssb_set_interleaved_layers(1 if on else 0)
+
+
 def test_mel_sampler_T100_pair_kernels_vs_simt_philox_20k_frames():
+    """Three runs of the same T=100 Philox sampler: interleaved dual kernel (default: the gate conv of one utterance group and
+    the 1x1 residual conv of the other share a launch), one launch per GEMM, and the fp32 FFMA path."""
     T = 100
     m = acoustic_engine(T, 4)
     offs, n, cond, coarse = _batch_inputs(31)
@@ -119,19 +126,27 @@ def test_mel_sampler_T100_pair_kernels_vs_simt_philox_20k_frames():
     out, ran = {}, {}
     try:
         m.set_persistent(False)
-        for tc in (True, False):
-            m.set_tensor_cores(tc)
+        for mode in ("dual", "tc", "simt"):
+            m.set_tensor_cores(mode != "simt")
+            _interleaved(mode == "dual")
             before = _variants()
-            out[tc] = m.mel_diffusion(cond, coarse, offs, None, seed=17).clone()
-            ran[tc] = _delta(before, _variants())
+            out[mode] = m.mel_diffusion(cond, coarse, offs, None, seed=17).clone()
+            ran[mode] = _delta(before, _variants())
     finally:
         m.set_tensor_cores(True)
         m.set_persistent(True)
-    err = _maxabs(out[True], out[False])
-    print(f"mel sampler T=100, {n} frames, philox: pair-tc vs simt L-inf {err:.3e}; tc kernels {ran[True]}")
-    assert ran[True].get("tc2r<128,GATE>", 0) == T * 20 and ran[True].get("tc2<128,RES_SKIP>", 0) == T * 20
-    assert not ran[False], ran[False]  # the fp32 FFMA path launches no tcgen05 kernel
-    assert torch.isfinite(out[True]).all() and err < 1e-3
+        _interleaved(True)
+    err = _maxabs(out["tc"], out["simt"])
+    err_d = _maxabs(out["dual"], out["tc"])
+    print(f"mel sampler T=100, {n} frames, philox: pair-tc vs simt L-inf {err:.3e}, interleaved vs per-GEMM {err_d:.3e}; "
+          f"kernels {ran['dual']} | {ran['tc']}")
+    assert ran["tc"].get("tc2r<128,GATE>", 0) == T * 20 and ran["tc"].get("tc2<128,RES_SKIP>", 0) == T * 20
+    # two lanes, software-pipelined by half a layer: first gate and last 1x1 alone, 2L - 1 interleaved launches in between
+    assert ran["dual"].get("tc2d<128,GATE+RES_SKIP>", 0) == T * 39, ran["dual"]
+    assert ran["dual"].get("tc2r<128,GATE>", 0) + ran["dual"].get("tc2<128,GATE>", 0) == T
+    assert ran["dual"].get("tc2<128,RES_SKIP>", 0) == T
+    assert not ran["simt"], ran["simt"]  # the fp32 FFMA path launches no tcgen05 kernel
+    assert torch.isfinite(out["dual"]).all() and err < 1e-3 and err_d < 1e-4
 
 
 def test_mel_sampler_T100_pair_kernels_vs_oracle_two_utterances_of_the_batch():
@@ -148,7 +163,7 @@ def test_mel_sampler_T100_pair_kernels_vs_oracle_two_utterances_of_the_batch():
         ran = _delta(before, _variants())
     finally:
         m.set_persistent(True)
-    assert ran.get("tc2r<128,GATE>", 0) == T * 20, ran
+    assert ran.get("tc2d<128,GATE+RES_SKIP>", 0) == T * 39, ran  # the interleaved gate / 1x1 kernel (default path)
     worst = 0.0
     for b in (3, 9):  # 800 and 1111 frames
         a, e = int(offs[b]), int(offs[b + 1])
@@ -193,6 +208,36 @@ def test_f0_sampler_T100_pair_kernels_vs_oracle_two_utterances_of_the_batch():
         total += Fr
     print(f"f0 sampler T=100 inside a {n}-frame batch (pair kernels {ran}) vs oracle: {agree}/{total} frames agree")
     assert agree >= 0.99 * total
+
+
+def test_forward_f0_nets_interleaved_vs_per_gemm_batch():
+    """Full forward on a 20 k-frame batch (mel diffusion skipped): the two F0/UV samplers run in lock step with their residual
+    layers interleaved on the dual kernel (tc2d<96,...>); same Philox streams as the per-GEMM schedule, so pitch must agree
+    except where a Gumbel-argmax UV decision sits within rounding distance of a tie."""
+    from stylesinger_b200 import synth
+    from stylesinger_b200.engine import pack_batch
+    T = 25
+    m = acoustic_engine(4, T)
+    utts = [synth.make_utterance(L / 187.5, utt_idx=40 + i, frames=L) for i, L in enumerate(BATCH_LENS)]
+    pb = pack_batch(utts).to(DEV)
+    out, ran = {}, {}
+    try:
+        for on in (True, False):
+            _interleaved(on)
+            before = _variants()
+            r = m.forward(pb, seed=5, skip_mel_diffusion=True, want=("pitch_pred", "f0_denorm"))
+            out[on] = {k: v.clone() for k, v in r.items()}
+            ran[on] = _delta(before, _variants())
+    finally:
+        _interleaved(True)
+    assert ran[True].get("tc2d<96,GATE+RES_SKIP>", 0) == T * 19, ran[True]  # L = 10: 2L - 1 interleaved launches per step
+    assert "tc2d<96,GATE+RES_SKIP>" not in ran[False]
+    pp_a, pp_b = out[True]["pitch_pred"].cpu().numpy(), out[False]["pitch_pred"].cpu().numpy()
+    same_uv = (pp_a[:, 1] > 0) == (pp_b[:, 1] > 0)
+    close = np.abs(pp_a[:, 0] - pp_b[:, 0]) < 1e-3
+    frac = float((same_uv & close).mean())
+    print(f"forward, {pb.total_frames} frames, T_f0={T}: interleaved vs per-GEMM F0 nets agree on {frac * 100:.3f} % of the frames; {ran[True]}")
+    assert frac >= 0.995
 
 
 # ---------------------------------------------------------------------------------------------------
