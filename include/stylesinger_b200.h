@@ -271,6 +271,11 @@ int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin
 /* Unit-test granularity: multi-head attention, 2 heads x 128; q [sumL,256], k/v [sumS,256]. */
 int ssb_op_attention(const float* q, const float* k, const float* v, const int32_t* q_offsets,
                      const int32_t* k_offsets, int32_t B, float scale, float* out, void* stream);
+/* Same contract on the tcgen05 / TMA attention kernel (csrc/attention_tc.cu; 3-pass fp16 hi/lo split MMAs for QK^T and PV,
+ * TMA-staged K / V^T tiles), the path long batches take inside the FFT blocks (common_layers.py:277-286) and the style
+ * aligner (lse.py:41). */
+int ssb_op_attention_tc(const float* q, const float* k, const float* v, const int32_t* q_offsets,
+                        const int32_t* k_offsets, int32_t B, float scale, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ EXPORTS = [
     "ssb_vocoder_set_tensor_cores", "ssb_variant_launch_count", "ssb_variant_names", "ssb_tensor_map_cache_stats",
     "ssb_model_set_persistent_groups", "ssb_model_set_cond_hoist", "ssb_mel_diffusion_plms_workspace_bytes",
     "ssb_mel_diffusion_sample_plms", "ssb_fft_workspace_bytes", "ssb_fft_encoder", "ssb_fft_decoder",
-    "ssb_get_style_workspace_bytes", "ssb_get_style", "ssb_set_interleaved_layers",
+    "ssb_get_style_workspace_bytes", "ssb_get_style", "ssb_set_interleaved_layers", "ssb_op_attention_tc",
 ]
 
 
@@ -92,6 +92,7 @@ def _load():
         "ssb_hifigan_generate": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, u64, vp, vp, sz, vp]),
         "ssb_op_conv1d": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
         "ssb_op_attention": (C.c_int, [vp, vp, vp, vp, vp, i32, C.c_float, vp, vp]),
+        "ssb_op_attention_tc": (C.c_int, [vp, vp, vp, vp, vp, i32, C.c_float, vp, vp]),
         "ssb_mel_postprocess": (C.c_int, [vp, C.c_int64, C.c_float, C.c_float, vp, vp]),
         "ssb_launch_count": (C.c_int64, []),
         "ssb_model_set_tensor_cores": (C.c_int, [vp, i32]),

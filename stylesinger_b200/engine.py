@@ -496,12 +496,14 @@ def op_conv1d_tc(x, offsets, w, b, dilation=1):
     return out
 
 
-def op_attention(q, k, v, q_offsets, k_offsets, scale):
+def op_attention(q, k, v, q_offsets, k_offsets, scale, tc=False):
+    """tc=True: the tcgen05 / TMA kernel (ssb_op_attention_tc) instead of the fp32 one."""
     _require_cuda()
     qo = np.ascontiguousarray(q_offsets, np.int32)
     ko = np.ascontiguousarray(k_offsets, np.int32)
     out = torch.empty_like(q)
     stream = C.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
-    check(lib.ssb_op_attention(_ptr(q), _ptr(k), _ptr(v), qo.ctypes.data, ko.ctypes.data, len(qo) - 1, float(scale),
-                               _ptr(out), stream), "ssb_op_attention")
+    fn = lib.ssb_op_attention_tc if tc else lib.ssb_op_attention
+    check(fn(_ptr(q), _ptr(k), _ptr(v), qo.ctypes.data, ko.ctypes.data, len(qo) - 1, float(scale),
+             _ptr(out), stream), "ssb_op_attention_tc" if tc else "ssb_op_attention")
     return out

@@ -10,7 +10,7 @@ t0=$(date +%s)
 lap() { echo "== [$(( $(date +%s) - t0 )) s] $*"; }
 if has tests; then
   lap "targeted tests"
-  timeout 1500 python -m pytest tests/test_gpu_scale.py tests/test_gpu_tc.py -m gpu -q -rA -x -p no:cacheprovider > $O/tests_${tag}.log 2>&1
+  timeout 1500 python -m pytest tests/test_gpu_scale.py tests/test_gpu_tc.py -m gpu -q -rA -p no:cacheprovider > $O/tests_${tag}.log 2>&1
   grep -E "passed|failed|error" $O/tests_${tag}.log | tail -3
   grep -E "^(FAILED|ERROR)|L-inf|agree" $O/tests_${tag}.log | head -30
 fi
