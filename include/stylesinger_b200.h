@@ -264,6 +264,11 @@ void ssb_tensor_map_cache_stats(int64_t* encodes, int64_t* hits);
  * Results are identical either way (same kernels' arithmetic); tests use it for A/B checks.  Returns the new state. */
 int32_t ssb_set_interleaved_layers(int32_t enable);
 
+/* Process-wide switch of the tcgen05 / TMA attention kernel (csrc/attention_tc.cu) for the long-batch paths of the FFT blocks
+ * (common_layers.py:277-286) and of the style aligner's cross-attention (lse.py:41); short batches always use the fp32
+ * kernel.  Returns the new state. */
+int32_t ssb_set_attention_tensor_cores(int32_t enable);
+
 /* Unit-test granularity: one Conv1d over ragged rows with torch-layout HOST weights [N,Cin,k]
  * (packs on the fly with cudaMalloc; not for production use).  act: 0 none 1 relu 2 gelu 3 leaky(0.1) 4 tanh. */
 int ssb_op_conv1d(const float* x, const int32_t* offsets, int32_t B, int32_t Cin, const float* w_host,

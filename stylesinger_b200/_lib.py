@@ -58,7 +58,7 @@ EXPORTS = [
     "ssb_vocoder_set_tensor_cores", "ssb_variant_launch_count", "ssb_variant_names", "ssb_tensor_map_cache_stats",
     "ssb_model_set_persistent_groups", "ssb_model_set_cond_hoist", "ssb_mel_diffusion_plms_workspace_bytes",
     "ssb_mel_diffusion_sample_plms", "ssb_fft_workspace_bytes", "ssb_fft_encoder", "ssb_fft_decoder",
-    "ssb_get_style_workspace_bytes", "ssb_get_style", "ssb_set_interleaved_layers", "ssb_op_attention_tc",
+    "ssb_get_style_workspace_bytes", "ssb_get_style", "ssb_set_interleaved_layers", "ssb_op_attention_tc", "ssb_set_attention_tensor_cores",
 ]
 
 
@@ -111,6 +111,7 @@ def _load():
         "ssb_variant_names": (i32, [C.c_char_p, i32]),
         "ssb_tensor_map_cache_stats": (None, [P(C.c_int64), P(C.c_int64)]),
         "ssb_set_interleaved_layers": (i32, [i32]),
+        "ssb_set_attention_tensor_cores": (i32, [i32]),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

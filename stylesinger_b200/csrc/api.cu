@@ -683,6 +683,7 @@ int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, in
 }
 int64_t ssb_launch_count(void) { return (int64_t)ssb::g_launches.load(); }
 int32_t ssb_set_interleaved_layers(int32_t enable) { return ssb::set_dual_enabled(enable); }
+int32_t ssb_set_attention_tensor_cores(int32_t enable) { return ssb::set_attention_tc_enabled(enable); }
 int64_t ssb_variant_launch_count(const char* variant) { return variant ? (int64_t)ssb::variant_launch_count(variant) : 0; }
 int32_t ssb_variant_names(char* buf, int32_t cap) { return buf && cap > 0 ? ssb::variant_names(buf, cap) : 0; }
 void ssb_tensor_map_cache_stats(int64_t* encodes, int64_t* hits) {

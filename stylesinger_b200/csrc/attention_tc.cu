@@ -12,6 +12,8 @@
 // epilogue divides by l.  P is carried as fp16 hi/lo planes of 256 * p so that weights down to 2^-33 survive the split.
 // The [L, S] score matrix is never materialised (63 MB / utterance / layer in the reference at F = 2812).
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: softmax / epilogue (thread = query row)
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -324,6 +326,21 @@ __global__ void k_transpose_planes(const __half* __restrict__ xh, const __half* 
 }
 
 }  // namespace
+
+static std::atomic<int> g_attn_tc{-1};
+bool attention_tc_enabled() {
+  int v = g_attn_tc.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("SSB_ATTN_TC");
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 0;  // default OFF until validated on hardware
+    g_attn_tc.store(v, std::memory_order_relaxed);
+  }
+  return v != 0 && tc_available();
+}
+int set_attention_tc_enabled(int on) {
+  g_attn_tc.store(on ? 1 : 0, std::memory_order_relaxed);
+  return on ? 1 : 0;
+}
 
 int transpose_planes(Ctx& ctx, const __half* xh, const __half* xl, int ld, int col0, int64_t rows, int C, __half* th, __half* tl,
                      int64_t ldt) {

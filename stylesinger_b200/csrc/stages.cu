@@ -78,9 +78,17 @@ int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* kee
   float* att = alloc_rows(c, s, H);
   float* ff = tc ? nullptr : alloc_rows(c, s, 4 * H);
   __half *hh = nullptr, *hl = nullptr, *fh = nullptr, *fl = nullptr;  // fp16 hi/lo planes of h and of gelu(ffn_1)
+  // tcgen05 attention (attention_tc.cu): q/k/v only as fp16 hi/lo planes [rows, 768] + V^T planes [256, ldvt]
+  const bool atc = tc && attention_tc_enabled();
+  const int64_t ldvt = (s.rows + 7) & ~int64_t(7);
+  __half *qh = nullptr, *ql = nullptr, *vth = nullptr, *vtl = nullptr;
   if (tc) {
     hh = alloc_half_rows(c, s, H); hl = alloc_half_rows(c, s, H);
     fh = alloc_half_rows(c, s, 4 * H); fl = alloc_half_rows(c, s, 4 * H);
+  }
+  if (atc) {
+    qh = alloc_half_rows(c, s, 3 * H); ql = alloc_half_rows(c, s, 3 * H);
+    vth = c.alloc<__half>((size_t)ldvt * H); vtl = c.alloc<__half>((size_t)ldvt * H);
   }
   WS_OK(c);
   for (size_t i = 0; i < f.layers.size(); ++i) {
@@ -90,14 +98,26 @@ int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* kee
       RUN(split_planes(c, h, H, s.rows, H, 1.0f, hh, hl));
       GemmTC g;
       g.A_hi = hh; g.A_lo = hl; g.rows_total = s.rows; g.w = &L.qkv_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
-      g.e.mode = EPI_GENERIC; g.e.out = qkv; g.e.ldo = 3 * H;
+      g.e.mode = EPI_GENERIC;
+      if (atc) { g.e.oh = qh; g.e.ol = ql; g.e.ldh = 3 * H; }
+      else { g.e.out = qkv; g.e.ldo = 3 * H; }
       RUN(conv_gemm_tc(c, g));
     } else {
       ConvGemm g = make_gemm(L.qkv, s, h, H);
       g.e.out = qkv; g.e.ldo = 3 * H;
       RUN(conv_gemm(c, g));
     }
-    {
+    if (atc) {
+      RUN(transpose_planes(c, qh, ql, 3 * H, 2 * H, s.rows, H, vth, vtl, ldvt));
+      AttnTCArgs a;
+      a.utt_q = s.utt; a.utt_k = s.utt; a.B = s.B; a.max_q = s.maxlen; a.heads = 2;
+      a.Qh = qh; a.Ql = ql; a.rows_q = s.rows; a.ldq = 3 * H; a.qcol0 = 0;
+      a.Kh = qh; a.Kl = ql; a.rows_k = s.rows; a.ldk = 3 * H; a.kcol0 = H;
+      a.Vth = vth; a.Vtl = vtl; a.ldvt = ldvt;
+      a.keymask = keep; a.scale = 0.08838834764831845f;  // 128^-0.5
+      a.oh = hh; a.ol = hl; a.ldh = H;                   // straight into the out-projection's A planes
+      RUN(attention_tc(c, a));
+    } else {
       AttnArgs a;
       a.utt_q = s.utt; a.utt_k = s.utt; a.B = s.B; a.max_q = s.maxlen; a.heads = 2;
       a.Q = qkv; a.ldq = 3 * H; a.K = qkv + H; a.ldk = 3 * H; a.V = qkv + 2 * H; a.ldv = 3 * H;
@@ -106,7 +126,7 @@ int fft_blocks(Ctx& c, const FFT& f, const SeqDev& s, float* x, const float* kee
       RUN(attention(c, a));
     }
     if (tc) {
-      RUN(split_planes(c, att, H, s.rows, H, 1.0f, hh, hl));
+      if (!atc) RUN(split_planes(c, att, H, s.rows, H, 1.0f, hh, hl));
       GemmTC g;
       g.A_hi = hh; g.A_lo = hl; g.rows_total = s.rows; g.w = &L.out_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
       g.e.mode = EPI_GENERIC; g.e.res = x; g.e.ld_res = H; g.e.rowmask = keep; g.e.out = x; g.e.ldo = H;
@@ -328,6 +348,15 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
     WS_OK(c);
     RUN(split_planes(c, zl, H, sr.rows, H, 1.0f, zlh, zll));
   }
+  const bool atc = tc && attention_tc_enabled();
+  const int64_t ldvt = (sr.rows + 7) & ~int64_t(7);
+  __half *aqh = nullptr, *aql = nullptr, *akh = nullptr, *akl = nullptr, *avth = nullptr, *avtl = nullptr;
+  if (atc) {
+    aqh = alloc_half_rows(c, sf, H); aql = alloc_half_rows(c, sf, H);
+    akh = alloc_half_rows(c, sr, 2 * H); akl = alloc_half_rows(c, sr, 2 * H);
+    avth = c.alloc<__half>((size_t)ldvt * H); avtl = c.alloc<__half>((size_t)ldvt * H);
+    WS_OK(c);
+  }
   auto tcg = [&](const SeqDev& sq, const __half* ah, const __half* al, const ConvTC& w) {
     GemmTC g;
     g.A_hi = ah; g.A_lo = al; g.rows_total = sq.rows; g.w = &w; g.tiles = sq.tiles; g.ntiles = sq.ntiles;
@@ -339,10 +368,12 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
     if (tc) {
       RUN(split_planes(c, style, H, sf.rows, H, 1.0f, sth, stl));
       GemmTC gq = tcg(sf, sth, stl, L.q_tc);
-      gq.e.out = q; gq.e.ldo = H;
+      if (atc) { gq.e.oh = aqh; gq.e.ol = aql; gq.e.ldh = H; }
+      else { gq.e.out = q; gq.e.ldo = H; }
       RUN(conv_gemm_tc(c, gq));
       GemmTC gk = tcg(sr, zlh, zll, L.kv_tc);
-      gk.e.out = kv; gk.e.ldo = 2 * H;
+      if (atc) { gk.e.oh = akh; gk.e.ol = akl; gk.e.ldh = 2 * H; }
+      else { gk.e.out = kv; gk.e.ldo = 2 * H; }
       RUN(conv_gemm_tc(c, gk));
     } else {
       {
@@ -356,7 +387,17 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
         RUN(conv_gemm(c, g));
       }
     }
-    {
+    if (atc) {  // cross-attention on the tcgen05 kernel: q planes [F rows, 256], k | v planes [R rows, 512]
+      RUN(transpose_planes(c, akh, akl, 2 * H, H, sr.rows, H, avth, avtl, ldvt));
+      AttnTCArgs a;
+      a.utt_q = sf.utt; a.utt_k = sr.utt; a.B = sf.B; a.max_q = sf.maxlen; a.heads = 2;
+      a.Qh = aqh; a.Ql = aql; a.rows_q = sf.rows; a.ldq = H; a.qcol0 = 0;
+      a.Kh = akh; a.Kl = akl; a.rows_k = sr.rows; a.ldk = 2 * H; a.kcol0 = 0;
+      a.Vth = avth; a.Vtl = avtl; a.ldvt = ldvt;
+      a.keymask = kmask; a.scale = 0.08838834764831845f;
+      a.oh = sth; a.ol = stl; a.ldh = H;
+      RUN(attention_tc(c, a));
+    } else {
       AttnArgs a;
       a.utt_q = sf.utt; a.utt_k = sr.utt; a.B = sf.B; a.max_q = sf.maxlen; a.heads = 2;
       a.Q = q; a.ldq = H; a.K = kv; a.ldk = 2 * H; a.V = kv + H; a.ldv = 2 * H;
@@ -364,7 +405,7 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
       RUN(attention(c, a));
     }
     if (tc) {
-      RUN(split_planes(c, att, H, sf.rows, H, 1.0f, sth, stl));
+      if (!atc) RUN(split_planes(c, att, H, sf.rows, H, 1.0f, sth, stl));
       GemmTC g = tcg(sf, sth, stl, L.out_tc);
       g.e.res = style; g.e.ld_res = H; g.e.out = tmp; g.e.ldo = H;
       RUN(conv_gemm_tc(c, g));

@@ -243,3 +243,32 @@ def test_attention_tc_op_matches_torch(ql, kl):
             worst = max(worst, float((out[qo[i]:qo[i + 1], h * 128:(h + 1) * 128].double() - ref).abs().max()))
     print(f"attention_tc {ql} x {kl}: L-inf vs float64 {worst:.3e}; fp32 kernel vs tc {float((out - simt).abs().max()):.3e}")
     assert torch.isfinite(out).all() and worst < 2e-5
+
+
+ATTN_TC_DEFAULT = 0  # library default of the switch (csrc/attention_tc.cu attention_tc_enabled)
+
+
+def test_forward_attention_tensor_cores_match_fp32_kernel():
+    """Same 12 s forward with the decoder's self-attention and the aligner's cross-attention on the tcgen05 kernel vs the
+    fp32 kernel (all projections on tcgen05 both times): style / decoder_inp / coarse_mel agree to fp32 rounding."""
+    from stylesinger_b200 import synth
+    from stylesinger_b200._lib import lib
+    from stylesinger_b200.engine import pack_batch
+    u = synth.make_utterance(12.0, utt_idx=78)
+    m = acoustic_engine(4)
+    pb = pack_batch([u]).to(DEV)
+    out = {}
+    try:
+        for on in (True, False):
+            lib.ssb_set_attention_tensor_cores(1 if on else 0)
+            l0 = lib.ssb_launch_count()
+            o = m.forward(pb, seed=12, skip_mel_diffusion=True, want=("decoder_inp", "coarse_mel", "style"))
+            out[on] = {k: v.clone() for k, v in o.items()}
+            out[on]["launches"] = lib.ssb_launch_count() - l0
+    finally:
+        lib.ssb_set_attention_tensor_cores(ATTN_TC_DEFAULT)
+    for k in ("style", "decoder_inp", "coarse_mel"):
+        e = _maxabs(out[True][k], out[False][k])
+        sc = float(out[False][k].abs().max())
+        print(f"{k}: attention tcgen05 vs fp32 kernel max |diff| {e:.3e} (max |value| {sc:.2f})")
+        assert torch.isfinite(out[True][k]).all() and e < 1e-4 * max(1.0, sc), k
