@@ -140,6 +140,7 @@ struct VocStage {
   Conv up;          // transposed conv as 3-tap conv, N = u * Cout
   int u = 1, Cout = 0;
   float *nc_w = nullptr, *nc_b = nullptr; int nc_s = 1;  // noise conv
+  float* nc_wt = nullptr;                                 // the same weights as [K, C] (tiled kernel)
   struct RB { Conv c1[3], c2[3]; ConvTC c1_tc[3], c2_tc[3]; } rb[4];
   ConvTC up_tc;     // tensor-core packing of the transposed conv
   bool res_tc = false;  // all ResBlock convs of this stage are tensor-core eligible (C % 64 == 0)

@@ -144,7 +144,8 @@ int nsf_source(Ctx&, const SeqDev& s1, const SeqDev& s256, const float* f0, cons
 size_t nsf_scratch_doubles(const SeqDev& s256);
 // x[r, n] += b[n] + sum_j w[n][j] * har[r*s - s/2 + j]   (noise_convs[i], kernel 2s stride s; s==1: kernel 1)
 int noise_conv_add(Ctx&, const SeqDev& sx, const SeqDev& s256, float* x, int ld, int C, const float* har, const float* w,
-                   const float* b, int s, __half* ph = nullptr, __half* pl = nullptr, float plane_slope = 0.1f);
+                   const float* b, int s, __half* ph = nullptr, __half* pl = nullptr, float plane_slope = 0.1f,
+                   const float* wt = nullptr);  // wt: the weights as [K, C] -> tiled kernel
 // wav[tight] = tanh(x[r,0])
 int tanh_out(Ctx&, const SeqDev&, const float* x, int ld, float* wav_tight);
 // mask/clip mel (inference/StyleSinger.py:56-58) in place on guarded rows; f0 masked the same way

@@ -540,6 +540,15 @@ int build_vocoder(TensorMap& tm, const ssb_vocoder_config& cfg, Vocoder* v) {
         s.nc_s = prod_after;  // stride = prod(upsample_rates[i+1:]) (hifigan_nsf.py:126-132)
         s.nc_w = upload_tensor(pool, tm.get(n + "weight"));
         s.nc_b = upload_tensor(pool, tm.get(n + "bias"));
+        if (const HostTensor* wt = tm.get(n + "weight")) {  // [C, 1, K] -> [K, C]: lanes of the tiled kernel read contiguous channels
+          const int K = s.nc_s == 1 ? 1 : 2 * s.nc_s, Cn = s.Cout;
+          if (wt->numel() == (size_t)K * Cn) {
+            std::vector<float> T((size_t)K * Cn);
+            for (int cc = 0; cc < Cn; ++cc)
+              for (int j = 0; j < K; ++j) T[(size_t)j * Cn + cc] = wt->data[(size_t)cc * K + j];
+            s.nc_wt = pool.upload(T);
+          }
+        }
       }
       for (int j = 0; j < cfg.n_res; ++j) {
         const int k = cfg.res_kernels[j];

@@ -1226,7 +1226,7 @@ int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight
       if (res_tc && !nsf) { g.e.out2_h = px_h; g.e.out2_l = px_l; g.e.ldh = st.u * Co; g.e.plane_act = ACT_LRELU; g.e.plane_slope = 0.1f; }
       RUN(conv_gemm(c, g));
     }
-    if (nsf) RUN(noise_conv_add(c, so, s256, xu, Co, Co, har, st.nc_w, st.nc_b, st.nc_s, res_tc ? px_h : nullptr, px_l, 0.1f));
+    if (nsf) RUN(noise_conv_add(c, so, s256, xu, Co, Co, har, st.nc_w, st.nc_b, st.nc_s, res_tc ? px_h : nullptr, px_l, 0.1f, st.nc_wt));
     for (int j = 0; j < v.nk; ++j) {  // MRF: mean of the resblocks
       const float* rin = xu;
       const __half *rin_h = px_h, *rin_l = px_l;
