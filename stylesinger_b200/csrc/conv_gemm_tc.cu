@@ -180,8 +180,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     const int64_t st = 4 * (int64_t)e.ldh;
     __half* ph = e.oh + rb * e.ldh + (n4 >> 1);
     __half* pl = e.ol + rb * e.ldh + (n4 >> 1);
-#pragma unroll
     const bool has_add = e.add != nullptr;
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < nsteps) {
         const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
@@ -190,7 +190,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
           const float4 ad = pre.a[i];
           g0 += ad.x; f0 += ad.y; g1 += ad.z; f1 += ad.w;
         }
-        split_store2(ph + i * st, pl + i * st, sigmoidf_(g0) * tanhf(f0), sigmoidf_(g1) * tanhf(f1));
+        split_store2(ph + i * st, pl + i * st, gate_act(g0, f0), gate_act(g1, f1));
       }
     }
   } else if constexpr (MODE == EPI_RES_SKIP) {

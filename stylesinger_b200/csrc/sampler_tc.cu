@@ -106,7 +106,7 @@ __device__ __forceinline__ void epilogue32(const SPhase& e, int64_t r, int64_t t
   if (e.mode == SP_GATE) {
     float z[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) z[q] = sigmoidf_(v[2 * q]) * tanhf(v[2 * q + 1]);
+    for (int q = 0; q < 16; ++q) z[q] = gate_act(v[2 * q], v[2 * q + 1]);
     split_store16(e.oh + r * e.ldh + (n >> 1), e.ol + r * e.ldh + (n >> 1), z);
     return;
   }

@@ -115,6 +115,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// WaveNet gate sigmoid(g) * tanh(f) = (e^{2f} - 1) / ((e^{2f} + 1) (1 + e^{-g})): two ex2.approx (2 ulp), one fast division,
+// branch-free.  The libm forms (expf + IEEE division, tanhf with its range branches) cost ~100 dependent instructions per
+// gate and made the epilogue warps - not the tensor pipe - the limiter of the gate GEMM (profiles/r02_ncu_dual_v3.md:
+// 0.17 IPC per epilogue warp).  Absolute error <= ~3e-7, the size of the fp32 rounding already in the accumulators.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gate_act(float g, float f) {
+  f = fminf(fmaxf(f, -15.0f), 15.0f);   // tanh(15) == 1 in fp32; keeps e^{2f} <= 1.1e13
+  g = fmaxf(g, -50.0f);                 // sigmoid(-50) = 2e-22; keeps the denominator below 2^126 (__fdividef's range)
+  const float e2f = ex2_approx(f * 2.8853900817779268f);
+  const float eg = ex2_approx(g * -1.4426950408889634f);
+  return __fdividef(e2f - 1.0f, (e2f + 1.0f) * (1.0f + eg));
+}
+
 __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* z) {
   // 16 consecutive values -> two 16-byte stores per plane
   __align__(16) __half h[16], l[16];

@@ -143,8 +143,9 @@ def test_mel_sampler_T100_pair_kernels_vs_simt_philox_20k_frames():
     assert ran["tc"].get("tc2r<128,GATE>", 0) == T * 20 and ran["tc"].get("tc2<128,RES_SKIP>", 0) == T * 20
     # two lanes, software-pipelined by half a layer: first gate and last 1x1 alone, 2L - 1 interleaved launches in between
     assert ran["dual"].get("tc2d<128,GATE+RES_SKIP>", 0) == T * 39, ran["dual"]
-    assert ran["dual"].get("tc2r<128,GATE>", 0) + ran["dual"].get("tc2<128,GATE>", 0) == T
-    assert ran["dual"].get("tc2<128,RES_SKIP>", 0) == T
+    # (the lone first gate / last 1x1 of a step cover half the batch: here small enough for the single-CTA kernel)
+    assert sum(v for k, v in ran["dual"].items() if k.endswith(",GATE>")) == T, ran["dual"]
+    assert sum(v for k, v in ran["dual"].items() if k.endswith(",RES_SKIP>")) == T, ran["dual"]
     assert not ran["simt"], ran["simt"]  # the fp32 FFMA path launches no tcgen05 kernel
     assert torch.isfinite(out["dual"]).all() and err < 1e-3 and err_d < 1e-4
 
