@@ -58,10 +58,12 @@ def build(force=False, verbose=True):
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [_nvcc()] + flags + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        tmp = LIB + ".tmp"  # link beside the target, then rename: a snapshot of the tree never sees a half-written .so
+        cmd = [_nvcc()] + flags + ["-shared", "-o", tmp] + objs + ["-lcudart"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        os.replace(tmp, LIB)
     return LIB
 
 

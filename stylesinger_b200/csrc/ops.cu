@@ -615,6 +615,43 @@ __global__ void k_tanh_out(const int4* utt, const float* x, int ld, float* wav) 
   if (t >= u.y) return;
   wav[(int64_t)u.z + t] = tanhf(x[((int64_t)u.x + t) * ld]);
 }
+// conv_post + tanh of the HiFi-GAN generator (hifigan_nsf.py:165-167): wav[t] = tanh(b + sum_{j,c} W[j][c] * leaky_relu(x[t + j - center][c])).
+// N = 1 makes the implicit-GEMM kernels waste 63/64 of a tile; here a block stages CP_T + taps - 1 rows of leaky_relu(x) in
+// shared memory (row pitch C + 1: conflict-free) and every thread reduces the window of one output sample.
+constexpr int CP_T = 256;
+__global__ void __launch_bounds__(CP_T) k_conv_post_tanh(const int4* utt, const float* x, int ld, int C, int taps, int center, const float* W,
+                                                         int npad, const float* bias, float slope, float* wav) {
+  extern __shared__ float cp_sm[];  // [(CP_T + taps - 1) * (C + 1)] activations, then [taps * C] weights
+  const int b = blockIdx.y;
+  const int4 u = utt[b];
+  const int t0 = blockIdx.x * CP_T;
+  if (t0 >= u.y) return;
+  const int pitch = C + 1, nr = CP_T + taps - 1;
+  float* sw = cp_sm + nr * pitch;
+  for (int i = threadIdx.x; i < taps * C; i += CP_T) sw[i] = W[(size_t)i * npad];
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < nr * c4n; i += CP_T) {
+    const int rl = i / c4n, c = (i - rl * c4n) << 2;
+    const int t = t0 + rl - center;  // rows outside the utterance are the zero "same" padding
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < u.y) v = *reinterpret_cast<const float4*>(x + ((int64_t)u.x + t) * ld + c);
+    float* d = cp_sm + rl * pitch + c;
+    d[0] = v.x > 0.f ? v.x : v.x * slope; d[1] = v.y > 0.f ? v.y : v.y * slope;
+    d[2] = v.z > 0.f ? v.z : v.z * slope; d[3] = v.w > 0.f ? v.w : v.w * slope;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= u.y) return;
+  float acc = bias ? bias[0] : 0.f;
+  for (int j = 0; j < taps; ++j) {
+    const float* xr = cp_sm + (threadIdx.x + j) * pitch;
+    const float* wr = sw + j * C;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) acc = fmaf(xr[c], wr[c], acc);
+  }
+  wav[(int64_t)u.z + t] = tanhf(acc);
+}
+
 __global__ void k_mel_post(const int4* utt, float* mel, int ld, float* f0, float vmin, float vmax) {
   ROW_SETUP();
   for (int c = threadIdx.x; c < 80; c += 32) mel[r * ld + c] = fminf(fmaxf(mel[r * ld + c], vmin), vmax);
@@ -844,6 +881,17 @@ int tanh_out(Ctx& ctx, const SeqDev& s, const float* x, int ld, float* wav) {
   if (ctx.dry || s.B == 0) return 0;
   k_tanh_out<<<dim3((s.maxlen + 255) / 256, s.B), 256, 0, ctx.stream>>>(s.utt, x, ld, wav);
     ++g_launches;
+  SSB_CUDA(cudaGetLastError());
+  return 0;
+}
+int conv_post_tanh(Ctx& ctx, const SeqDev& s, const float* x, int ld, int C, int taps, int center, const float* W, int npad,
+                   const float* bias, float slope, float* wav) {
+  if (ctx.dry || s.B == 0) return 0;
+  SSB_CHECK(C % 4 == 0 && ld % 4 == 0, "conv_post_tanh: channel count must be a multiple of 4");
+  const size_t smem = ((size_t)(CP_T + taps - 1) * (C + 1) + (size_t)taps * C) * sizeof(float);
+  SSB_CHECK(smem <= 48 * 1024, "conv_post_tanh: window does not fit the default shared-memory limit");
+  k_conv_post_tanh<<<dim3((s.maxlen + CP_T - 1) / CP_T, s.B), CP_T, smem, ctx.stream>>>(s.utt, x, ld, C, taps, center, W, npad, bias, slope, wav);
+  ++g_launches;
   SSB_CUDA(cudaGetLastError());
   return 0;
 }

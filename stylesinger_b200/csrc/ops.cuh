@@ -148,6 +148,9 @@ int noise_conv_add(Ctx&, const SeqDev& sx, const SeqDev& s256, float* x, int ld,
                    const float* wt = nullptr);  // wt: the weights as [K, C] -> tiled kernel
 // wav[tight] = tanh(x[r,0])
 int tanh_out(Ctx&, const SeqDev&, const float* x, int ld, float* wav_tight);
+// wav = tanh(conv_post(leaky_relu(x, slope))) for a 1-output-channel conv packed as W[taps][C][npad] (column 0)
+int conv_post_tanh(Ctx&, const SeqDev&, const float* x, int ld, int C, int taps, int center, const float* W, int npad,
+                   const float* bias, float slope, float* wav_tight);
 // mask/clip mel (inference/StyleSinger.py:56-58) in place on guarded rows; f0 masked the same way
 int mel_postprocess(Ctx&, const SeqDev&, float* mel, int ld, float* f0, float vmin, float vmax);
 

@@ -33,6 +33,7 @@ constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;  // 48 KB
 constexpr int STAGES = 4;
 constexpr int SMEM = STAGES * STAGE + 1024 + 512 + 1024;
 constexpr uint32_t TMEM_COLS = 2 * BN;
+static_assert(sizeof(SPhase) <= 1024, "the phase descriptor is staged in a 1 KB shared-memory slot");
 
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -90,6 +91,12 @@ __device__ __forceinline__ void prefetch32(const SPhase& e, int64_t r, int n, bo
 #pragma unroll
       for (int q = 0; q < 8; ++q) p.a[q] = __ldcg(sp + q);
     }
+  } else if (e.mode == SP_GATE) {
+    if (e.add) {
+      const float4* ap = reinterpret_cast<const float4*>(e.add + r * e.ld_add + n);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p.a[q] = __ldg(ap + q);
+    }
   } else if (e.mode == SP_MEL_SAMPLE) {
     const float4* xp = reinterpret_cast<const float4*>(e.out + r * e.ldo + n);
 #pragma unroll
@@ -104,6 +111,12 @@ __device__ __forceinline__ void epilogue32(const SPhase& e, int64_t r, int64_t t
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + __ldg(e.bias + n + j);
   if (e.mode == SP_GATE) {
+    if (e.add) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v[4 * q] += pre.a[q].x; v[4 * q + 1] += pre.a[q].y; v[4 * q + 2] += pre.a[q].z; v[4 * q + 3] += pre.a[q].w;
+      }
+    }
     float z[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) z[q] = gate_act(v[2 * q], v[2 * q + 1]);

@@ -24,6 +24,8 @@ struct SPhase {
   int ld_res;
   float beta;
   const float* vec2;   // step bias added before the planes are written
+  const float* add;    // GATE: hoisted conditioner projection of this layer [rows, ld_add] (packed gate column order), or null
+  int ld_add;
   float* skip;         // RES_SKIP: skip accumulator
   int ld_skip, C, skip_init;
   __half* sh;          // RES_SKIP (last layer): planes of the finished skip sum

@@ -701,6 +701,17 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
   RUN(mel_q_sample(c, s, coarse_g, 80, noise, m.spec_min, m.spec_max, sa, s1a, xm, 80, seed, 1000));
   RUN(x80_planes(c, xm, s.rows, pl[0], pl[1]));
   RUN(split_planes(c, cond_g, 256, s.rows, 256, 1.0f, pl[6], pl[7]));
+  // step-invariant conditioner projection of all L layers, once per call (one per-launch GEMM): the gate phases then
+  // contract K = 3C instead of 3C + 256 and add it in the epilogue
+  float* condpre = nullptr;
+  if (m.cond_hoist && d.cond_all_tc.ok) {
+    condpre = alloc_rows(c, s, L * 2 * C, false);
+    WS_OK(c);
+    GemmTC g;
+    g.A_hi = pl[6]; g.A_lo = pl[7]; g.rows_total = s.rows; g.w = &d.cond_all_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+    g.e.mode = EPI_GENERIC; g.e.out = condpre; g.e.ldo = L * 2 * C;
+    RUN(conv_gemm_tc(c, g));
+  }
   if (!c.dry) {
     std::vector<CUtensorMap> maps((size_t)nmaps);
     for (int i = 0; i < 6; ++i) {
@@ -735,6 +746,7 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
         a.a1 = 2; a.a2 = 6; a.w1 = W_L0 + 6 * l; a.w2 = W_L0 + 6 * l + 2; a.taps = 3; a.kchunks = C / 64; a.kchunks2 = 4;
         a.dil = d.layers[l].dil_tc.dil; a.center = 1; a.N = 2 * C; a.NT = 2 * C / 64; a.mode = SP_GATE;
         a.bias = d.layers[l].bias_gate_tc; a.oh = pl[4]; a.ol = pl[5]; a.ldh = C;
+        if (condpre) { a.a2 = -1; a.kchunks2 = 0; a.add = condpre + (size_t)l * 2 * C; a.ld_add = L * 2 * C; }
         ph[k++] = a;
         SPhase b = z;  // 1x1 output projection -> residual stream, next layer's input planes, skip sum
         b.a1 = 4; b.w1 = W_L0 + 6 * l + 4; b.kchunks = C / 64; b.N = 2 * C; b.NT = 2 * C / 64; b.mode = SP_RES_SKIP;
@@ -933,6 +945,17 @@ int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, co
     RUN(ddiff_input(c, s, z[n], uv[n], d.in_w, d.in_b, d.uv_emb, d.dtab + (size_t)(T - 1) * L * C, x[n], nullptr, C, pl[n][0], pl[n][1]));
     RUN(split_planes(c, n == 0 ? cond0 : cond1, 256, s.rows, 256, 1.0f, pl[n][4], pl[n][5]));
   }
+  float* condpre[2] = {nullptr, nullptr};  // hoisted conditioner projections (see run_mel_diffusion_persistent)
+  if (m.cond_hoist && m.f0net[0].cond_all_tc.ok && m.f0net[1].cond_all_tc.ok) {
+    for (int n = 0; n < 2; ++n) {
+      condpre[n] = alloc_rows(c, s, L * 2 * C, false);
+      WS_OK(c);
+      GemmTC g;
+      g.A_hi = pl[n][4]; g.A_lo = pl[n][5]; g.rows_total = s.rows; g.w = &m.f0net[n].cond_all_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
+      g.e.mode = EPI_GENERIC; g.e.out = condpre[n]; g.e.ldo = L * 2 * C;
+      RUN(conv_gemm_tc(c, g));
+    }
+  }
   if (!c.dry) {
     std::vector<CUtensorMap> maps((size_t)nmaps);
     std::vector<SPhase> ph((size_t)nph);
@@ -974,6 +997,7 @@ int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, co
           a.a1 = MB + 0; a.a2 = MB + 4; a.w1 = W_L0 + 6 * l; a.w2 = W_L0 + 6 * l + 2; a.taps = 3; a.kchunks = C / 64; a.kchunks2 = 4;
           a.dil = d.layers[l].dil_tc.dil; a.center = 1; a.N = 2 * C; a.NT = 2 * C / 64; a.mode = SP_GATE;
           a.bias = d.layers[l].bias_gate_tc; a.oh = pl[n][2]; a.ol = pl[n][3]; a.ldh = C;
+          if (condpre[n]) { a.a2 = -1; a.kchunks2 = 0; a.add = condpre[n] + (size_t)l * 2 * C; a.ld_add = L * 2 * C; }
           slot(k++) = a;
           SPhase b = zp;
           b.a1 = MB + 2; b.w1 = W_L0 + 6 * l + 4; b.kchunks = C / 64; b.N = 2 * C; b.NT = 2 * C / 64; b.mode = SP_RES_SKIP;
@@ -1277,7 +1301,10 @@ int run_vocoder(Ctx& c, const Vocoder& v, const Seq& seq, const float* mel_tight
     xin = acc; sin = so; C = Co; rate = rate_out;
     pin_h = pa_h; pin_l = pa_l;
   }
-  {
+  if (v.post.N == 1 && C % 4 == 0 && (size_t)((256 + v.post.taps - 1) * (C + 1) + v.post.taps * C) * 4 <= 48 * 1024) {
+    // N = 1: dedicated windowed reduction (leaky_relu 0.01 -> conv_post -> tanh in one pass over x)
+    RUN(conv_post_tanh(c, sin, xin, C, C, v.post.taps, v.post.center, v.post.W, v.post.Npad, v.post.bias, 0.01f, wav_tight));
+  } else {
     float* y = alloc_rows(c, sin, 4);
     WS_OK(c);
     ConvGemm g = make_gemm(v.post, sin, xin, C);
