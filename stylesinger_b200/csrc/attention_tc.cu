@@ -91,9 +91,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
+  // Key tiles sit on a grid aligned to 8 rows of the K/V layout: the V^T planes are read with the key index as the INNER
+  // TMA coordinate, whose byte offset must be a multiple of 16.  The (up to 7) rows in front of the utterance are masked.
   const int klen = uk.y;
-  const int n = (klen + AK - 1) / AK;  // key tiles
-  const int qrow0 = uq.x + q0, krow0 = uk.x;
+  const int kshift = uk.x & 7;
+  const int krow0 = uk.x - kshift;
+  const int n = (kshift + klen + AK - 1) / AK;  // key tiles
+  const int qrow0 = uq.x + q0;
   const int hq = p.qcol0 + head * HD, hk = p.kcol0 + head * HD;
 
   if (warp == 0) {
@@ -193,11 +197,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_con
     int g = 0;
     float m = -INFINITY;
     auto key_masks = [&](int j, uint32_t& m0, uint32_t& m1) {
-      const int k0 = j * AK + lane, k1 = k0 + 32;
-      bool v0 = k0 < klen, v1 = k1 < klen;
+      const int k0 = j * AK + lane - kshift, k1 = k0 + 32;  // key index inside the utterance
+      bool v0 = k0 >= 0 && k0 < klen, v1 = k1 >= 0 && k1 < klen;
       if (p.keymask) {
-        if (v0) v0 = __ldg(p.keymask + krow0 + k0) != 0.f;
-        if (v1) v1 = __ldg(p.keymask + krow0 + k1) != 0.f;
+        if (v0) v0 = __ldg(p.keymask + uk.x + k0) != 0.f;
+        if (v1) v1 = __ldg(p.keymask + uk.x + k1) != 0.f;
       }
       m0 = __ballot_sync(0xffffffffu, v0);
       m1 = __ballot_sync(0xffffffffu, v1);
