@@ -336,7 +336,7 @@ bool attention_tc_enabled() {
   int v = g_attn_tc.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("SSB_ATTN_TC");
-    v = e ? (atoi(e) != 0 ? 1 : 0) : 0;  // default OFF until validated on hardware
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 1;  // default on (validated on B200: tests/test_gpu_tc.py, profiles/r02_*attention*)
     g_attn_tc.store(v, std::memory_order_relaxed);
   }
   return v != 0 && tc_available();

@@ -464,6 +464,61 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 }
 
+// ---- epilogue warp loop of the CTA-pair kernels ------------------------------------------------------------------
+// Measured (tools/probe_layer.sh, profiles/r02_probe_layer_v5.md): with the epilogue reduced to draining TMEM the 1x1
+// residual GEMM still took 134 us of its 159 us - it was bound by the DEPENDENT global loads of its own epilogue operands
+// (one 32 x 32 chunk in flight per warp, issued one chunk ahead).  So the operands of ALL chunks a warp owns in a tile
+// (CPW = BN / 64 chunks: 4 at BN = 256) now live in registers and are fetched ONE TILE AHEAD: right after chunk k of tile i is
+// finished its register set is refilled with chunk k of tile i + 1.  That needs ~200 registers per epilogue thread, which the
+// kernels get with setmaxnreg (producer / MMA / allocator / L2-prefetch warps shrink to 40, the 8 epilogue warps grow to 232).
+struct EpiTile {
+  int64_t r0;   // first row of this warp's 32-row slice
+  int nrows;    // valid rows in the slice
+  int n0;       // first output column of the tile
+  int prob;     // dual kernel: 0 = gate problem, 1 = residual problem
+  int ok;       // 0: past the last tile
+};
+template <int CPW, int MODE0, int MODE1, typename TileFn>
+__device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC& e1, TileFn tile_at, float4* xb, uint32_t tmem_lanes,
+                                                   uint32_t acc_stride, uint32_t tfull0, uint32_t ltempty0, int eg, int lane, int dbg) {
+  auto fetch = [&](const EpiTile& t, int k, Pre& dst) {
+    const int n = t.n0 + (eg + 2 * k) * 32;
+    if constexpr (MODE0 == MODE1) prefetch_chunk<MODE0>(e0, t.r0, t.nrows, n, lane, dst);
+    else if (t.prob == 0) prefetch_chunk<MODE0>(e0, t.r0, t.nrows, n, lane, dst);
+    else prefetch_chunk<MODE1>(e1, t.r0, t.nrows, n, lane, dst);
+  };
+  EpiTile cur = tile_at(0);
+  Pre pr[CPW];
+  if (cur.ok) {
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) fetch(cur, k, pr[k]);
+  }
+  for (int it = 0; cur.ok; ++it) {
+    const int a = it & 1;
+    const EpiTile nx = tile_at(it + 1);
+    mbar_wait(tfull0 + 8 * a, (uint32_t)((it >> 1) & 1));
+    tc_fence_after();
+#pragma unroll 1
+    for (int k = 0; k < CPW; ++k) {
+      uint32_t v[32];
+      const int ch = eg + 2 * k;
+      tmem_ld32(tmem_lanes + (uint32_t)a * acc_stride + (uint32_t)(ch * 32), v);
+      if (cur.nrows > 0 && !(dbg & 1)) {
+        if constexpr (MODE0 == MODE1) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[0]);
+        else if (cur.prob == 0) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[0]);
+        else epilogue_chunk<MODE1>(e1, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[0]);
+      }
+#pragma unroll
+      for (int i = 0; i + 1 < CPW; ++i) pr[i] = pr[i + 1];
+      if (nx.ok) fetch(nx, k, pr[CPW - 1]);  // chunk k of the NEXT tile takes the register set that was just consumed
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    cur = nx;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x (2*HB) tile.  Each CTA stages its own
 // 128 rows of A (its own row tile of the ragged layout: the two row tiles of a pair need not be adjacent) and HB of
@@ -529,6 +584,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   const int nk1 = p.taps * p.kchunks;
   const int nk = nk1 + p.kchunks2;
 
+  if (warp < 4) {  // warpgroup 0 (producer, MMA issuer, TMEM allocator, L2 prefetch) needs few registers
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::: "memory");
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t lfull0 = mapa_u32(full0, 0);  // the leader's full barriers (cluster address)
@@ -619,38 +676,27 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       if (tile + ncl < total) pf(tile + ncl);
       if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
     }
-  } else if (warp >= 4) {
+  }
+  } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
     const int ew = warp & 3;
     const int eg = (warp - 4) >> 2;
-    constexpr int NCH = BN / 32;
-    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
-    int it = 0;
-    for (int tile = cid; tile < total; tile += ncl, ++it) {
-      const int a = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
+    auto tile_at = [&](int it) {
+      EpiTile t;
+      const int tile = cid + it * ncl;
+      t.ok = tile < total;
+      t.prob = 0;
+      if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; return t; }
       const int mp = tile / p.NT, nt = tile - mp * p.NT;
       const int mt = 2 * mp + (int)rank;
-      const bool have = mt < p.ntiles;
-      const int2 t = have ? p.tiles[mt] : make_int2(0, 0);
-      const int64_t r0 = (int64_t)t.x + ew * 32;
-      const int nrows = min(32, max(0, t.y - ew * 32));
-      float4* xb = xpose + (warp - 4) * 256;
-      Pre cur, nxt;
-      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + eg * 32, lane, cur);
-      mbar_wait(tfull0 + 8 * a, aph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch = eg; ch < NCH; ch += 2) {
-        if (ch + 2 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * K::ACC_STRIDE + (uint32_t)(ch * 32), v);
-        if (nrows > 0 && !(p.dbg & 1)) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
-        cur = nxt;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
-    }
+      const int2 tl = mt < p.ntiles ? p.tiles[mt] : make_int2(0, 0);
+      t.r0 = (int64_t)tl.x + ew * 32;
+      t.nrows = min(32, max(0, tl.y - ew * 32));
+      t.n0 = nt * BN;
+      return t;
+    };
+    pair_epilogue_loop<BN / 64, MODE, MODE>(p.e, p.e, tile_at, xpose + (warp - 4) * 256, tmem_base + ((uint32_t)(ew * 32) << 16),
+                                            K::ACC_STRIDE, tfull0, mapa_u32(tempty0, 0), eg, lane, p.dbg);
   }
   tc_fence_before();
   cluster_sync_all();  // neither CTA may exit (or free TMEM) while its pair still reads / signals it
@@ -728,6 +774,8 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
   const int total = npairs * p.NT;
   const int nkc = p.kchunks;
 
+  if (warp < 4) {  // warpgroup 0 (producer, MMA issuer, TMEM allocator, L2 prefetch) needs few registers
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::: "memory");
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t lafull0 = mapa_u32(afull0, 0), lbfull0 = mapa_u32(bfull0, 0);
@@ -810,38 +858,27 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
       if (tile + ncl < total) pf(tile + ncl);
       if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
     }
-  } else if (warp >= 4) {
+  }
+  } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
     const int ew = warp & 3;
     const int eg = (warp - 4) >> 2;
-    constexpr int NCH = BN / 32;
-    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
-    int it = 0;
-    for (int tile = cid; tile < total; tile += ncl, ++it) {
-      const int a = it & 1;
-      const uint32_t tph = (it >> 1) & 1;
+    auto tile_at = [&](int it) {
+      EpiTile t;
+      const int tile = cid + it * ncl;
+      t.ok = tile < total;
+      t.prob = 0;
+      if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; return t; }
       const int mp = tile / p.NT, nt = tile - mp * p.NT;
       const int mt = 2 * mp + (int)rank;
-      const bool have = mt < p.ntiles;
-      const int2 t = have ? p.tiles[mt] : make_int2(0, 0);
-      const int64_t r0 = (int64_t)t.x + ew * 32;
-      const int nrows = min(32, max(0, t.y - ew * 32));
-      float4* xb = xpose + (warp - 4) * 256;
-      Pre cur, nxt;
-      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + eg * 32, lane, cur);
-      mbar_wait(tfull0 + 8 * a, tph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch = eg; ch < NCH; ch += 2) {
-        if (ch + 2 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * K::ACC_STRIDE + (uint32_t)(ch * 32), v);
-        if (nrows > 0) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
-        cur = nxt;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
-    }
+      const int2 tl = mt < p.ntiles ? p.tiles[mt] : make_int2(0, 0);
+      t.r0 = (int64_t)tl.x + ew * 32;
+      t.nrows = min(32, max(0, tl.y - ew * 32));
+      t.n0 = nt * BN;
+      return t;
+    };
+    pair_epilogue_loop<BN / 64, MODE, MODE>(p.e, p.e, tile_at, xpose + (warp - 4) * 256, tmem_base + ((uint32_t)(ew * 32) << 16),
+                                            K::ACC_STRIDE, tfull0, mapa_u32(tempty0, 0), eg, lane, 0);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -928,6 +965,8 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
+  if (warp < 4) {  // warpgroup 0 (producer, MMA issuer, TMEM allocator, L2 prefetch) needs few registers
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::: "memory");
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t lfull0 = mapa_u32(full0, 0);
@@ -1016,54 +1055,29 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
       pf(it + 1);
       if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
     }
-  } else if (warp >= 4) {
+  }
+  } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
     const int ew = warp & 3;
     const int eg = (warp - 4) >> 2;
-    constexpr int NCH = BN / 32;
-    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
-    float4* xb = xpose + (warp - 4) * 256;
-    int p, t;
-    for (int it = 0; dual_decode(it, cid, ncl, n0, n1, p, t); ++it) {
-      const int a = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
+    auto tile_at = [&](int it) {
+      EpiTile e;
+      int p, t;
+      e.ok = dual_decode(it, cid, ncl, n0, n1, p, t);
+      if (!e.ok) { e.r0 = 0; e.nrows = 0; e.n0 = 0; e.prob = 0; return e; }
+      e.prob = p;
       const int NT = DQ(NT);
       const int mp = t / NT, nt = t - mp * NT;
       const int mt = 2 * mp + (int)rank;
-      const bool have = mt < DQ(ntiles);
-      const int2 tl = have ? DQ(tiles)[mt] : make_int2(0, 0);
-      const int64_t r0 = (int64_t)tl.x + ew * 32;
-      const int nrows = min(32, max(0, tl.y - ew * 32));
-      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)a * K::ACC_STRIDE;
-      Pre cur, nxt;
-      if (p == 0) {
-        prefetch_chunk<EPI_GATE>(P.q[0].e, r0, nrows, nt * BN + eg * 32, lane, cur);
-        mbar_wait(tfull0 + 8 * a, aph);
-        tc_fence_after();
-#pragma unroll 1
-        for (int ch = eg; ch < NCH; ch += 2) {
-          if (ch + 2 < NCH) prefetch_chunk<EPI_GATE>(P.q[0].e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)(ch * 32), v);
-          if (nrows > 0) epilogue_chunk<EPI_GATE>(P.q[0].e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
-          cur = nxt;
-        }
-      } else {
-        prefetch_chunk<EPI_RES_SKIP>(P.q[1].e, r0, nrows, nt * BN + eg * 32, lane, cur);
-        mbar_wait(tfull0 + 8 * a, aph);
-        tc_fence_after();
-#pragma unroll 1
-        for (int ch = eg; ch < NCH; ch += 2) {
-          if (ch + 2 < NCH) prefetch_chunk<EPI_RES_SKIP>(P.q[1].e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)(ch * 32), v);
-          if (nrows > 0) epilogue_chunk<EPI_RES_SKIP>(P.q[1].e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
-          cur = nxt;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
-    }
+      const int2 tl = mt < DQ(ntiles) ? DQ(tiles)[mt] : make_int2(0, 0);
+      e.r0 = (int64_t)tl.x + ew * 32;
+      e.nrows = min(32, max(0, tl.y - ew * 32));
+      e.n0 = nt * BN;
+      return e;
+    };
+    pair_epilogue_loop<BN / 64, EPI_GATE, EPI_RES_SKIP>(P.q[0].e, P.q[1].e, tile_at, xpose + (warp - 4) * 256,
+                                                        tmem_base + ((uint32_t)(ew * 32) << 16), K::ACC_STRIDE, tfull0,
+                                                        mapa_u32(tempty0, 0), eg, lane, 0);
   }
   tc_fence_before();
   cluster_sync_all();
