@@ -258,6 +258,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     const int64_t sto = 4 * (int64_t)e.ldo, sth = 4 * (int64_t)e.ldh;
     __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
     __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
+    // MRF accumulation reads `out` back: all 8 rows up front (one exposed round trip per chunk instead of one per step - the
+    // compiler cannot move a load above the previous step's store to the same array)
+    float4 oacc[8];
+    if (has_out && accum) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nsteps) oacc[i] = *reinterpret_cast<const float4*>(po + i * sto);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < nsteps) {
@@ -279,7 +287,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
         if (has_out) {
           float4* op = reinterpret_cast<float4*>(po + i * sto);
           if (accum) {
-            const float4 o = *op;
+            const float4 o = oacc[i];
             v0 = (v0 + o.x) * gamma; v1 = (v1 + o.y) * gamma; v2 = (v2 + o.z) * gamma; v3 = (v3 + o.w) * gamma;
           }
           *op = make_float4(v0, v1, v2, v3);
@@ -467,10 +475,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // ---- epilogue warp loop of the CTA-pair kernels ------------------------------------------------------------------
 // Measured (tools/probe_layer.sh, profiles/r02_probe_layer_v5.md): with the epilogue reduced to draining TMEM the 1x1
 // residual GEMM still took 134 us of its 159 us - it was bound by the DEPENDENT global loads of its own epilogue operands
-// (one 32 x 32 chunk in flight per warp, issued one chunk ahead).  So the operands of ALL chunks a warp owns in a tile
-// (CPW = BN / 64 chunks: 4 at BN = 256) now live in registers and are fetched ONE TILE AHEAD: right after chunk k of tile i is
-// finished its register set is refilled with chunk k of tile i + 1.  That needs ~200 registers per epilogue thread, which the
-// kernels get with setmaxnreg (producer / MMA / allocator / L2-prefetch warps shrink to 40, the 8 epilogue warps grow to 232).
+// (one 32 x 32 chunk in flight per warp, issued one chunk ahead, and handed over with a register copy `cur = nxt` that
+// stalls on the load it copies).  Now the operands are fetched TWO CHUNKS ahead (across tile boundaries) into two ping-pong register sets.  The epilogue threads get the
+// registers for that with setmaxnreg (producer / MMA / allocator / L2-prefetch warps shrink to 40, the 8 epilogue warps grow to 232).
 struct EpiTile {
   int64_t r0;   // first row of this warp's 32-row slice
   int nrows;    // valid rows in the slice
@@ -487,11 +494,15 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
     else if (t.prob == 0) prefetch_chunk<MODE0>(e0, t.r0, t.nrows, n, lane, dst);
     else prefetch_chunk<MODE1>(e1, t.r0, t.nrows, n, lane, dst);
   };
+  // DEPTH register sets, each owned by fixed chunk positions (no moves of registers with loads in flight - a rotating ring
+  // stalled every chunk on the scoreboard of the load issued one chunk earlier).  Even CPW: two sets in ping-pong, the chunk
+  // loop runs in pairs (lookahead = 2 chunks, crossing into the next tile); odd CPW: one set per chunk, fully unrolled.
+  constexpr int DEPTH = (CPW % 2 == 0) ? 2 : CPW;
   EpiTile cur = tile_at(0);
-  Pre pr[CPW];
+  Pre pr[DEPTH];
   if (cur.ok) {
 #pragma unroll
-    for (int k = 0; k < CPW; ++k) fetch(cur, k, pr[k]);
+    for (int k = 0; k < DEPTH; ++k) fetch(cur, k, pr[k]);
   }
   for (int it = 0; cur.ok; ++it) {
     const int a = it & 1;
@@ -499,18 +510,22 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
     mbar_wait(tfull0 + 8 * a, (uint32_t)((it >> 1) & 1));
     tc_fence_after();
 #pragma unroll 1
-    for (int k = 0; k < CPW; ++k) {
-      uint32_t v[32];
-      const int ch = eg + 2 * k;
-      tmem_ld32(tmem_lanes + (uint32_t)a * acc_stride + (uint32_t)(ch * 32), v);
-      if (cur.nrows > 0 && !(dbg & 1)) {
-        if constexpr (MODE0 == MODE1) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[0]);
-        else if (cur.prob == 0) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[0]);
-        else epilogue_chunk<MODE1>(e1, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[0]);
-      }
+    for (int k0 = 0; k0 < CPW; k0 += DEPTH) {
 #pragma unroll
-      for (int i = 0; i + 1 < CPW; ++i) pr[i] = pr[i + 1];
-      if (nx.ok) fetch(nx, k, pr[CPW - 1]);  // chunk k of the NEXT tile takes the register set that was just consumed
+      for (int j = 0; j < DEPTH; ++j) {
+        uint32_t v[32];
+        const int k = k0 + j;
+        const int ch = eg + 2 * k;
+        tmem_ld32(tmem_lanes + (uint32_t)a * acc_stride + (uint32_t)(ch * 32), v);
+        if (cur.nrows > 0 && !(dbg & 1)) {
+          if constexpr (MODE0 == MODE1) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j]);
+          else if (cur.prob == 0) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j]);
+          else epilogue_chunk<MODE1>(e1, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j]);
+        }
+        // the register set just consumed takes the chunk DEPTH positions later: of this tile, or of the next one
+        if (k + DEPTH < CPW) fetch(cur, k + DEPTH, pr[j]);
+        else if (nx.ok) fetch(nx, k + DEPTH - CPW, pr[j]);
+      }
     }
     tc_fence_before();
     __syncwarp();
@@ -1086,6 +1101,179 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS) : "memory");
   }
 }
+
+// Dual kernel on the tap-reuse rings (Cfg3): the gate tiles load one halo-extended activation tile per K block and address
+// the three taps through row-shifted descriptors (-31 % operand bytes of the gate GEMM, which is bound by L2->SM operand
+// traffic: profiles/r02_probe_layer_v5.md); the 1x1 tiles use the same rings with a single tap (their 144-row box carries
+// 16 unused halo rows).
+template <int HB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
+                       const __grid_constant__ CUtensorMap tmB0_hi, const __grid_constant__ CUtensorMap tmB0_lo,
+                       const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
+                       const __grid_constant__ CUtensorMap tmB1_hi, const __grid_constant__ CUtensorMap tmB1_lo,
+                       const __grid_constant__ TCDual P) {
+  using K = Cfg3<HB>;
+  constexpr int BN = K::BN, AS = K::ASLOTS, BS = K::BSLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float4* xpose = reinterpret_cast<float4*>(smem + K::RING);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::RING + XPOSE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AS + 2 * BS + 4);
+  const uint32_t abase = smem_u32(smem), bbase = abase + AS * K::ASLOT;
+  const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * AS, bfull0 = aempty0 + 8 * AS, bempty0 = bfull0 + 8 * BS;
+  const uint32_t tfull0 = bempty0 + 8 * BS, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int n0 = P.n0, n1 = P.n1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * AS + 2 * BS; ++s) mbar_init(afull0 + 8 * s, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::: "memory");
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t lafull0 = mapa_u32(afull0, 0), lbfull0 = mapa_u32(bfull0, 0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int p, t;
+      for (int i = 0; dual_decode(i, cid, ncl, n0, n1, p, t); ++i) {
+        const int NT = DQ(NT), ntl = DQ(ntiles), kch = DQ(kchunks), taps = DQ(taps), N = DQ(N);
+        const int2* tiles = DQ(tiles);
+        const CUtensorMap* mAh = p ? &tmA1_hi : &tmA0_hi;
+        const CUtensorMap* mAl = p ? &tmA1_lo : &tmA0_lo;
+        const CUtensorMap* mBh = p ? &tmB1_hi : &tmB0_hi;
+        const CUtensorMap* mBl = p ? &tmB1_lo : &tmB0_lo;
+        const int mp = t / NT, nt = t - mp * NT;
+        int mt = 2 * mp + (int)rank;
+        if (mt >= ntl) mt = 2 * mp;
+        const int row0 = tiles[mt].x;
+        for (int kc = 0; kc < kch; ++kc) {
+          mbar_wait(aempty0 + 8 * as, aph ^ 1);
+          if (rank == 0) mbar_expect_tx(afull0 + 8 * as, 2 * K::ASLOT);
+          const uint32_t sa = abase + as * K::ASLOT;
+          tma_load_2d_pair(sa, mAh, lafull0 + 8 * as, kc * BK, row0 - HALO);
+          tma_load_2d_pair(sa + A3_TILE, mAl, lafull0 + 8 * as, kc * BK, row0 - HALO);
+          if (++as == AS) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(bempty0 + 8 * bs, bph ^ 1);
+            if (rank == 0) mbar_expect_tx(bfull0 + 8 * bs, 2 * K::BSLOT);
+            const uint32_t sb = bbase + bs * K::BSLOT;
+            const int brow = tap * N + nt * BN + (int)rank * HB;
+            tma_load_2d_pair(sb, mBh, lbfull0 + 8 * bs, kc * BK, brow);
+            tma_load_2d_pair(sb + K::B_TILE, mBl, lbfull0 + 8 * bs, kc * BK, brow);
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int p, t;
+      for (int it = 0; dual_decode(it, cid, ncl, n0, n1, p, t); ++it) {
+        const int a = it & 1;
+        const int kch = DQ(kchunks), taps = DQ(taps), dil = DQ(dil), center = DQ(center);
+        mbar_wait(tempty0 + 8 * a, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * K::ACC_STRIDE;
+        for (int kc = 0; kc < kch; ++kc) {
+          mbar_wait(afull0 + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t sa = abase + as * K::ASLOT;
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(bfull0 + 8 * bs, bph);
+            tc_fence_after();
+            const uint32_t sh = (uint32_t)(HALO + (tap - center) * dil) * 128u;
+            const uint32_t sb = bbase + bs * K::BSLOT;
+            const uint64_t dah = make_sdesc(sa + sh), dal = make_sdesc(sa + A3_TILE + sh);
+            const uint64_t dbh = make_sdesc(sb), dbl = make_sdesc(sb + K::B_TILE);
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t off = (uint64_t)((ks * 32) >> 4);
+              tc_mma_pair(d_tmem, dah + off, dbh + off, idesc, (kc | tap | ks) != 0 ? 1u : 0u);
+              tc_mma_pair(d_tmem, dah + off, dbl + off, idesc, 1u);
+              tc_mma_pair(d_tmem, dal + off, dbh + off, idesc, 1u);
+            }
+            tc_commit_pair(bempty0 + 8 * bs);
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          tc_commit_pair(aempty0 + 8 * as);
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+        tc_commit_pair(tfull0 + 8 * a);
+      }
+    }
+  } else if (warp == 3) {
+    const uint32_t ltempty0 = mapa_u32(tempty0, 0);
+    auto pf = [&](int i) {
+      int p, t;
+      if (!dual_decode(i, cid, ncl, n0, n1, p, t)) return;
+      const int NT = DQ(NT);
+      const int mp = t / NT, nt = t - mp * NT;
+      const int mt = 2 * mp + (int)rank;
+      if (mt >= DQ(ntiles)) return;
+      if (p == 0) prefetch_tile_l2<EPI_GATE>(P.q[0].e, P.q[0].tiles[mt], nt * BN, BN, lane);
+      else prefetch_tile_l2<EPI_RES_SKIP>(P.q[1].e, P.q[1].tiles[mt], nt * BN, BN, lane);
+    };
+    pf(0);
+    int p, t;
+    for (int it = 0; dual_decode(it, cid, ncl, n0, n1, p, t); ++it) {
+      const int a = it & 1;
+      if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
+      __syncwarp();
+      pf(it + 1);
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
+    const int ew = warp & 3;
+    const int eg = (warp - 4) >> 2;
+    auto tile_at = [&](int it) {
+      EpiTile e;
+      int p, t;
+      e.ok = dual_decode(it, cid, ncl, n0, n1, p, t);
+      if (!e.ok) { e.r0 = 0; e.nrows = 0; e.n0 = 0; e.prob = 0; return e; }
+      e.prob = p;
+      const int NT = DQ(NT);
+      const int mp = t / NT, nt = t - mp * NT;
+      const int mt = 2 * mp + (int)rank;
+      const int2 tl = mt < DQ(ntiles) ? DQ(tiles)[mt] : make_int2(0, 0);
+      e.r0 = (int64_t)tl.x + ew * 32;
+      e.nrows = min(32, max(0, tl.y - ew * 32));
+      e.n0 = nt * BN;
+      return e;
+    };
+    pair_epilogue_loop<BN / 64, EPI_GATE, EPI_RES_SKIP>(P.q[0].e, P.q[1].e, tile_at, xpose + (warp - 4) * 256,
+                                                        tmem_base + ((uint32_t)(ew * 32) << 16), K::ACC_STRIDE, tfull0,
+                                                        mapa_u32(tempty0, 0), eg, lane, 0);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS) : "memory");
+  }
+}
 #undef DQ
 
 __global__ void k_split_planes(const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {
@@ -1492,14 +1680,15 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
 }
 
 namespace {
-template <int HB>
+template <int HB, bool REUSE>
 int launch_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r, int num_sms) {
-  using KCfg = Cfg2<HB>;
+  constexpr int SMEM_BYTES = REUSE ? Cfg3<HB>::SMEM : Cfg2<HB>::SMEM;
   static std::atomic<bool> configured[MAX_DEV];
-  if (configure_once(conv_gemm_tc2d_kernel<HB>, configured, KCfg::SMEM)) return -2;
+  if (REUSE ? configure_once(conv_gemm_tc2dr_kernel<HB>, configured, SMEM_BYTES) : configure_once(conv_gemm_tc2d_kernel<HB>, configured, SMEM_BYTES))
+    return -2;
   static std::atomic<long long>* const counter = [] {
     static char name[48];
-    snprintf(name, sizeof(name), "tc2d<%d,GATE+RES_SKIP>", HB);
+    snprintf(name, sizeof(name), "tc2d<%d,GATE+RES_SKIP>", HB);  // same name with or without tap reuse (SSB_TC_NO_TAP_REUSE)
     return variant_counter(name);
   }();
   const GemmTC* gs[2] = {&g, &r};
@@ -1508,8 +1697,8 @@ int launch_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r, int num_sms) {
   for (int i = 0; i < 2; ++i) {
     const GemmTC& q = *gs[i];
     const ConvTC& w = *q.w;
-    if (cached_act_map(&ta[i][0], q.A_hi, (uint64_t)q.rows_total, (uint64_t)w.Cin, BM)) return -1;
-    if (cached_act_map(&ta[i][1], q.A_lo, (uint64_t)q.rows_total, (uint64_t)w.Cin, BM)) return -1;
+    if (cached_act_map(&ta[i][0], q.A_hi, (uint64_t)q.rows_total, (uint64_t)w.Cin, REUSE ? A3_ROWS : BM)) return -1;
+    if (cached_act_map(&ta[i][1], q.A_lo, (uint64_t)q.rows_total, (uint64_t)w.Cin, REUSE ? A3_ROWS : BM)) return -1;
     TCProb& t = P.q[i];
     t.tiles = q.tiles; t.ntiles = q.ntiles; t.NT = w.N / (2 * HB); t.taps = w.taps; t.kchunks = w.Cin / BK;
     t.dil = w.dil; t.center = w.center; t.N = w.N; t.e = q.e;
@@ -1527,8 +1716,12 @@ int launch_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r, int num_sms) {
       lk.lock();
       pair_guard_begin(dev, ctx.stream);
     }
-    conv_gemm_tc2d_kernel<HB><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
-                                                                         r.w->tm2_hi, r.w->tm2_lo, P);
+    if (REUSE)
+      conv_gemm_tc2dr_kernel<HB><<<2 * ncl, NTHREADS, SMEM_BYTES, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
+                                                                            r.w->tm2_hi, r.w->tm2_lo, P);
+    else
+      conv_gemm_tc2d_kernel<HB><<<2 * ncl, NTHREADS, SMEM_BYTES, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
+                                                                           r.w->tm2_hi, r.w->tm2_lo, P);
     const cudaError_t le = cudaGetLastError();
     if (guard) pair_guard_end(dev, ctx.stream);
     SSB_CUDA(le);
@@ -1571,7 +1764,10 @@ int conv_gemm_tc_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r) {
     if (int rc = conv_gemm_tc(ctx, g)) return rc;
     return conv_gemm_tc(ctx, r);
   }
-  return wg.hb == 128 ? launch_dual<128>(ctx, g, r, num_sms) : launch_dual<96>(ctx, g, r, num_sms);
+  static const bool no_reuse = getenv("SSB_TC_NO_TAP_REUSE") != nullptr;
+  if (!no_reuse && wg.center == 1 && wg.dil >= 1 && wg.dil <= HALO && wr.center == 0)
+    return wg.hb == 128 ? launch_dual<128, true>(ctx, g, r, num_sms) : launch_dual<96, true>(ctx, g, r, num_sms);
+  return wg.hb == 128 ? launch_dual<128, false>(ctx, g, r, num_sms) : launch_dual<96, false>(ctx, g, r, num_sms);
 }
 
 int split_planes(Ctx& ctx, const float* x, int ld, int64_t rows, int C, float scale, __half* hi, __half* lo) {
