@@ -122,7 +122,7 @@ __device__ __forceinline__ void split_store2(__half* hi, __half* lo, float a, fl
 // residual-layer kernels ran at 22 % tensor activity / 43 % of the DRAM bandwidth (profiles/r01_ncu_full_pair_v2_*).
 template <int MODE>
 __device__ __forceinline__ void prefetch_tile_l2(const EpiTC& e, int2 t, int n0, int bn, int lane) {
-  if (e.n_valid > 0 && n0 >= e.n_valid) return;
+  if (!e.l2_prefetch || (e.n_valid > 0 && n0 >= e.n_valid)) return;
   const char* s1 = nullptr;
   const char* s2 = nullptr;
   int64_t st1 = 0, st2 = 0;       // row strides in bytes
@@ -1404,6 +1404,11 @@ std::atomic<long long>* variant_counter(const char* name) {
 }
 const char* mode_name(int mode) { return mode == EPI_GATE ? "GATE" : (mode == EPI_RES_SKIP ? "RES_SKIP" : "GENERIC"); }
 
+bool l2_prefetch_enabled() {
+  static const bool off = getenv("SSB_TC_NO_L2_PREFETCH") != nullptr;
+  return !off;
+}
+
 template <int BN, int MODE>
 int launch_m(Ctx& ctx, const GemmTC& p, const TCParams& tp, int num_sms) {
   using KCfg = Cfg<BN>;
@@ -1645,6 +1650,7 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
     tp.dbg = d ? atoi(d) : 0;
   }
   if (!tp.e.bias) tp.e.bias = w.bias;
+  tp.e.l2_prefetch = l2_prefetch_enabled() ? 1 : 0;
   // large problems: CTA pairs (256 x 2*hb tiles) halve the operand bytes each SM pulls through L2
   const bool pair_off = getenv("SSB_TC_NO_PAIR") != nullptr;
   if (!pair_off && w.hb > 0 && (!p.w2 || p.w2->hb == w.hb) &&
@@ -1703,6 +1709,7 @@ int launch_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r, int num_sms) {
     t.tiles = q.tiles; t.ntiles = q.ntiles; t.NT = w.N / (2 * HB); t.taps = w.taps; t.kchunks = w.Cin / BK;
     t.dil = w.dil; t.center = w.center; t.N = w.N; t.e = q.e;
     if (!t.e.bias) t.e.bias = w.bias;
+    t.e.l2_prefetch = l2_prefetch_enabled() ? 1 : 0;
   }
   P.n0 = ((g.ntiles + 1) / 2) * P.q[0].NT;
   P.n1 = ((r.ntiles + 1) / 2) * P.q[1].NT;

@@ -69,6 +69,7 @@ struct EpiTC {
   float alpha = 1.0f;            // GENERIC: v = act((acc + bias) * alpha)   (ACT_GELU supported here for the FFT FFN)
   const float* rowmask = nullptr;  // GENERIC: v = (v + res) * rowmask[row]
   int n_valid = 0;               // > 0: output columns >= n_valid are padding (weights padded to a tile multiple): skipped
+  int l2_prefetch = 1;           // warp 3 pulls the next tile's epilogue operands into L2 (SSB_TC_NO_L2_PREFETCH=1: off)
   __half* sh = nullptr;          // RES_SKIP (last layer): the finished skip sum also as fp16 planes [rows, C]
   __half* sl = nullptr;
 };
