@@ -61,7 +61,7 @@ struct Pre {
 
 // rows of this warp: r0 + [0, 32); nrows valid ones.  Lane's row in step i: 4i + (lane >> 3); columns n4 .. n4+3.
 template <int MODE>
-__device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int nrows, int n, int lane, Pre& p) {
+__device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int nrows, int n, int lane, Pre& p, int tq) {
   if (e.n_valid > 0 && n >= e.n_valid) return;
   const float* src = nullptr;
   int ld = 0;
@@ -85,8 +85,16 @@ __device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int n
         return;
       }
       src = e.res + n; ld = e.ld_res;
-    } else if (!e.skip_init) { src = e.skip + (n - e.C); ld = e.ld_skip; }
-    else return;
+    } else if (!e.skip_init) {
+      if (e.skip_tiled) {  // chunk (tq, (n - C) / 32) is a contiguous [32 rows][32 cols] block
+        const float* sp = e.skip + ((int64_t)tq * (e.C >> 5) + ((n - e.C) >> 5)) * 1024 + (lane >> 3) * 32 + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (4 * i + (lane >> 3) < nrows) p.a[i] = *reinterpret_cast<const float4*>(sp + i * 128);
+        return;
+      }
+      src = e.skip + (n - e.C); ld = e.ld_skip;
+    } else return;
   } else {  // EPI_GATE: the hoisted conditioner projection of this layer
     if (!e.add) return;
     src = e.add + n; ld = e.ld_add;
@@ -121,7 +129,7 @@ __device__ __forceinline__ void split_store2(__half* hi, __half* lo, float a, fl
 // tile is being finished: the epilogue warps can keep only one chunk of loads in flight each, so with DRAM latency the
 // residual-layer kernels ran at 22 % tensor activity / 43 % of the DRAM bandwidth (profiles/r01_ncu_full_pair_v2_*).
 template <int MODE>
-__device__ __forceinline__ void prefetch_tile_l2(const EpiTC& e, int2 t, int n0, int bn, int lane) {
+__device__ __forceinline__ void prefetch_tile_l2(const EpiTC& e, int2 t, int n0, int bn, int lane, int mt) {
   if (!e.l2_prefetch || (e.n_valid > 0 && n0 >= e.n_valid)) return;
   const char* s1 = nullptr;
   const char* s2 = nullptr;
@@ -139,7 +147,11 @@ __device__ __forceinline__ void prefetch_tile_l2(const EpiTC& e, int2 t, int n0,
         s1 = reinterpret_cast<const char*>(e.res + n0); st1 = 4 * (int64_t)e.ld_res; b1 = (uint32_t)bn * 4u;
       }
     } else if (!e.skip_init) {
-      s1 = reinterpret_cast<const char*>(e.skip + (n0 - e.C)); st1 = 4 * (int64_t)e.ld_skip; b1 = (uint32_t)bn * 4u;
+      if (e.skip_tiled) {  // the tile's accumulator is one contiguous 128 x C block: walk it in C-float pieces
+        s1 = reinterpret_cast<const char*>(e.skip + ((int64_t)(e.tile_base + mt) * TILE_M - t.x) * e.C); st1 = 4 * (int64_t)e.C; b1 = (uint32_t)e.C * 4u;
+      } else {
+        s1 = reinterpret_cast<const char*>(e.skip + (n0 - e.C)); st1 = 4 * (int64_t)e.ld_skip; b1 = (uint32_t)bn * 4u;
+      }
     }
   } else {  // EPI_GATE
     if (e.add) { s1 = reinterpret_cast<const char*>(e.add + n0); st1 = 4 * (int64_t)e.ld_add; b1 = (uint32_t)bn * 4u; }
@@ -161,7 +173,7 @@ __device__ __forceinline__ float act_slope_of(int act, float slope) {  // act(v)
 }
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64_t r0, int nrows, int n, int lane,
-                                               const uint32_t (&raw)[32], const Pre& pre) {
+                                               const uint32_t (&raw)[32], const Pre& pre, int tq) {
   if (e.n_valid > 0 && n >= e.n_valid) return;  // warp-uniform
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -227,8 +239,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
       const int sc = n4 - e.C;
       const bool init = e.skip_init != 0;
       const bool planes = e.sh != nullptr;
-      float* ps = e.skip + rb * e.ld_skip + sc;
-      const int64_t sts = 4 * (int64_t)e.ld_skip, sth = 4 * (int64_t)e.C;
+      float* ps = e.skip_tiled ? e.skip + ((int64_t)tq * (e.C >> 5) + ((n - e.C) >> 5)) * 1024 + rq * 32 + 4 * q
+                               : e.skip + rb * e.ld_skip + sc;
+      const int64_t sts = e.skip_tiled ? 128 : 4 * (int64_t)e.ld_skip, sth = 4 * (int64_t)e.C;
       __half* ph = planes ? e.sh + rb * e.C + sc : nullptr;
       __half* pl = planes ? e.sl + rb * e.C + sc : nullptr;
 #pragma unroll
@@ -255,7 +268,13 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (planes && e.vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
     float* po = has_out ? e.out + rb * e.ldo + n4 : nullptr;
-    const int64_t sto = 4 * (int64_t)e.ldo, sth = 4 * (int64_t)e.ldh;
+    int64_t sto = 4 * (int64_t)e.ldo;
+    const int64_t sth = 4 * (int64_t)e.ldh;
+    if (has_out && e.out_nb > 0) {  // column-block-major output (one [rows, out_nb] matrix per block of columns)
+      const int blk = n4 / e.out_nb;
+      po = e.out + (int64_t)blk * e.out_bs + rb * e.out_nb + (n4 - blk * e.out_nb);
+      sto = 4 * (int64_t)e.out_nb;
+    }
     __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
     __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
     // MRF accumulation reads `out` back: all 8 rows up front (one exposed round trip per chunk instead of one per step - the
@@ -418,7 +437,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   } else if (warp == 3) {
     if ((int)blockIdx.x < total) {
       const int mt = (int)blockIdx.x / p.NT, nt = (int)blockIdx.x - mt * p.NT;
-      prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+      prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane, mt);
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -429,7 +448,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int nx = tile + gridDim.x;
         if (nx < total) {
           const int mt = nx / p.NT, nt = nx - mt * p.NT;
-          prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+          prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane, mt);
         }
       }
       if (lane == 0) mbar_arrive(tempty0 + 8 * a);
@@ -448,15 +467,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const int nrows = min(32, max(0, t.y - ew * 32));
       float4* xb = xpose + (warp - 4) * 256;
       Pre cur, nxt;
-      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + eg * 32, lane, cur);  // issued before the accumulator is ready: overlaps the MMAs
+      prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + eg * 32, lane, cur, (p.e.tile_base + mt) * 4 + ew);  // issued before the accumulator is ready: overlaps the MMAs
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
 #pragma unroll 1
       for (int ch = eg; ch < NCH; ch += 2) {
-        if (ch + 2 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt);
+        if (ch + 2 < NCH) prefetch_chunk<MODE>(p.e, r0, nrows, nt * BN + (ch + 2) * 32, lane, nxt, (p.e.tile_base + mt) * 4 + ew);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BN + ch * 32), v);
-        if (nrows > 0 && !(p.dbg & 1)) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur);
+        if (nrows > 0 && !(p.dbg & 1)) epilogue_chunk<MODE>(p.e, xb, r0, nrows, nt * BN + ch * 32, lane, v, cur, (p.e.tile_base + mt) * 4 + ew);
         cur = nxt;
       }
       tc_fence_before();
@@ -483,6 +502,7 @@ struct EpiTile {
   int nrows;    // valid rows in the slice
   int n0;       // first output column of the tile
   int prob;     // dual kernel: 0 = gate problem, 1 = residual problem
+  int tq;       // tile-quarter index (row tile * 4 + warp quarter): address of the chunk-tiled skip accumulator
   int ok;       // 0: past the last tile
 };
 template <int CPW, int MODE0, int MODE1, typename TileFn>
@@ -490,9 +510,9 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
                                                    uint32_t acc_stride, uint32_t tfull0, uint32_t ltempty0, int eg, int lane, int dbg) {
   auto fetch = [&](const EpiTile& t, int k, Pre& dst) {
     const int n = t.n0 + (eg + 2 * k) * 32;
-    if constexpr (MODE0 == MODE1) prefetch_chunk<MODE0>(e0, t.r0, t.nrows, n, lane, dst);
-    else if (t.prob == 0) prefetch_chunk<MODE0>(e0, t.r0, t.nrows, n, lane, dst);
-    else prefetch_chunk<MODE1>(e1, t.r0, t.nrows, n, lane, dst);
+    if constexpr (MODE0 == MODE1) prefetch_chunk<MODE0>(e0, t.r0, t.nrows, n, lane, dst, t.tq);
+    else if (t.prob == 0) prefetch_chunk<MODE0>(e0, t.r0, t.nrows, n, lane, dst, t.tq);
+    else prefetch_chunk<MODE1>(e1, t.r0, t.nrows, n, lane, dst, t.tq);
   };
   // DEPTH register sets, each owned by fixed chunk positions (no moves of registers with loads in flight - a rotating ring
   // stalled every chunk on the scoreboard of the load issued one chunk earlier).  Even CPW: two sets in ping-pong, the chunk
@@ -518,9 +538,9 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
         const int ch = eg + 2 * k;
         tmem_ld32(tmem_lanes + (uint32_t)a * acc_stride + (uint32_t)(ch * 32), v);
         if (cur.nrows > 0 && !(dbg & 1)) {
-          if constexpr (MODE0 == MODE1) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j]);
-          else if (cur.prob == 0) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j]);
-          else epilogue_chunk<MODE1>(e1, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j]);
+          if constexpr (MODE0 == MODE1) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j], cur.tq);
+          else if (cur.prob == 0) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j], cur.tq);
+          else epilogue_chunk<MODE1>(e1, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j], cur.tq);
         }
         // the register set just consumed takes the chunk DEPTH positions later: of this tile, or of the next one
         if (k + DEPTH < CPW) fetch(cur, k + DEPTH, pr[j]);
@@ -680,7 +700,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     auto pf = [&](int tile) {
       const int mp = tile / p.NT, nt = tile - mp * p.NT;
       const int mt = 2 * mp + (int)rank;
-      if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+      if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane, mt);
     };
     if (cid < total) pf(cid);
     int it = 0;
@@ -701,11 +721,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int tile = cid + it * ncl;
       t.ok = tile < total;
       t.prob = 0;
-      if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; return t; }
+      if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; t.tq = 0; return t; }
       const int mp = tile / p.NT, nt = tile - mp * p.NT;
       const int mt = 2 * mp + (int)rank;
       const int2 tl = mt < p.ntiles ? p.tiles[mt] : make_int2(0, 0);
       t.r0 = (int64_t)tl.x + ew * 32;
+      t.tq = (p.e.tile_base + mt) * 4 + ew;
       t.nrows = min(32, max(0, tl.y - ew * 32));
       t.n0 = nt * BN;
       return t;
@@ -862,7 +883,7 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
     auto pf = [&](int tile) {
       const int mp = tile / p.NT, nt = tile - mp * p.NT;
       const int mt = 2 * mp + (int)rank;
-      if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane);
+      if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane, mt);
     };
     if (cid < total) pf(cid);
     int it = 0;
@@ -883,11 +904,12 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
       const int tile = cid + it * ncl;
       t.ok = tile < total;
       t.prob = 0;
-      if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; return t; }
+      if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; t.tq = 0; return t; }
       const int mp = tile / p.NT, nt = tile - mp * p.NT;
       const int mt = 2 * mp + (int)rank;
       const int2 tl = mt < p.ntiles ? p.tiles[mt] : make_int2(0, 0);
       t.r0 = (int64_t)tl.x + ew * 32;
+      t.tq = (p.e.tile_base + mt) * 4 + ew;
       t.nrows = min(32, max(0, tl.y - ew * 32));
       t.n0 = nt * BN;
       return t;
@@ -1058,8 +1080,8 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
       const int mp = t / NT, nt = t - mp * NT;
       const int mt = 2 * mp + (int)rank;
       if (mt >= DQ(ntiles)) return;
-      if (p == 0) prefetch_tile_l2<EPI_GATE>(P.q[0].e, P.q[0].tiles[mt], nt * BN, BN, lane);
-      else prefetch_tile_l2<EPI_RES_SKIP>(P.q[1].e, P.q[1].tiles[mt], nt * BN, BN, lane);
+      if (p == 0) prefetch_tile_l2<EPI_GATE>(P.q[0].e, P.q[0].tiles[mt], nt * BN, BN, lane, mt);
+      else prefetch_tile_l2<EPI_RES_SKIP>(P.q[1].e, P.q[1].tiles[mt], nt * BN, BN, lane, mt);
     };
     pf(0);
     int p, t;
@@ -1079,13 +1101,14 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
       EpiTile e;
       int p, t;
       e.ok = dual_decode(it, cid, ncl, n0, n1, p, t);
-      if (!e.ok) { e.r0 = 0; e.nrows = 0; e.n0 = 0; e.prob = 0; return e; }
+      if (!e.ok) { e.r0 = 0; e.nrows = 0; e.n0 = 0; e.prob = 0; e.tq = 0; return e; }
       e.prob = p;
       const int NT = DQ(NT);
       const int mp = t / NT, nt = t - mp * NT;
       const int mt = 2 * mp + (int)rank;
       const int2 tl = mt < DQ(ntiles) ? DQ(tiles)[mt] : make_int2(0, 0);
       e.r0 = (int64_t)tl.x + ew * 32;
+      e.tq = (DQ(e.tile_base) + mt) * 4 + ew;
       e.nrows = min(32, max(0, tl.y - ew * 32));
       e.n0 = nt * BN;
       return e;
@@ -1231,8 +1254,8 @@ conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid
       const int mp = t / NT, nt = t - mp * NT;
       const int mt = 2 * mp + (int)rank;
       if (mt >= DQ(ntiles)) return;
-      if (p == 0) prefetch_tile_l2<EPI_GATE>(P.q[0].e, P.q[0].tiles[mt], nt * BN, BN, lane);
-      else prefetch_tile_l2<EPI_RES_SKIP>(P.q[1].e, P.q[1].tiles[mt], nt * BN, BN, lane);
+      if (p == 0) prefetch_tile_l2<EPI_GATE>(P.q[0].e, P.q[0].tiles[mt], nt * BN, BN, lane, mt);
+      else prefetch_tile_l2<EPI_RES_SKIP>(P.q[1].e, P.q[1].tiles[mt], nt * BN, BN, lane, mt);
     };
     pf(0);
     int p, t;
@@ -1252,13 +1275,14 @@ conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid
       EpiTile e;
       int p, t;
       e.ok = dual_decode(it, cid, ncl, n0, n1, p, t);
-      if (!e.ok) { e.r0 = 0; e.nrows = 0; e.n0 = 0; e.prob = 0; return e; }
+      if (!e.ok) { e.r0 = 0; e.nrows = 0; e.n0 = 0; e.prob = 0; e.tq = 0; return e; }
       e.prob = p;
       const int NT = DQ(NT);
       const int mp = t / NT, nt = t - mp * NT;
       const int mt = 2 * mp + (int)rank;
       const int2 tl = mt < DQ(ntiles) ? DQ(tiles)[mt] : make_int2(0, 0);
       e.r0 = (int64_t)tl.x + ew * 32;
+      e.tq = (DQ(e.tile_base) + mt) * 4 + ew;
       e.nrows = min(32, max(0, tl.y - ew * 32));
       e.n0 = nt * BN;
       return e;

@@ -69,6 +69,11 @@ struct EpiTC {
   float alpha = 1.0f;            // GENERIC: v = act((acc + bias) * alpha)   (ACT_GELU supported here for the FFT FFN)
   const float* rowmask = nullptr;  // GENERIC: v = (v + res) * rowmask[row]
   int n_valid = 0;               // > 0: output columns >= n_valid are padding (weights padded to a tile multiple): skipped
+  int skip_tiled = 0;            // RES_SKIP: skip accumulator stored chunk-tiled - [row tile][32-row quarter][32-col chunk][32 rows][32 cols]
+                                 //   fp32, so that every 32 x 32 epilogue chunk is one contiguous 4 KB block (private to this epilogue)
+  int tile_base = 0;             //   index of tiles[0] in the full tile table (a GEMM over a sub-range of the row tiles)
+  int out_nb = 0;                // GENERIC, > 0: `out` is column-block-major: block j = columns [j*out_nb, (j+1)*out_nb) is its own
+  int64_t out_bs = 0;            //   [rows, out_nb] matrix at out + j * out_bs (the hoisted conditioner: one matrix per layer)
   int l2_prefetch = 1;           // warp 3 pulls the next tile's epilogue operands into L2 (SSB_TC_NO_L2_PREFETCH=1: off)
   __half* sh = nullptr;          // RES_SKIP (last layer): the finished skip sum also as fp16 planes [rows, C]
   __half* sl = nullptr;

@@ -450,8 +450,8 @@ static GemmTC layer_gate_gemm(const Denoiser& d, const DenoiserBufs& b, int64_t 
   const int C = d.C, L = d.L;
   GemmTC g;
   g.A_hi = b.yh; g.A_lo = b.yl; g.rows_total = rows; g.w = &d.layers[l].dil_tc; g.tiles = tiles; g.ntiles = ntiles;
-  if (b.condpre) {  // conditioner hoisted: K = 3*C only, the projection arrives as an epilogue addend
-    g.e.add = b.condpre + (size_t)l * 2 * C; g.e.ld_add = L * 2 * C;
+  if (b.condpre) {  // conditioner hoisted: K = 3*C only, the projection arrives as an epilogue addend (one [rows, 2C] matrix per layer)
+    g.e.add = b.condpre + (size_t)l * (size_t)rows * 2 * C; g.e.ld_add = 2 * C;
   } else {
     g.A2_hi = b.ch; g.A2_lo = b.cl; g.w2 = &d.layers[l].cond_tc;  // K = 3*C (taps of y) + 256 (cond)
   }
@@ -460,7 +460,7 @@ static GemmTC layer_gate_gemm(const Denoiser& d, const DenoiserBufs& b, int64_t 
   return g;
 }
 static GemmTC layer_res_gemm(const Denoiser& d, const DenoiserBufs& b, int64_t rows, const int2* tiles, int ntiles, int l,
-                             const float* dt) {
+                             const float* dt, int tile0 = 0 /* index of tiles[0] in the layout's tile table */) {
   const int C = d.C, L = d.L;
   GemmTC g;
   g.A_hi = b.zh; g.A_lo = b.zl; g.rows_total = rows; g.w = &d.layers[l].outp_tc; g.tiles = tiles; g.ntiles = ntiles;
@@ -470,6 +470,7 @@ static GemmTC layer_res_gemm(const Denoiser& d, const DenoiserBufs& b, int64_t r
   g.e.rh = b.yh; g.e.rl = b.yl; g.e.ld_rh = C; g.e.vec1 = dt + (size_t)l * C;
   if (l + 1 < L) { g.e.oh = b.yh; g.e.ol = b.yl; g.e.ldh = C; g.e.vec2 = dt + (size_t)(l + 1) * C; }
   g.e.skip = b.skip; g.e.ld_skip = C; g.e.skip_init = (l == 0);
+  g.e.skip_tiled = b.skip_tiled ? 1 : 0; g.e.tile_base = tile0;
   if (b.tc_heads && l == L - 1) { g.e.sh = b.skh; g.e.sl = b.skl; }
   return g;
 }
@@ -482,6 +483,7 @@ struct Lane {
   const int2* tiles;
   int ntiles;
   int t;
+  int tile0;  // index of tiles[0] in the layout's tile table
 };
 // Residual layers of TWO independent lanes, software-pipelined by half a layer: every launch but the first and the last is
 // the interleaved dual kernel (conv_gemm_tc_dual) working on the gate conv of one lane and the 1x1 residual conv of the
@@ -493,12 +495,12 @@ static int denoiser_layers_dual(Ctx& c, const Lane& A, const Lane& B) {
   RUN(conv_gemm_tc(c, layer_gate_gemm(*A.d, *A.b, A.rows, A.tiles, A.ntiles, 0)));
   for (int l = 0; l < L; ++l) {
     RUN(conv_gemm_tc_dual(c, layer_gate_gemm(*B.d, *B.b, B.rows, B.tiles, B.ntiles, l),
-                          layer_res_gemm(*A.d, *A.b, A.rows, A.tiles, A.ntiles, l, dtA)));
+                          layer_res_gemm(*A.d, *A.b, A.rows, A.tiles, A.ntiles, l, dtA, A.tile0)));
     if (l + 1 < L)
       RUN(conv_gemm_tc_dual(c, layer_gate_gemm(*A.d, *A.b, A.rows, A.tiles, A.ntiles, l + 1),
-                            layer_res_gemm(*B.d, *B.b, B.rows, B.tiles, B.ntiles, l, dtB)));
+                            layer_res_gemm(*B.d, *B.b, B.rows, B.tiles, B.ntiles, l, dtB, B.tile0)));
     else
-      RUN(conv_gemm_tc(c, layer_res_gemm(*B.d, *B.b, B.rows, B.tiles, B.ntiles, l, dtB)));
+      RUN(conv_gemm_tc(c, layer_res_gemm(*B.d, *B.b, B.rows, B.tiles, B.ntiles, l, dtB, B.tile0)));
   }
   return 0;
 }
@@ -548,7 +550,7 @@ int denoiser_stack(Ctx& c, const Denoiser& d, const SeqDev& s, int t, DenoiserBu
   SSB_CHECK(d.dtab != nullptr && t >= 0 && t < d.T, "denoiser: schedule not set (ssb_model_set_schedule) or bad t");
   const float* dt = d.dtab + (size_t)t * L * C;
   if (split > 0 && split < s.ntiles && dual_lane_ok(d, b) && !c.dry) {
-    const Lane A{&d, &b, s.rows, s.tiles, split, t}, B{&d, &b, s.rows, s.tiles + split, s.ntiles - split, t};
+    const Lane A{&d, &b, s.rows, s.tiles, split, t, 0}, B{&d, &b, s.rows, s.tiles + split, s.ntiles - split, t, split};
     RUN(denoiser_layers_dual(c, A, B));
     return denoiser_heads(c, d, s, b);
   }
@@ -619,7 +621,15 @@ int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, Denoiser
     b->zg = alloc_rows(c, s, d.C);
     b->condall = alloc_rows(c, s, d.L * 2 * d.C, false);
   }
-  b->skip = alloc_rows(c, s, d.C);
+  // tensor-core heads: the fp32 skip accumulator is private to the RES_SKIP epilogue (the heads read the planes the last
+  // layer writes), so it is kept chunk-tiled (every 32 x 32 epilogue chunk one contiguous 4 KB block; conv_gemm_tc.cuh)
+  b->skip_tiled = b->tc_heads;
+  if (b->skip_tiled) {
+    const size_t n = (size_t)s.ntiles * TILE_M * d.C;
+    b->skip = c.alloc<float>(n);  // fully written by layer 0 (skip_init) before it is read: no memset
+  } else {
+    b->skip = alloc_rows(c, s, d.C);
+  }
   b->sbuf = b->tc_heads ? nullptr : alloc_rows(c, s, d.C);
   b->ld_head = b->tc_heads ? d.out_tc.N : ((d.out_dims + 3) & ~3);
   b->head = alloc_rows(c, s, b->ld_head);
@@ -635,6 +645,7 @@ int prepare_cond(Ctx& c, const Denoiser& d, const SeqDev& s, const float* cond_g
     GemmTC g;  // all L conditioner projections at once: [rows, 256] x [256, L*2C], once per sampler call
     g.A_hi = b.ch; g.A_lo = b.cl; g.rows_total = s.rows; g.w = &d.cond_all_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
     g.e.mode = EPI_GENERIC; g.e.out = b.condpre; g.e.ldo = d.L * 2 * d.C;
+    g.e.out_nb = 2 * d.C; g.e.out_bs = (int64_t)s.rows * 2 * d.C;  // layer-major: row pitch 2C floats instead of L * 2C
     return conv_gemm_tc(c, g);
   }
   ConvGemm g = make_gemm(d.cond_all, s, cond_g, 256);
@@ -710,6 +721,7 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
     GemmTC g;
     g.A_hi = pl[6]; g.A_lo = pl[7]; g.rows_total = s.rows; g.w = &d.cond_all_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
     g.e.mode = EPI_GENERIC; g.e.out = condpre; g.e.ldo = L * 2 * C;
+    g.e.out_nb = 2 * C; g.e.out_bs = (int64_t)s.rows * 2 * C;
     RUN(conv_gemm_tc(c, g));
   }
   if (!c.dry) {
@@ -746,7 +758,7 @@ static int run_mel_diffusion_persistent(Ctx& c, const Model& m, const SeqDev& s,
         a.a1 = 2; a.a2 = 6; a.w1 = W_L0 + 6 * l; a.w2 = W_L0 + 6 * l + 2; a.taps = 3; a.kchunks = C / 64; a.kchunks2 = 4;
         a.dil = d.layers[l].dil_tc.dil; a.center = 1; a.N = 2 * C; a.NT = 2 * C / 64; a.mode = SP_GATE;
         a.bias = d.layers[l].bias_gate_tc; a.oh = pl[4]; a.ol = pl[5]; a.ldh = C;
-        if (condpre) { a.a2 = -1; a.kchunks2 = 0; a.add = condpre + (size_t)l * 2 * C; a.ld_add = L * 2 * C; }
+        if (condpre) { a.a2 = -1; a.kchunks2 = 0; a.add = condpre + (size_t)l * (size_t)s.rows * 2 * C; a.ld_add = 2 * C; }
         ph[k++] = a;
         SPhase b = z;  // 1x1 output projection -> residual stream, next layer's input planes, skip sum
         b.a1 = 4; b.w1 = W_L0 + 6 * l + 4; b.kchunks = C / 64; b.N = 2 * C; b.NT = 2 * C / 64; b.mode = SP_RES_SKIP;
@@ -953,6 +965,7 @@ int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, co
       GemmTC g;
       g.A_hi = pl[n][4]; g.A_lo = pl[n][5]; g.rows_total = s.rows; g.w = &m.f0net[n].cond_all_tc; g.tiles = s.tiles; g.ntiles = s.ntiles;
       g.e.mode = EPI_GENERIC; g.e.out = condpre[n]; g.e.ldo = L * 2 * C;
+      g.e.out_nb = 2 * C; g.e.out_bs = (int64_t)s.rows * 2 * C;
       RUN(conv_gemm_tc(c, g));
     }
   }
@@ -997,7 +1010,7 @@ int run_f0_diffusion_pair_persistent(Ctx& c, const Model& m, const SeqDev& s, co
           a.a1 = MB + 0; a.a2 = MB + 4; a.w1 = W_L0 + 6 * l; a.w2 = W_L0 + 6 * l + 2; a.taps = 3; a.kchunks = C / 64; a.kchunks2 = 4;
           a.dil = d.layers[l].dil_tc.dil; a.center = 1; a.N = 2 * C; a.NT = 2 * C / 64; a.mode = SP_GATE;
           a.bias = d.layers[l].bias_gate_tc; a.oh = pl[n][2]; a.ol = pl[n][3]; a.ldh = C;
-          if (condpre[n]) { a.a2 = -1; a.kchunks2 = 0; a.add = condpre[n] + (size_t)l * 2 * C; a.ld_add = L * 2 * C; }
+          if (condpre[n]) { a.a2 = -1; a.kchunks2 = 0; a.add = condpre[n] + (size_t)l * (size_t)s.rows * 2 * C; a.ld_add = 2 * C; }
           slot(k++) = a;
           SPhase b = zp;
           b.a1 = MB + 2; b.w1 = W_L0 + 6 * l + 4; b.kchunks = C / 64; b.N = 2 * C; b.NT = 2 * C / 64; b.mode = SP_RES_SKIP;
@@ -1137,7 +1150,7 @@ int run_f0_diffusion_dual(Ctx& c, const Model& m, const SeqDev& s, const float* 
       RUN(ddiff_input(c, s, z[n], uv[n], d.in_w, d.in_b, d.uv_emb, d.dtab + (size_t)t * d.L * d.C, nullptr, b[n].y, d.C, b[n].yh, b[n].yl));
     }
     if (!c.dry) {
-      const Lane A{&m.f0net[0], &b[0], s.rows, s.tiles, s.ntiles, t}, B{&m.f0net[1], &b[1], s.rows, s.tiles, s.ntiles, t};
+      const Lane A{&m.f0net[0], &b[0], s.rows, s.tiles, s.ntiles, t, 0}, B{&m.f0net[1], &b[1], s.rows, s.tiles, s.ntiles, t, 0};
       RUN(denoiser_layers_dual(c, A, B));
     }
     for (int n = 0; n < 2; ++n) {

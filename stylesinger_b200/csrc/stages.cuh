@@ -19,6 +19,7 @@ struct DenoiserBufs {
   __half *skh, *skl, *sh, *sl;  // tensor-core heads: planes of the skip sum and of relu(skip_proj)
   __half *x80h, *x80l;          // mel net, tensor-core in_proj: planes of x_t padded to 128 columns
   bool tc_heads;
+  bool skip_tiled;              // skip accumulator in the chunk-tiled layout (EpiTC::skip_tiled)
   int ld_head;
   bool tc;
 };
