@@ -60,51 +60,47 @@ struct Pre {
 };
 
 // rows of this warp: r0 + [0, 32); nrows valid ones.  Lane's row in step i: 4i + (lane >> 3); columns n4 .. n4+3.
+// Loads are UNCONDITIONAL (rows past the end of an utterance lie inside the guard band / tail slack of every buffer, and
+// their values are never stored) and walk one pointer with a constant step: the first version spent more instructions on
+// per-access 64-bit address arithmetic and row predicates than on the epilogue itself (profiles/r02_epilogue_sass_v9.md).
 template <int MODE>
 __device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int nrows, int n, int lane, Pre& p, int tq) {
+  (void)nrows;
   if (e.n_valid > 0 && n >= e.n_valid) return;
+  const int rq = lane >> 3, q4 = (lane & 7) * 4;
   const float* src = nullptr;
-  int ld = 0;
+  int64_t st = 0;  // floats between consecutive steps (4 rows)
   if constexpr (MODE == EPI_GENERIC) {
     if (!e.res) return;
-    src = e.res + n; ld = e.ld_res;
+    src = e.res + (r0 + rq) * e.ld_res + n + q4; st = 4 * (int64_t)e.ld_res;
   } else if constexpr (MODE == EPI_RES_SKIP) {
     if (n < e.C) {
       if (e.rh) {  // residual stream carried as fp16 hi/lo planes: 4 columns = 8 bytes per plane, packed into one float4
-        const __half* ph = e.rh + n + (lane & 7) * 4;
-        const __half* pl = e.rl + n + (lane & 7) * 4;
+        const __half* ph = e.rh + (r0 + rq) * e.ld_rh + n + q4;
+        const __half* pl = e.rl + (r0 + rq) * e.ld_rh + n + q4;
+        const int64_t sth = 4 * (int64_t)e.ld_rh;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + (lane >> 3);
-          if (rr < nrows) {
-            const uint2 h = *reinterpret_cast<const uint2*>(ph + (r0 + rr) * e.ld_rh);
-            const uint2 l = *reinterpret_cast<const uint2*>(pl + (r0 + rr) * e.ld_rh);
-            p.a[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
-          }
+        for (int i = 0; i < 8; ++i, ph += sth, pl += sth) {
+          const uint2 h = *reinterpret_cast<const uint2*>(ph);
+          const uint2 l = *reinterpret_cast<const uint2*>(pl);
+          p.a[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
         }
         return;
       }
-      src = e.res + n; ld = e.ld_res;
+      src = e.res + (r0 + rq) * e.ld_res + n + q4; st = 4 * (int64_t)e.ld_res;
     } else if (!e.skip_init) {
       if (e.skip_tiled) {  // chunk (tq, (n - C) / 32) is a contiguous [32 rows][32 cols] block
-        const float* sp = e.skip + ((int64_t)tq * (e.C >> 5) + ((n - e.C) >> 5)) * 1024 + (lane >> 3) * 32 + (lane & 7) * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (4 * i + (lane >> 3) < nrows) p.a[i] = *reinterpret_cast<const float4*>(sp + i * 128);
-        return;
+        src = e.skip + ((int64_t)tq * (e.C >> 5) + ((n - e.C) >> 5)) * 1024 + rq * 32 + q4; st = 128;
+      } else {
+        src = e.skip + (r0 + rq) * e.ld_skip + (n - e.C) + q4; st = 4 * (int64_t)e.ld_skip;
       }
-      src = e.skip + (n - e.C); ld = e.ld_skip;
     } else return;
   } else {  // EPI_GATE: the hoisted conditioner projection of this layer
     if (!e.add) return;
-    src = e.add + n; ld = e.ld_add;
+    src = e.add + (r0 + rq) * e.ld_add + n + q4; st = 4 * (int64_t)e.ld_add;
   }
-  src += (lane & 7) * 4;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = 4 * i + (lane >> 3);
-    if (rr < nrows) p.a[i] = *reinterpret_cast<const float4*>(src + (int64_t)(r0 + rr) * ld);
-  }
+  for (int i = 0; i < 8; ++i, src += st) p.a[i] = *reinterpret_cast<const float4*>(src);  // one 64-bit add per step
 }
 
 __device__ __forceinline__ void split_store4(__half* hi, __half* lo, float a, float b, float c, float d) {
@@ -186,54 +182,64 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
   const float4* xr = xb + rq * 8;          // row rq + 4i, chunk q ^ ((rq + 4i) & 7) = (q ^ rq) ^ (4 * (i & 1))
   const int qx = q ^ rq;
   float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-  if (e.bias) { b0 = __ldg(e.bias + n4); b1 = __ldg(e.bias + n4 + 1); b2 = __ldg(e.bias + n4 + 2); b3 = __ldg(e.bias + n4 + 3); }
-  const int nsteps = nrows > rq ? (nrows - rq + 3) >> 2 : 0;  // steps i < nsteps have a valid row
+  if (e.bias) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n4));
+    b0 = bv.x; b1 = bv.y; b2 = bv.z; b3 = bv.w;
+  }
+  // Everything below is computed for all 8 steps; only the STORES are predicated on the row being valid (i < nsteps).
+  const int nsteps = nrows > rq ? (nrows - rq + 3) >> 2 : 0;
   if constexpr (MODE == EPI_GATE) {
     const int64_t st = 4 * (int64_t)e.ldh;
     __half* ph = e.oh + rb * e.ldh + (n4 >> 1);
     __half* pl = e.ol + rb * e.ldh + (n4 >> 1);
     const bool has_add = e.add != nullptr;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < nsteps) {
-        const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
-        float g0 = acc.x + b0, f0 = acc.y + b1, g1 = acc.z + b2, f1 = acc.w + b3;
-        if (has_add) {
-          const float4 ad = pre.a[i];
-          g0 += ad.x; f0 += ad.y; g1 += ad.z; f1 += ad.w;
-        }
-        split_store2(ph + i * st, pl + i * st, gate_act(g0, f0), gate_act(g1, f1));
+    for (int i = 0; i < 8; ++i, ph += st, pl += st) {
+      const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+      float g0 = acc.x + b0, f0 = acc.y + b1, g1 = acc.z + b2, f1 = acc.w + b3;
+      if (has_add) {
+        const float4 ad = pre.a[i];
+        g0 += ad.x; f0 += ad.y; g1 += ad.z; f1 += ad.w;
       }
+      const float z0 = gate_act(g0, f0), z1 = gate_act(g1, f1);
+      if (i < nsteps) split_store2(ph, pl, z0, z1);
     }
   } else if constexpr (MODE == EPI_RES_SKIP) {
     if (n < e.C) {
       const float beta = e.beta;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       const bool planes = e.oh != nullptr;
-      if (planes && e.vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
+      if (planes && e.vec2) {
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(e.vec2 + n4));
+        s0 = sv.x; s1 = sv.y; s2 = sv.z; s3 = sv.w;
+      }
       const bool res_planes = e.rh != nullptr, has_out = e.out != nullptr;
       float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;  // step bias of the current layer: x = (hi + lo) - c
-      if (res_planes && e.vec1) { c0 = __ldg(e.vec1 + n4); c1 = __ldg(e.vec1 + n4 + 1); c2 = __ldg(e.vec1 + n4 + 2); c3 = __ldg(e.vec1 + n4 + 3); }
+      if (res_planes && e.vec1) {
+        const float4 cv = __ldg(reinterpret_cast<const float4*>(e.vec1 + n4));
+        c0 = cv.x; c1 = cv.y; c2 = cv.z; c3 = cv.w;
+      }
       float* po = has_out ? e.out + rb * e.ldo + n4 : nullptr;
       const int64_t sto = 4 * (int64_t)e.ldo, sth = 4 * (int64_t)e.ldh;
       __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
       __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (i < nsteps) {
-          const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
-          float4 x0 = pre.a[i];
-          if (res_planes) {  // (hi0 hi1 | hi2 hi3 | lo0 lo1 | lo2 lo3) as raw half2 bits
-            const uint32_t u0 = __float_as_uint(x0.x), u1 = __float_as_uint(x0.y), u2 = __float_as_uint(x0.z), u3 = __float_as_uint(x0.w);
-            const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&u0)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
-            const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&u2)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&u3));
-            x0 = make_float4((h01.x + l01.x) - c0, (h01.y + l01.y) - c1, (h23.x + l23.x) - c2, (h23.y + l23.y) - c3);
-          }
-          const float v0 = (acc.x + b0 + x0.x) * beta, v1 = (acc.y + b1 + x0.y) * beta;
-          const float v2 = (acc.z + b2 + x0.z) * beta, v3 = (acc.w + b3 + x0.w) * beta;
-          if (has_out) *reinterpret_cast<float4*>(po + i * sto) = make_float4(v0, v1, v2, v3);
-          if (planes) split_store4(ph + i * sth, pl + i * sth, v0 + s0, v1 + s1, v2 + s2, v3 + s3);
+        const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+        float4 x0 = pre.a[i];
+        if (res_planes) {  // (hi0 hi1 | hi2 hi3 | lo0 lo1 | lo2 lo3) as raw half2 bits
+          const uint32_t u0 = __float_as_uint(x0.x), u1 = __float_as_uint(x0.y), u2 = __float_as_uint(x0.z), u3 = __float_as_uint(x0.w);
+          const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&u0)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+          const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&u2)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&u3));
+          x0 = make_float4((h01.x + l01.x) - c0, (h01.y + l01.y) - c1, (h23.x + l23.x) - c2, (h23.y + l23.y) - c3);
         }
+        const float v0 = (acc.x + b0 + x0.x) * beta, v1 = (acc.y + b1 + x0.y) * beta;
+        const float v2 = (acc.z + b2 + x0.z) * beta, v3 = (acc.w + b3 + x0.w) * beta;
+        if (i < nsteps) {
+          if (has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
+          if (planes) split_store4(ph, pl, v0 + s0, v1 + s1, v2 + s2, v3 + s3);
+        }
+        po += sto; ph += sth; pl += sth;
       }
     } else {
       const int sc = n4 - e.C;
@@ -246,16 +252,17 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
       __half* pl = planes ? e.sl + rb * e.C + sc : nullptr;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (i < nsteps) {
-          const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
-          float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
-          if (!init) {
-            const float4 o = pre.a[i];
-            v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
-          }
-          *reinterpret_cast<float4*>(ps + i * sts) = make_float4(v0, v1, v2, v3);
-          if (planes) split_store4(ph + i * sth, pl + i * sth, v0, v1, v2, v3);
+        const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+        float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
+        if (!init) {
+          const float4 o = pre.a[i];
+          v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
         }
+        if (i < nsteps) {
+          *reinterpret_cast<float4*>(ps) = make_float4(v0, v1, v2, v3);
+          if (planes) split_store4(ph, pl, v0, v1, v2, v3);
+        }
+        ps += sts; ph += sth; pl += sth;
       }
     }
   } else {  // EPI_GENERIC: v = act(acc + bias) (+ res); out = accum ? (out + v) * gamma : v; planes = plane_act(v + vec2)
@@ -266,7 +273,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     const bool has_res = e.res != nullptr, has_out = e.out != nullptr, accum = e.accum != 0, planes = e.oh != nullptr;
     const float gamma = e.gamma;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (planes && e.vec2) { s0 = __ldg(e.vec2 + n4); s1 = __ldg(e.vec2 + n4 + 1); s2 = __ldg(e.vec2 + n4 + 2); s3 = __ldg(e.vec2 + n4 + 3); }
+    if (planes && e.vec2) {
+      const float4 sv = __ldg(reinterpret_cast<const float4*>(e.vec2 + n4));
+      s0 = sv.x; s1 = sv.y; s2 = sv.z; s3 = sv.w;
+    }
     float* po = has_out ? e.out + rb * e.ldo + n4 : nullptr;
     int64_t sto = 4 * (int64_t)e.ldo;
     const int64_t sth = 4 * (int64_t)e.ldh;
@@ -281,41 +291,39 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
     // compiler cannot move a load above the previous step's store to the same array)
     float4 oacc[8];
     if (has_out && accum) {
+      const float* pr = po;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nsteps) oacc[i] = *reinterpret_cast<const float4*>(po + i * sto);
+      for (int i = 0; i < 8; ++i, pr += sto) oacc[i] = *reinterpret_cast<const float4*>(pr);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
+      float v0 = (acc.x + b0) * alpha, v1 = (acc.y + b1) * alpha, v2 = (acc.z + b2) * alpha, v3 = (acc.w + b3) * alpha;
+      if (gelu) {
+        v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+      } else {
+        v0 = fmaxf(v0, v0 * sa); v1 = fmaxf(v1, v1 * sa); v2 = fmaxf(v2, v2 * sa); v3 = fmaxf(v3, v3 * sa);
+      }
+      if (has_res) {
+        const float4 x0 = pre.a[i];
+        v0 += x0.x; v1 += x0.y; v2 += x0.z; v3 += x0.w;
+      }
+      if (rmask) {
+        const float mk = rmask[4 * i];
+        v0 *= mk; v1 *= mk; v2 *= mk; v3 *= mk;
+      }
+      if (has_out && accum) {
+        const float4 o = oacc[i];
+        v0 = (v0 + o.x) * gamma; v1 = (v1 + o.y) * gamma; v2 = (v2 + o.z) * gamma; v3 = (v3 + o.w) * gamma;
+      }
       if (i < nsteps) {
-        const float4 acc = xr[i * 32 + (qx ^ (4 * (i & 1)))];
-        float v0 = (acc.x + b0) * alpha, v1 = (acc.y + b1) * alpha, v2 = (acc.z + b2) * alpha, v3 = (acc.w + b3) * alpha;
-        if (gelu) {
-          v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
-        } else {
-          v0 = fmaxf(v0, v0 * sa); v1 = fmaxf(v1, v1 * sa); v2 = fmaxf(v2, v2 * sa); v3 = fmaxf(v3, v3 * sa);
-        }
-        if (has_res) {
-          const float4 x0 = pre.a[i];
-          v0 += x0.x; v1 += x0.y; v2 += x0.z; v3 += x0.w;
-        }
-        if (rmask) {
-          const float mk = rmask[4 * i];
-          v0 *= mk; v1 *= mk; v2 *= mk; v3 *= mk;
-        }
-        if (has_out) {
-          float4* op = reinterpret_cast<float4*>(po + i * sto);
-          if (accum) {
-            const float4 o = oacc[i];
-            v0 = (v0 + o.x) * gamma; v1 = (v1 + o.y) * gamma; v2 = (v2 + o.z) * gamma; v3 = (v3 + o.w) * gamma;
-          }
-          *op = make_float4(v0, v1, v2, v3);
-        }
+        if (has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
         if (planes) {
-          v0 += s0; v1 += s1; v2 += s2; v3 += s3;
-          split_store4(ph + i * sth, pl + i * sth, fmaxf(v0, v0 * sp), fmaxf(v1, v1 * sp), fmaxf(v2, v2 * sp), fmaxf(v3, v3 * sp));
+          const float w0 = v0 + s0, w1 = v1 + s1, w2 = v2 + s2, w3 = v3 + s3;
+          split_store4(ph, pl, fmaxf(w0, w0 * sp), fmaxf(w1, w1 * sp), fmaxf(w2, w2 * sp), fmaxf(w3, w3 * sp));
         }
       }
+      po += sto; ph += sth; pl += sth;
     }
   }
   __syncwarp();  // the next chunk reuses the transpose buffer
