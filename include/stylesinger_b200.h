@@ -31,6 +31,7 @@ extern "C" {
 
 typedef struct ssb_model ssb_model_t;     /* packed StyleSinger acoustic model (immutable after create) */
 typedef struct ssb_vocoder ssb_vocoder_t; /* packed HiFi-GAN(-NSF) generator */
+typedef struct ssb_melspec ssb_melspec_t; /* STFT + mel filterbank of the reference-audio front-end */
 
 /* One named fp32 HOST tensor of a reference state_dict (names exactly as in the reference's
  * checkpoints: utils/commons/ckpt_utils.py:26-67 loads state_dict['model']). */
@@ -244,6 +245,23 @@ int ssb_op_conv1d_tc(const float* x, const int32_t* offsets, int32_t B, int32_t 
  * clips mel [n_frames,80] in place to [vmin, vmax] and counts the frames with sum|mel| > 0 into
  * *nonzero_frames (device int32; the reference drops all-zero frames, which only padding can produce). */
 int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, int32_t* nonzero_frames, void* stream);
+
+/* ---- f3: mel-spectrogram of the reference audio -------------------------------------------------
+ * Replaces utils/audios/__init__.py:36-84 librosa_wav2spec as called by inference/StyleSinger.py:79-92 (process_audio):
+ * librosa.stft(center=True, pad_mode="constant", periodic Hann window) -> |.| -> librosa.filters.mel (Slaney scale and
+ * normalisation, built inside create) -> log10(max(eps, .)).  fmin / fmax < 0 mean 0 / sample_rate / 2 like the reference.
+ * Constraints of the implicit-GEMM formulation: fft_size / 2 a multiple of hop_size, hop_size a multiple of 16, n_mels of 4
+ * (egs/stylesinger.yaml: 48 kHz, fft 1024, hop 256, win 1024, 80 mels, 20..24000 Hz).  An utterance of n samples yields
+ * ssb_melspec_num_frames = 1 + n / hop_size frames.  wav: device fp32, utterances concatenated, sample_offsets: host [B+1];
+ * mel_out: device fp32 [sum frames, n_mels].  loud_norm / trim_long_sil of the reference are not implemented (both false in
+ * the reference's configuration); the speaker / emotion encoders and the Praat pitch tracker are outside this library. */
+int ssb_melspec_create(ssb_melspec_t** out, int32_t sample_rate, int32_t fft_size, int32_t hop_size, int32_t win_length,
+                       int32_t n_mels, float fmin, float fmax, float eps);
+void ssb_melspec_free(ssb_melspec_t* m);
+int32_t ssb_melspec_num_frames(const ssb_melspec_t* m, int64_t n_samples);
+size_t ssb_melspec_workspace_bytes(const ssb_melspec_t* m, const int32_t* sample_offsets, int32_t B);
+int ssb_melspec_forward(const ssb_melspec_t* m, const float* wav, const int32_t* sample_offsets, int32_t B, float* mel_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels this library has launched in this process so far (bench.py reports the delta). */
 int64_t ssb_launch_count(void);

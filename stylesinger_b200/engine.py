@@ -468,6 +468,53 @@ class Vocoder:
 
 
 # unit-test granularity ops -------------------------------------------------------------------------
+class MelSpectrogram:
+    """log10-mel front-end of the reference audio (ssb_melspec_t): librosa_wav2spec of the reference
+    (utils/audios/__init__.py:36-84) with the hparams of egs/stylesinger.yaml by default."""
+
+    def __init__(self, hp=None, device=None, eps=1e-6):
+        _require_cuda()
+        h = dict(audio_sample_rate=48000, fft_size=1024, hop_size=256, win_size=1024, audio_num_mel_bins=80, fmin=20, fmax=24000)
+        h.update({k: v for k, v in (hp or {}).items() if k in h})
+        self.hp = h
+        self.device = torch.device(device if device is not None else "cuda:0")
+        torch.cuda.set_device(self.device)
+        handle = C.c_void_p()
+        check(lib.ssb_melspec_create(C.byref(handle), h["audio_sample_rate"], h["fft_size"], h["hop_size"], h["win_size"],
+                                     h["audio_num_mel_bins"], float(h["fmin"]), float(h["fmax"]), float(eps)), "ssb_melspec_create")
+        self._h = handle
+        self._ws = _Workspace(self.device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.ssb_melspec_free(h)
+            self._h = None
+
+    def num_frames(self, n_samples):
+        return int(lib.ssb_melspec_num_frames(self._h, int(n_samples)))
+
+    def __call__(self, wavs):
+        """wavs: list of 1-D float32 arrays / tensors (or one).  Returns a list of device tensors [frames, n_mels]."""
+        single = not isinstance(wavs, (list, tuple))
+        wavs = [wavs] if single else list(wavs)
+        ts = [torch.as_tensor(np.asarray(w, dtype=np.float32) if not isinstance(w, torch.Tensor) else w, dtype=torch.float32).reshape(-1)
+              for w in wavs]
+        offs = np.concatenate([[0], np.cumsum([t.numel() for t in ts])]).astype(np.int32)
+        wav = torch.cat(ts).to(self.device).contiguous() if ts else torch.zeros(0, device=self.device)
+        frames = [self.num_frames(t.numel()) for t in ts]
+        out = torch.empty(sum(frames), self.hp["audio_num_mel_bins"], dtype=torch.float32, device=self.device)
+        n = lib.ssb_melspec_workspace_bytes(self._h, offs.ctypes.data, len(ts))
+        if n == 0:
+            check(-1, "ssb_melspec_workspace_bytes")
+        ws = self._ws.get(n)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib.ssb_melspec_forward(self._h, _ptr(wav), offs.ctypes.data, len(ts), _ptr(out), _ptr(ws), ws.numel(), stream),
+              "ssb_melspec_forward")
+        mels = list(torch.split(out, frames))
+        return mels[0] if single else mels
+
+
 def op_conv1d(x, offsets, w, b, dilation=1, act=0):
     _require_cuda()
     off = np.ascontiguousarray(offsets, np.int32)

@@ -55,6 +55,24 @@ class StyleSingerInfer:
         self._pinned[i] = (t, weakref.ref(arr.base if arr.base is not None else arr))
         return arr
 
+    # ---- reference-audio front-end (f3, mel half) -----------------------------------------------------
+    def process_audio(self, wav):
+        """reference inference/StyleSinger.py:79-92 for a waveform ARRAY already at ``audio_sample_rate`` (decoding and
+        resampling a file is librosa's job in the reference and stays outside this package): returns ``(wav, mel)`` with the
+        waveform zero-padded / cut to ``len(mel) * hop_size`` samples as float16 and the log10-mel [T, 80] as float32 numpy,
+        computed by the CUDA front-end (ssb_melspec_forward)."""
+        from .engine import MelSpectrogram
+        if isinstance(wav, str):
+            raise NotImplementedError("pass the decoded waveform (float array at hparams['audio_sample_rate'])")
+        if getattr(self, "_melspec", None) is None:
+            self._melspec = MelSpectrogram(self.hparams, self.device)
+        wav = np.asarray(wav, dtype=np.float32).reshape(-1)
+        mel = self._to_host(self._melspec(wav))
+        n = mel.shape[0] * int(self.hparams.get("hop_size", 256))  # utils/audios/__init__.py:71-73 (librosa_pad_lr, then cut)
+        out = np.zeros(n, np.float32)
+        out[:min(n, len(wav))] = wav[:n]
+        return out.astype(np.float16), mel
+
     # ---- reference-compatible single-utterance path ------------------------------------------------
     def input_to_batch(self, item) -> PackedBatch:
         """reference inference/StyleSinger.py:139-170 (B=1 assembly).  ``item['f0']`` is the raw extractor output in Hz

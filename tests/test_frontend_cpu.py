@@ -1,0 +1,49 @@
+"""f3 front-end oracle (oracle/frontend_oracle.py) against what can be checked without librosa: scipy's STFT and the defining
+properties of the Slaney mel filterbank."""
+import numpy as np
+import scipy.signal
+
+from oracle import frontend_oracle as FO
+
+
+def test_stft_matches_scipy():
+    rng = np.random.default_rng(0)
+    for n in (48000, 12345, 1024):  # (scipy refuses signals shorter than the window; librosa pads them)
+        y = rng.standard_normal(n).astype(np.float32)
+        S = FO.stft(y, 1024, 256, 1024)
+        assert S.shape == (513, 1 + n // 256)
+        w = FO.hann_periodic(1024)
+        _, _, Z = scipy.signal.stft(y.astype(np.float64), window=w, nperseg=1024, noverlap=768, nfft=1024, boundary="zeros",
+                                    padded=False, return_onesided=True)
+        Z = Z * w.sum()  # scipy scales by 1 / sum(window)
+        T = min(Z.shape[1], S.shape[1])  # scipy drops the last partial hop
+        assert T >= S.shape[1] - 1
+        scale = np.abs(Z[:, :T]).max()
+        assert np.abs(Z[:, :T] - S[:, :T]).max() < 2e-6 * scale
+
+
+def test_mel_basis_is_the_slaney_construction():
+    sr, n_fft, n_mels, fmin, fmax = 48000, 1024, 80, 20, 24000
+    B = FO.mel_basis(sr, n_fft, n_mels, fmin, fmax)
+    assert B.shape == (80, 513) and B.dtype == np.float32 and (B >= 0).all()
+    edges = FO.mel_to_hz(np.linspace(FO.hz_to_mel(fmin), FO.hz_to_mel(fmax), n_mels + 2))
+    assert abs(edges[0] - fmin) < 1e-9 and abs(edges[-1] - fmax) < 1e-6
+    assert abs(float(FO.hz_to_mel(1000.0)) - 15.0) < 1e-12            # Slaney: 1 kHz = 15 mel, linear below
+    assert abs(float(FO.hz_to_mel(6400.0)) - 42.0) < 1e-9             # 27 log-spaced steps up to 6.4 kHz
+    freqs = np.linspace(0, sr / 2, 513)
+    enorm = 2.0 / (edges[2:] - edges[:-2])
+    tri = B / enorm[:, None]                                          # un-normalised triangles
+    for i in (0, 17, 40, 79):
+        inside = (freqs > edges[i]) & (freqs < edges[i + 2])
+        assert (tri[i][~inside] == 0).all() and tri[i].max() <= 1.0 + 1e-6
+        peak = freqs[np.argmax(tri[i])]
+        assert abs(peak - edges[i + 1]) <= sr / n_fft                 # apex at the centre frequency (to one bin)
+    # neighbouring triangles sum to one between the first and the last centre frequency
+    mid = (freqs >= edges[1]) & (freqs <= edges[-2])
+    assert np.abs(tri.sum(0)[mid] - 1.0).max() < 1e-5
+
+
+def test_wav2mel_shape_and_floor():
+    y = np.zeros(5000, np.float32)
+    m = FO.wav2mel(y)
+    assert m.shape == (1 + 5000 // 256, 80) and np.allclose(m, -6.0)  # log10(eps)
