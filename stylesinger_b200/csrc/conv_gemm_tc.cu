@@ -459,7 +459,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane, mt);
         }
       }
-      if (lane == 0) mbar_arrive(tempty0 + 8 * a);
+      if (lane == 0) mbar_arrive_relaxed(tempty0 + 8 * a);
     }
   } else if (warp >= 4) {
     const int ew = warp & 3;          // TMEM lanes [32*ew, 32*ew + 32)
@@ -488,7 +488,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * a);
+      if (lane == 0) mbar_arrive_relaxed(tempty0 + 8 * a);
     }
   }
   tc_fence_before();
@@ -537,14 +537,20 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
     const EpiTile nx = tile_at(it + 1);
     mbar_wait(tfull0 + 8 * a, (uint32_t)((it >> 1) & 1));
     tc_fence_after();
+    // the accumulator chunks are pipelined as well: the tcgen05.ld of chunk k + 1 is in flight while chunk k is processed
+    // (ncu: the epilogue warps of the residual GEMM spent 9 % of their samples waiting on LDTM)
+    const uint32_t tacc = tmem_lanes + (uint32_t)a * acc_stride + (uint32_t)(eg * 32);
+    uint32_t vv[2][32];
+    tmem_ld32_issue(tacc, vv[0]);
 #pragma unroll 1
     for (int k0 = 0; k0 < CPW; k0 += DEPTH) {
 #pragma unroll
       for (int j = 0; j < DEPTH; ++j) {
-        uint32_t v[32];
+        uint32_t (&v)[32] = vv[j & 1];  // DEPTH is 1, 2 or 3: chunk k lives in buffer k & 1 for every k0 (k0 even or DEPTH == CPW)
         const int k = k0 + j;
         const int ch = eg + 2 * k;
-        tmem_ld32(tmem_lanes + (uint32_t)a * acc_stride + (uint32_t)(ch * 32), v);
+        tmem_ld_wait32(v);
+        if (k + 1 < CPW) tmem_ld32_issue(tacc + (uint32_t)((k + 1) * 64), vv[(j + 1) & 1]);
         if (cur.nrows > 0 && !(dbg & 1)) {
           if constexpr (MODE0 == MODE1) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j], cur.tq);
           else if (cur.prob == 0) epilogue_chunk<MODE0>(e0, xb, cur.r0, cur.nrows, cur.n0 + ch * 32, lane, v, pr[j], cur.tq);
@@ -557,7 +563,7 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+    if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     cur = nx;
   }
 }
@@ -717,7 +723,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
       __syncwarp();
       if (tile + ncl < total) pf(tile + ncl);
-      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+      if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     }
   }
   } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
@@ -900,7 +906,7 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
       if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
       __syncwarp();
       if (tile + ncl < total) pf(tile + ncl);
-      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+      if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     }
   }
   } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
@@ -1098,7 +1104,7 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
       if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
       __syncwarp();
       pf(it + 1);
-      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+      if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     }
   }
   } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
@@ -1272,7 +1278,7 @@ conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid
       if (lane == 0) mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
       __syncwarp();
       pf(it + 1);
-      if (lane == 0) mbar_arrive_cluster(ltempty0 + 8 * a);
+      if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     }
   }
   } else {

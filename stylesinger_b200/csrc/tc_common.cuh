@@ -81,6 +81,16 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
+// "Accumulator drained" signal of the epilogue warps: RELAXED.  By the time it is sent the warp's tcgen05.ld have completed
+// (tcgen05.wait::ld), which is all the MMA issuer needs; the default release semantics made every epilogue warp wait, once
+// per tile, until ALL its global stores of that tile had drained (ncu: 0.92 membar stalls per issued instruction in the
+// residual GEMM, profiles/r02_ncu_nodual_v11.md) although nobody synchronises on those stores inside the kernel.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // MMA completion -> the barrier at this smem offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -130,6 +140,30 @@ __device__ __forceinline__ float gate_act(float g, float f) {
   const float e2f = ex2_approx(f * 2.8853900817779268f);
   const float eg = ex2_approx(g * -1.4426950408889634f);
   return __fdividef(e2f - 1.0f, (e2f + 1.0f) * (1.0f + eg));
+}
+
+// Split form of tmem_ld32 for software pipelining: issue the load of the NEXT chunk, work on the current one, then wait.
+// The wait names the destination registers as in/out operands so that the compiler cannot move a use above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* z) {
