@@ -499,6 +499,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 }
 
+// tile (= cid + it * ncl) -> (row-tile pair, N tile).  With NT == 2 and an even cluster count the plain mapping
+// (mp = tile / 2, nt = tile % 2) hands every cluster tiles of ONE nt only; in the residual GEMM nt = 0 is the residual half
+// (planes in, planes out: the expensive epilogue) and nt = 1 the skip half, so half of the clusters did all the expensive
+// tiles and set the kernel's time (154 us measured whatever was optimised inside the epilogue).  Here the two tiles of a row
+// pair still go to neighbouring clusters, but which one gets which alternates with the iteration.
+__device__ __forceinline__ void pair_tile_decode(int tile, int cid, int ncl, int NT, int& mp, int& nt) {
+  if (NT == 2) {
+    const int it = (tile - cid) / ncl;
+    mp = tile >> 1;
+    nt = (ncl & 1) ? (tile & 1) : ((it + cid) & 1);
+  } else {
+    mp = tile / NT;
+    nt = tile - mp * NT;
+  }
+}
+
 // ---- epilogue warp loop of the CTA-pair kernels ------------------------------------------------------------------
 // Measured (tools/probe_layer.sh, profiles/r02_probe_layer_v5.md): with the epilogue reduced to draining TMEM the 1x1
 // residual GEMM still took 134 us of its 159 us - it was bound by the DEPENDENT global loads of its own epilogue operands
@@ -641,7 +657,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cid; tile < total; tile += ncl) {
-        const int mp = tile / p.NT, nt = tile - mp * p.NT;
+        int mp, nt;
+      pair_tile_decode(tile, cid, ncl, p.NT, mp, nt);
         int mt = 2 * mp + (int)rank;
         if (mt >= p.ntiles) mt = 2 * mp;  // odd tile count: the peer duplicates the leader's rows, writes nothing
         const int row0 = p.tiles[mt].x;
@@ -712,7 +729,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   } else if (warp == 3) {
     const uint32_t ltempty0 = mapa_u32(tempty0, 0);
     auto pf = [&](int tile) {
-      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      int mp, nt;
+      pair_tile_decode(tile, cid, ncl, p.NT, mp, nt);
       const int mt = 2 * mp + (int)rank;
       if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane, mt);
     };
@@ -736,7 +754,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       t.ok = tile < total;
       t.prob = 0;
       if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; t.tq = 0; return t; }
-      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      int mp, nt;
+      pair_tile_decode(tile, cid, ncl, p.NT, mp, nt);
       const int mt = 2 * mp + (int)rank;
       const int2 tl = mt < p.ntiles ? p.tiles[mt] : make_int2(0, 0);
       t.r0 = (int64_t)tl.x + ew * 32;
@@ -832,7 +851,8 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int tile = cid; tile < total; tile += ncl) {
-        const int mp = tile / p.NT, nt = tile - mp * p.NT;
+        int mp, nt;
+      pair_tile_decode(tile, cid, ncl, p.NT, mp, nt);
         int mt = 2 * mp + (int)rank;
         if (mt >= p.ntiles) mt = 2 * mp;
         const int row0 = p.tiles[mt].x;
@@ -895,7 +915,8 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
   } else if (warp == 3) {
     const uint32_t ltempty0 = mapa_u32(tempty0, 0);
     auto pf = [&](int tile) {
-      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      int mp, nt;
+      pair_tile_decode(tile, cid, ncl, p.NT, mp, nt);
       const int mt = 2 * mp + (int)rank;
       if (mt < p.ntiles) prefetch_tile_l2<MODE>(p.e, p.tiles[mt], nt * BN, BN, lane, mt);
     };
@@ -919,7 +940,8 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
       t.ok = tile < total;
       t.prob = 0;
       if (!t.ok) { t.r0 = 0; t.nrows = 0; t.n0 = 0; t.tq = 0; return t; }
-      const int mp = tile / p.NT, nt = tile - mp * p.NT;
+      int mp, nt;
+      pair_tile_decode(tile, cid, ncl, p.NT, mp, nt);
       const int mt = 2 * mp + (int)rank;
       const int2 tl = mt < p.ntiles ? p.tiles[mt] : make_int2(0, 0);
       t.r0 = (int64_t)tl.x + ew * 32;
