@@ -322,9 +322,9 @@ def run_b200(args, rank, world, local_rank):
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops"], "traffic": (traffic or {}).get("bytes_per_launch"),
             "traffic_detail": traffic, "peak_source": pk["src"] + " (cuBLAS bf16, sustained)",
-            "kernel": "conv_gemm_tc2dr_kernel<128> (tcgen05 cta_group::2, gate conv of one utterance group interleaved with the 1x1 "
-                      "residual conv of the other; mel denoiser stage: %d launches per sampler call, of which %d interleaved layer launches)"
-                      % (n_mel, T * (2 * hp["residual_layers"] - 1)),
+            "kernel": "conv_gemm_tc2r_kernel<128, GATE> (tcgen05 cta_group::2, tap reuse; 90.6 %% tensor pipe active under ncu) + "
+                      "conv_gemm_tc2_kernel<128, RES_SKIP>; mel denoiser stage: %d launches per sampler call, of which %d residual-layer GEMMs"
+                      % (n_mel, 2 * T * hp["residual_layers"]),
             "avg_launch_us": 1000.0 * ms_mel / max(n_mel, 1), "stage_ms": ms_mel,
             "note": "useful FLOPs (26.43 MFLOP per frame-step, SURVEY 8d) over the CUDA-event time of the mel-diffusion stage; "
                     "the step-invariant conditioner projection is hoisted out of the T loop (executed_tflops counts what the tensor "

@@ -275,11 +275,12 @@ int64_t ssb_variant_launch_count(const char* variant);
 int32_t ssb_variant_names(char* buf, int32_t cap);
 void ssb_tensor_map_cache_stats(int64_t* encodes, int64_t* hits);
 
-/* Process-wide switch (default 1) of the interleaved residual-layer schedule of the large-batch samplers: the gate conv of
+/* Process-wide switch (default 0) of the interleaved residual-layer schedule of the large-batch samplers: the gate conv of
  * one group of utterances (or of one F0 net) and the 1x1 residual/skip conv of the other group share one launch and
  * alternate tile by tile inside every SM (kernel variant "tc2d<HB,GATE+RES_SKIP>"; reference loop net.py:66-78 inside
- * shallow_diffusion_tts.py:303-304 / gaussian_multinomial_diffusion.py:928-939).  0 restores one launch per GEMM.
- * Results are identical either way (same kernels' arithmetic); tests use it for A/B checks.  Returns the new state. */
+ * shallow_diffusion_tts.py:303-304 / gaussian_multinomial_diffusion.py:928-939).  Results agree with one launch per GEMM to
+ * fp32 rounding (tests/test_gpu_scale.py); measured 3 % slower than it on B200, hence opt-in.
+ * Returns the new state. */
 int32_t ssb_set_interleaved_layers(int32_t enable);
 
 /* Process-wide switch of the tcgen05 / TMA attention kernel (csrc/attention_tc.cu) for the long-batch paths of the FFT blocks

@@ -1803,7 +1803,11 @@ static std::atomic<int> g_dual_on{-1};  // -1: not decided yet (environment), 0 
 bool dual_enabled() {
   int v = g_dual_on.load(std::memory_order_relaxed);
   if (v < 0) {
-    v = getenv("SSB_TC_NO_DUAL") ? 0 : 1;
+    // Off by default: once the residual GEMM's tile assignment was balanced (pair_tile_decode) one launch per GEMM measured
+    // 3 % faster than the interleaved schedule on the same box (profiles/r02_stage_times_batch64_v13_*.json): the 8 epilogue
+    // warps are the shared resource of both tile kinds, so the overlap the schedule was built for does not materialise.
+    const char* e = getenv("SSB_TC_DUAL");
+    v = e && atoi(e) != 0 && !getenv("SSB_TC_NO_DUAL") ? 1 : 0;
     g_dual_on.store(v, std::memory_order_relaxed);
   }
   return v != 0;

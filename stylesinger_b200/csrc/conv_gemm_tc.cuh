@@ -98,10 +98,10 @@ int make_weight_maps(ConvTC* w);
 int make_act_map(CUtensorMap* m, const void* ptr, int64_t rows, int cols, int box_rows = 128);
 int conv_gemm_tc(Ctx& ctx, const GemmTC& p);
 // One launch for two INDEPENDENT problems, interleaved tile by tile: g = a 3-tap gate conv (EPI_GATE), r = a 1x1 residual conv
-// (EPI_RES_SKIP).  Falls back to two launches when the shapes do not qualify.  SSB_TC_NO_DUAL=1 disables it.
+// (EPI_RES_SKIP).  Falls back to two launches when the shapes do not qualify.  Opt-in: ssb_set_interleaved_layers(1) / SSB_TC_DUAL=1.
 int conv_gemm_tc_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r);
 bool dual_enabled();
-int set_dual_enabled(int on);  // process-wide switch (default on; SSB_TC_NO_DUAL=1 starts with it off)
+int set_dual_enabled(int on);  // process-wide switch (default off; SSB_TC_DUAL=1 starts with it on)
 // diagnostics: launches of one kernel variant ("tc2<128,GATE>", "tc<64,GENERIC>", ...), the variants seen so far,
 // and the activation-descriptor cache counters
 long long variant_launch_count(const char* name);
