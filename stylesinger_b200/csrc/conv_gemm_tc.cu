@@ -103,6 +103,22 @@ __device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int n
   for (int i = 0; i < 8; ++i, src += st) p.a[i] = *reinterpret_cast<const float4*>(src);  // one 64-bit add per step
 }
 
+// hi/lo split of 4 (2) values as packed words - computed OUTSIDE the row predicate so that a chunk's 8 steps stay one basic
+// block (only the store instructions are predicated) and the scheduler can interleave the steps' dependent chains
+__device__ __forceinline__ void split_pack4(float a, float b, float c, float d, uint2& uh, uint2& ul) {
+  const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(a - f0.x, b - f0.y), l1 = __floats2half2_rn(c - f1.x, d - f1.y);
+  uh.x = *reinterpret_cast<const uint32_t*>(&h0); uh.y = *reinterpret_cast<const uint32_t*>(&h1);
+  ul.x = *reinterpret_cast<const uint32_t*>(&l0); ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& uh, uint32_t& ul) {
+  const __half2 h0 = __floats2half2_rn(a, b);
+  const float2 f0 = __half22float2(h0);
+  const __half2 l0 = __floats2half2_rn(a - f0.x, b - f0.y);
+  uh = *reinterpret_cast<const uint32_t*>(&h0);
+  ul = *reinterpret_cast<const uint32_t*>(&l0);
+}
 __device__ __forceinline__ void split_store4(__half* hi, __half* lo, float a, float b, float c, float d) {
   const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
   const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
@@ -201,8 +217,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
         const float4 ad = pre.a[i];
         g0 += ad.x; f0 += ad.y; g1 += ad.z; f1 += ad.w;
       }
-      const float z0 = gate_act(g0, f0), z1 = gate_act(g1, f1);
-      if (i < nsteps) split_store2(ph, pl, z0, z1);
+      uint32_t zh, zl;
+      split_pack2(gate_act(g0, f0), gate_act(g1, f1), zh, zl);
+      if (i < nsteps) {
+        *reinterpret_cast<uint32_t*>(ph) = zh;
+        *reinterpret_cast<uint32_t*>(pl) = zl;
+      }
     }
   } else if constexpr (MODE == EPI_RES_SKIP) {
     if (n < e.C) {
@@ -235,9 +255,13 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
         }
         const float v0 = (acc.x + b0 + x0.x) * beta, v1 = (acc.y + b1 + x0.y) * beta;
         const float v2 = (acc.z + b2 + x0.z) * beta, v3 = (acc.w + b3 + x0.w) * beta;
-        if (i < nsteps) {
-          if (has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
-          if (planes) split_store4(ph, pl, v0 + s0, v1 + s1, v2 + s2, v3 + s3);
+        uint2 yh, yl;
+        split_pack4(v0 + s0, v1 + s1, v2 + s2, v3 + s3, yh, yl);
+        const bool ok = i < nsteps;
+        if (ok && has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
+        if (ok && planes) {
+          *reinterpret_cast<uint2*>(ph) = yh;
+          *reinterpret_cast<uint2*>(pl) = yl;
         }
         po += sto; ph += sth; pl += sth;
       }
@@ -258,9 +282,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
           const float4 o = pre.a[i];
           v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
         }
-        if (i < nsteps) {
-          *reinterpret_cast<float4*>(ps) = make_float4(v0, v1, v2, v3);
-          if (planes) split_store4(ph, pl, v0, v1, v2, v3);
+        const bool ok = i < nsteps;
+        if (ok) *reinterpret_cast<float4*>(ps) = make_float4(v0, v1, v2, v3);
+        if (planes) {  // last layer only
+          uint2 kh, kl;
+          split_pack4(v0, v1, v2, v3, kh, kl);
+          if (ok) {
+            *reinterpret_cast<uint2*>(ph) = kh;
+            *reinterpret_cast<uint2*>(pl) = kl;
+          }
         }
         ps += sts; ph += sth; pl += sth;
       }
@@ -316,11 +346,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
         const float4 o = oacc[i];
         v0 = (v0 + o.x) * gamma; v1 = (v1 + o.y) * gamma; v2 = (v2 + o.z) * gamma; v3 = (v3 + o.w) * gamma;
       }
-      if (i < nsteps) {
-        if (has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
-        if (planes) {
-          const float w0 = v0 + s0, w1 = v1 + s1, w2 = v2 + s2, w3 = v3 + s3;
-          split_store4(ph, pl, fmaxf(w0, w0 * sp), fmaxf(w1, w1 * sp), fmaxf(w2, w2 * sp), fmaxf(w3, w3 * sp));
+      const bool ok = i < nsteps;
+      if (ok && has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
+      if (planes) {
+        const float w0 = v0 + s0, w1 = v1 + s1, w2 = v2 + s2, w3 = v3 + s3;
+        uint2 qh, ql;
+        split_pack4(fmaxf(w0, w0 * sp), fmaxf(w1, w1 * sp), fmaxf(w2, w2 * sp), fmaxf(w3, w3 * sp), qh, ql);
+        if (ok) {
+          *reinterpret_cast<uint2*>(ph) = qh;
+          *reinterpret_cast<uint2*>(pl) = ql;
         }
       }
       po += sto; ph += sth; pl += sth;
