@@ -624,8 +624,7 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
 // 4.4 us of MMAs of a residual tile and almost the 13 us of a gate tile.  Sixteen epilogue warps (four per scheduler) halve
 // that: every warp owns one TMEM lane quarter (warp % 4) and one quarter of the tile's columns, and works through them in half
 // chunks of 16 columns (16 accumulator registers, 4 float4 of epilogue operands, a 2 KB transpose buffer) so that the whole
-// state fits the 104 registers setmaxnreg can give 512 epilogue threads (the CTA owns 640 x 96 registers from launch:
-// 128 x 40 + 512 x 104 uses them up; asking for more than the CTA owns blocks the last warpgroup forever).  Step i of 4 handles rows 8i + lane/4, columns
+// state fits the 112 registers setmaxnreg can give 512 epilogue threads.  Step i of 4 handles rows 8i + lane/4, columns
 // 4 (lane % 4) .. +3: every warp access covers 8 rows x 64 bytes.
 constexpr int PEW = 16;                    // epilogue warps of the pair kernels
 constexpr int PNT = 128 + 32 * PEW;        // 640 threads
@@ -1058,7 +1057,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
   }
   } else {  // warps 4-19: the four epilogue warpgroups take the registers the others released
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
     const int ew = warp & 3;
     const int cg = (warp - 4) >> 2;  // column group of this warp
     auto tile_at = [&](int it) {
@@ -1244,7 +1243,7 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
     }
   }
   } else {  // warps 4-19: the four epilogue warpgroups take the registers the others released
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
     const int ew = warp & 3;
     const int cg = (warp - 4) >> 2;  // column group of this warp
     auto tile_at = [&](int it) {
@@ -1443,7 +1442,7 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
     }
   }
   } else {  // warps 4-19: the four epilogue warpgroups take the registers the others released
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
     const int ew = warp & 3;
     const int cg = (warp - 4) >> 2;  // column group of this warp
     auto tile_at = [&](int it) {
@@ -1617,7 +1616,7 @@ conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
     const int ew = warp & 3;
     const int cg = (warp - 4) >> 2;  // column group of this warp
     auto tile_at = [&](int it) {
