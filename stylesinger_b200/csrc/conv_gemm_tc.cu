@@ -618,284 +618,6 @@ __device__ __forceinline__ void pair_epilogue_loop(const EpiTC& e0, const EpiTC&
   }
 }
 
-// ---- 16-warp epilogue of the CTA-pair kernels (half chunks of 32 rows x 16 columns) --------------------------------------
-// Both layer GEMMs of a denoiser need ~11 us of epilogue-warp time per 128 x 256 tile with 8 epilogue warps (two per
-// scheduler, dependent-latency bound at ~0.15 IPC each: profiles/r02_epilogue_sass_v9.md, r02_probe_layer_v5.md) - more than the
-// 4.4 us of MMAs of a residual tile and almost the 13 us of a gate tile.  Sixteen epilogue warps (four per scheduler) halve
-// that: every warp owns one TMEM lane quarter (warp % 4) and one quarter of the tile's columns, and works through them in half
-// chunks of 16 columns (16 accumulator registers, 4 float4 of epilogue operands, a 2 KB transpose buffer) so that the whole
-// state fits the 112 registers setmaxnreg can give 512 epilogue threads.  Step i of 4 handles rows 8i + lane/4, columns
-// 4 (lane % 4) .. +3: every warp access covers 8 rows x 64 bytes.
-constexpr int PEW = 16;                    // epilogue warps of the pair kernels
-constexpr int PNT = 128 + 32 * PEW;        // 640 threads
-static_assert(PEW * 32 * 16 * 4 == XPOSE_BYTES, "transpose buffers: one [32 x 16] fp32 per warp");
-
-struct Pre4 {
-  float4 a[4];
-};
-
-template <int MODE>
-__device__ __forceinline__ void prefetch_hc(const EpiTC& e, int64_t r0, int n, int lane, Pre4& p) {
-  if (e.n_valid > 0 && n >= e.n_valid) return;
-  const int rq = lane >> 2, q4 = (lane & 3) * 4;
-  const float* src = nullptr;
-  int64_t st = 0;  // floats between consecutive steps (8 rows)
-  if constexpr (MODE == EPI_GENERIC) {
-    if (!e.res) return;
-    src = e.res + (r0 + rq) * e.ld_res + n + q4; st = 8 * (int64_t)e.ld_res;
-  } else if constexpr (MODE == EPI_RES_SKIP) {
-    if (n < e.C) {
-      if (e.rh) {
-        const __half* ph = e.rh + (r0 + rq) * e.ld_rh + n + q4;
-        const __half* pl = e.rl + (r0 + rq) * e.ld_rh + n + q4;
-        const int64_t sth = 8 * (int64_t)e.ld_rh;
-#pragma unroll
-        for (int i = 0; i < 4; ++i, ph += sth, pl += sth) {
-          const uint2 h = *reinterpret_cast<const uint2*>(ph);
-          const uint2 l = *reinterpret_cast<const uint2*>(pl);
-          p.a[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
-        }
-        return;
-      }
-      src = e.res + (r0 + rq) * e.ld_res + n + q4; st = 8 * (int64_t)e.ld_res;
-    } else if (!e.skip_init) {
-      src = e.skip + (r0 + rq) * e.ld_skip + (n - e.C) + q4; st = 8 * (int64_t)e.ld_skip;
-    } else return;
-  } else {
-    if (!e.add) return;
-    src = e.add + (r0 + rq) * e.ld_add + n + q4; st = 8 * (int64_t)e.ld_add;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i, src += st) p.a[i] = *reinterpret_cast<const float4*>(src);
-}
-
-template <int MODE>
-__device__ __forceinline__ void epilogue_hc(const EpiTC& e, float4* xb, int64_t r0, int nrows, int n, int lane,
-                                            const uint32_t (&raw)[16], const Pre4& pre) {
-  if (e.n_valid > 0 && n >= e.n_valid) return;  // warp-uniform
-  {
-    const int sw = (lane >> 1) & 3;  // row `lane`, 16-byte chunk c at c ^ ((row / 2) % 4): conflict-free for both accesses
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      xb[lane * 4 + (c ^ sw)] = make_float4(__uint_as_float(raw[4 * c]), __uint_as_float(raw[4 * c + 1]),
-                                            __uint_as_float(raw[4 * c + 2]), __uint_as_float(raw[4 * c + 3]));
-  }
-  __syncwarp();
-  const int q = lane & 3, rq = lane >> 2;  // step i: row rq + 8i, columns n4 .. n4 + 3
-  const int n4 = n + 4 * q;
-  const int64_t rb = r0 + rq;
-  const float4* xr = xb + rq * 4 + (q ^ ((rq >> 1) & 3));  // + 32 i  (((rq + 8i) / 2) % 4 does not depend on i)
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-  if (e.bias) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n4));
-    b0 = bv.x; b1 = bv.y; b2 = bv.z; b3 = bv.w;
-  }
-  const int nsteps = nrows > rq ? (nrows - rq + 7) >> 3 : 0;  // steps with a valid row; only the stores are predicated
-  if constexpr (MODE == EPI_GATE) {
-    const int64_t st = 8 * (int64_t)e.ldh;
-    __half* ph = e.oh + rb * e.ldh + (n4 >> 1);
-    __half* pl = e.ol + rb * e.ldh + (n4 >> 1);
-    const bool has_add = e.add != nullptr;
-#pragma unroll
-    for (int i = 0; i < 4; ++i, ph += st, pl += st) {
-      const float4 acc = xr[i * 32];
-      float g0 = acc.x + b0, f0 = acc.y + b1, g1 = acc.z + b2, f1 = acc.w + b3;
-      if (has_add) {
-        const float4 ad = pre.a[i];
-        g0 += ad.x; f0 += ad.y; g1 += ad.z; f1 += ad.w;
-      }
-      uint32_t zh, zl;
-      split_pack2(gate_act(g0, f0), gate_act(g1, f1), zh, zl);
-      if (i < nsteps) {
-        *reinterpret_cast<uint32_t*>(ph) = zh;
-        *reinterpret_cast<uint32_t*>(pl) = zl;
-      }
-    }
-  } else if constexpr (MODE == EPI_RES_SKIP) {
-    if (n < e.C) {
-      const float beta = e.beta;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      const bool planes = e.oh != nullptr;
-      if (planes && e.vec2) {
-        const float4 sv = __ldg(reinterpret_cast<const float4*>(e.vec2 + n4));
-        s0 = sv.x; s1 = sv.y; s2 = sv.z; s3 = sv.w;
-      }
-      const bool res_planes = e.rh != nullptr, has_out = e.out != nullptr;
-      float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-      if (res_planes && e.vec1) {
-        const float4 cv = __ldg(reinterpret_cast<const float4*>(e.vec1 + n4));
-        c0 = cv.x; c1 = cv.y; c2 = cv.z; c3 = cv.w;
-      }
-      float* po = has_out ? e.out + rb * e.ldo + n4 : nullptr;
-      const int64_t sto = 8 * (int64_t)e.ldo, sth = 8 * (int64_t)e.ldh;
-      __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
-      __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 acc = xr[i * 32];
-        float4 x0 = pre.a[i];
-        if (res_planes) {
-          const uint32_t u0 = __float_as_uint(x0.x), u1 = __float_as_uint(x0.y), u2 = __float_as_uint(x0.z), u3 = __float_as_uint(x0.w);
-          const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&u0)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
-          const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&u2)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&u3));
-          x0 = make_float4((h01.x + l01.x) - c0, (h01.y + l01.y) - c1, (h23.x + l23.x) - c2, (h23.y + l23.y) - c3);
-        }
-        const float v0 = (acc.x + b0 + x0.x) * beta, v1 = (acc.y + b1 + x0.y) * beta;
-        const float v2 = (acc.z + b2 + x0.z) * beta, v3 = (acc.w + b3 + x0.w) * beta;
-        uint2 yh, yl;
-        split_pack4(v0 + s0, v1 + s1, v2 + s2, v3 + s3, yh, yl);
-        const bool ok = i < nsteps;
-        if (ok && has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
-        if (ok && planes) {
-          *reinterpret_cast<uint2*>(ph) = yh;
-          *reinterpret_cast<uint2*>(pl) = yl;
-        }
-        po += sto; ph += sth; pl += sth;
-      }
-    } else {
-      const int sc = n4 - e.C;
-      const bool init = e.skip_init != 0;
-      const bool planes = e.sh != nullptr;
-      float* ps = e.skip + rb * e.ld_skip + sc;
-      const int64_t sts = 8 * (int64_t)e.ld_skip, sth = 8 * (int64_t)e.C;
-      __half* ph = planes ? e.sh + rb * e.C + sc : nullptr;
-      __half* pl = planes ? e.sl + rb * e.C + sc : nullptr;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 acc = xr[i * 32];
-        float v0 = acc.x + b0, v1 = acc.y + b1, v2 = acc.z + b2, v3 = acc.w + b3;
-        if (!init) {
-          const float4 o = pre.a[i];
-          v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
-        }
-        const bool ok = i < nsteps;
-        if (ok) *reinterpret_cast<float4*>(ps) = make_float4(v0, v1, v2, v3);
-        if (planes) {
-          uint2 kh, kl;
-          split_pack4(v0, v1, v2, v3, kh, kl);
-          if (ok) {
-            *reinterpret_cast<uint2*>(ph) = kh;
-            *reinterpret_cast<uint2*>(pl) = kl;
-          }
-        }
-        ps += sts; ph += sth; pl += sth;
-      }
-    }
-  } else {  // EPI_GENERIC
-    const float sa = act_slope_of(e.act, e.act_slope), sp = act_slope_of(e.plane_act, e.plane_slope);
-    const bool gelu = e.act == ACT_GELU;
-    const float alpha = e.alpha;
-    const float* rmask = e.rowmask ? e.rowmask + rb : nullptr;
-    const bool has_res = e.res != nullptr, has_out = e.out != nullptr, accum = e.accum != 0, planes = e.oh != nullptr;
-    const float gamma = e.gamma;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (planes && e.vec2) {
-      const float4 sv = __ldg(reinterpret_cast<const float4*>(e.vec2 + n4));
-      s0 = sv.x; s1 = sv.y; s2 = sv.z; s3 = sv.w;
-    }
-    float* po = has_out ? e.out + rb * e.ldo + n4 : nullptr;
-    int64_t sto = 8 * (int64_t)e.ldo;
-    const int64_t sth = 8 * (int64_t)e.ldh;
-    if (has_out && e.out_nb > 0) {
-      const int blk = n4 / e.out_nb;
-      po = e.out + (int64_t)blk * e.out_bs + rb * e.out_nb + (n4 - blk * e.out_nb);
-      sto = 8 * (int64_t)e.out_nb;
-    }
-    __half* ph = planes ? e.oh + rb * e.ldh + n4 : nullptr;
-    __half* pl = planes ? e.ol + rb * e.ldh + n4 : nullptr;
-    float4 oacc[4];
-    if (has_out && accum) {
-      const float* pr = po;
-#pragma unroll
-      for (int i = 0; i < 4; ++i, pr += sto) oacc[i] = *reinterpret_cast<const float4*>(pr);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 acc = xr[i * 32];
-      float v0 = (acc.x + b0) * alpha, v1 = (acc.y + b1) * alpha, v2 = (acc.z + b2) * alpha, v3 = (acc.w + b3) * alpha;
-      if (gelu) {
-        v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
-      } else {
-        v0 = fmaxf(v0, v0 * sa); v1 = fmaxf(v1, v1 * sa); v2 = fmaxf(v2, v2 * sa); v3 = fmaxf(v3, v3 * sa);
-      }
-      if (has_res) {
-        const float4 x0 = pre.a[i];
-        v0 += x0.x; v1 += x0.y; v2 += x0.z; v3 += x0.w;
-      }
-      if (rmask) {
-        const float mk = rmask[8 * i];
-        v0 *= mk; v1 *= mk; v2 *= mk; v3 *= mk;
-      }
-      if (has_out && accum) {
-        const float4 o = oacc[i];
-        v0 = (v0 + o.x) * gamma; v1 = (v1 + o.y) * gamma; v2 = (v2 + o.z) * gamma; v3 = (v3 + o.w) * gamma;
-      }
-      const bool ok = i < nsteps;
-      if (ok && has_out) *reinterpret_cast<float4*>(po) = make_float4(v0, v1, v2, v3);
-      if (planes) {
-        const float w0 = v0 + s0, w1 = v1 + s1, w2 = v2 + s2, w3 = v3 + s3;
-        uint2 qh, ql;
-        split_pack4(fmaxf(w0, w0 * sp), fmaxf(w1, w1 * sp), fmaxf(w2, w2 * sp), fmaxf(w3, w3 * sp), qh, ql);
-        if (ok) {
-          *reinterpret_cast<uint2*>(ph) = qh;
-          *reinterpret_cast<uint2*>(pl) = ql;
-        }
-      }
-      po += sto; ph += sth; pl += sth;
-    }
-  }
-  __syncwarp();
-}
-
-// Epilogue loop of one of the 16 epilogue warps: lane quarter ew = warp % 4 (in tile_at), column group cg = (warp - 4) / 4,
-// HPW = BN / 64 half chunks per tile; operands two half chunks ahead in ping-pong register sets (across tiles).
-template <int HPW, int MODE0, int MODE1, typename TileFn>
-__device__ __forceinline__ void pair_epilogue_loop16(const EpiTC& e0, const EpiTC& e1, TileFn tile_at, float4* xb, uint32_t tmem_lanes,
-                                                     uint32_t acc_stride, uint32_t tfull0, uint32_t ltempty0, int cg, int lane, int dbg) {
-  auto fetch = [&](const EpiTile& t, int k, Pre4& dst) {
-    const int n = t.n0 + (cg * HPW + k) * 16;
-    if constexpr (MODE0 == MODE1) prefetch_hc<MODE0>(e0, t.r0, n, lane, dst);
-    else if (t.prob == 0) prefetch_hc<MODE0>(e0, t.r0, n, lane, dst);
-    else prefetch_hc<MODE1>(e1, t.r0, n, lane, dst);
-  };
-  constexpr int DEPTH = (HPW % 2 == 0) ? 2 : HPW;
-  EpiTile cur = tile_at(0);
-  Pre4 pr[DEPTH];
-  if (cur.ok) {
-#pragma unroll
-    for (int k = 0; k < DEPTH; ++k) fetch(cur, k, pr[k]);
-  }
-  for (int it = 0; cur.ok; ++it) {
-    const int a = it & 1;
-    const EpiTile nx = tile_at(it + 1);
-    mbar_wait(tfull0 + 8 * a, (uint32_t)((it >> 1) & 1));
-    tc_fence_after();
-    const uint32_t tacc = tmem_lanes + (uint32_t)a * acc_stride + (uint32_t)(cg * HPW * 16);
-#pragma unroll 1
-    for (int k0 = 0; k0 < HPW; k0 += DEPTH) {
-#pragma unroll
-      for (int j = 0; j < DEPTH; ++j) {
-        uint32_t v[16];
-        const int k = k0 + j;
-        const int n = cur.n0 + (cg * HPW + k) * 16;
-        tmem_ld16_issue(tacc + (uint32_t)(k * 16), v);  // (pipelining the TMEM load measured nothing and costs 16 registers)
-        tmem_ld_wait16(v);
-        if (cur.nrows > 0 && !(dbg & 1)) {
-          if constexpr (MODE0 == MODE1) epilogue_hc<MODE0>(e0, xb, cur.r0, cur.nrows, n, lane, v, pr[j]);
-          else if (cur.prob == 0) epilogue_hc<MODE0>(e0, xb, cur.r0, cur.nrows, n, lane, v, pr[j]);
-          else epilogue_hc<MODE1>(e1, xb, cur.r0, cur.nrows, n, lane, v, pr[j]);
-        }
-        if (k + DEPTH < HPW) fetch(cur, k + DEPTH, pr[j]);
-        else if (nx.ok) fetch(nx, k + DEPTH - HPW, pr[j]);
-      }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
-    cur = nx;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x (2*HB) tile.  Each CTA stages its own
 // 128 rows of A (its own row tile of the ragged layout: the two row tiles of a pair need not be adjacent) and HB of
@@ -916,7 +638,7 @@ struct Cfg2 {
 };
 
 template <int HB, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PNT, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                      const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
@@ -943,7 +665,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 2 * PEW + 2);  // + the two L2 prefetch warps
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);  // + the two L2 prefetch warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1056,10 +778,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     }
   }
-  } else {  // warps 4-19: the four epilogue warpgroups take the registers the others released
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
+  } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
     const int ew = warp & 3;
-    const int cg = (warp - 4) >> 2;  // column group of this warp
+    const int eg = (warp - 4) >> 2;
     auto tile_at = [&](int it) {
       EpiTile t;
       const int tile = cid + it * ncl;
@@ -1076,8 +798,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       t.n0 = nt * BN;
       return t;
     };
-    pair_epilogue_loop16<BN / 64, MODE, MODE>(p.e, p.e, tile_at, xpose + (warp - 4) * 128, tmem_base + ((uint32_t)(ew * 32) << 16),
-                                            K::ACC_STRIDE, tfull0, mapa_u32(tempty0, 0), cg, lane, p.dbg);
+    pair_epilogue_loop<BN / 64, MODE, MODE>(p.e, p.e, tile_at, xpose + (warp - 4) * 256, tmem_base + ((uint32_t)(ew * 32) << 16),
+                                            K::ACC_STRIDE, tfull0, mapa_u32(tempty0, 0), eg, lane, p.dbg);
   }
   tc_fence_before();
   cluster_sync_all();  // neither CTA may exit (or free TMEM) while its pair still reads / signals it
@@ -1116,7 +838,7 @@ struct Cfg3 {
 };
 
 template <int HB, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PNT, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TCParams p) {
   using K = Cfg3<HB>;
@@ -1138,7 +860,7 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
     for (int s = 0; s < 2 * AS + 2 * BS; ++s) mbar_init(afull0 + 8 * s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 2 * PEW + 2);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1242,10 +964,10 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
       if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     }
   }
-  } else {  // warps 4-19: the four epilogue warpgroups take the registers the others released
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
+  } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
     const int ew = warp & 3;
-    const int cg = (warp - 4) >> 2;  // column group of this warp
+    const int eg = (warp - 4) >> 2;
     auto tile_at = [&](int it) {
       EpiTile t;
       const int tile = cid + it * ncl;
@@ -1262,8 +984,8 @@ conv_gemm_tc2r_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_c
       t.n0 = nt * BN;
       return t;
     };
-    pair_epilogue_loop16<BN / 64, MODE, MODE>(p.e, p.e, tile_at, xpose + (warp - 4) * 128, tmem_base + ((uint32_t)(ew * 32) << 16),
-                                            K::ACC_STRIDE, tfull0, mapa_u32(tempty0, 0), cg, lane, 0);
+    pair_epilogue_loop<BN / 64, MODE, MODE>(p.e, p.e, tile_at, xpose + (warp - 4) * 256, tmem_base + ((uint32_t)(ew * 32) << 16),
+                                            K::ACC_STRIDE, tfull0, mapa_u32(tempty0, 0), eg, lane, 0);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1309,7 +1031,7 @@ __device__ __forceinline__ bool dual_decode(int i, int cid, int ncl, int n0, int
 #define DQ(field) (p ? P.q[1].field : P.q[0].field)
 
 template <int HB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PNT, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
                       const __grid_constant__ CUtensorMap tmB0_hi, const __grid_constant__ CUtensorMap tmB0_lo,
                       const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
@@ -1337,7 +1059,7 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 2 * PEW + 2);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1441,10 +1163,10 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
       if (lane == 0) mbar_arrive_cluster_relaxed(ltempty0 + 8 * a);
     }
   }
-  } else {  // warps 4-19: the four epilogue warpgroups take the registers the others released
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
+  } else {  // warps 4-11: the epilogue warpgroups take the registers the others released
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
     const int ew = warp & 3;
-    const int cg = (warp - 4) >> 2;  // column group of this warp
+    const int eg = (warp - 4) >> 2;
     auto tile_at = [&](int it) {
       EpiTile e;
       int p, t;
@@ -1461,9 +1183,9 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
       e.n0 = nt * BN;
       return e;
     };
-    pair_epilogue_loop16<BN / 64, EPI_GATE, EPI_RES_SKIP>(P.q[0].e, P.q[1].e, tile_at, xpose + (warp - 4) * 128,
+    pair_epilogue_loop<BN / 64, EPI_GATE, EPI_RES_SKIP>(P.q[0].e, P.q[1].e, tile_at, xpose + (warp - 4) * 256,
                                                         tmem_base + ((uint32_t)(ew * 32) << 16), K::ACC_STRIDE, tfull0,
-                                                        mapa_u32(tempty0, 0), cg, lane, 0);
+                                                        mapa_u32(tempty0, 0), eg, lane, 0);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1478,7 +1200,7 @@ conv_gemm_tc2d_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_
 // traffic: profiles/r02_probe_layer_v5.md); the 1x1 tiles use the same rings with a single tap (their 144-row box carries
 // 16 unused halo rows).
 template <int HB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PNT, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
                        const __grid_constant__ CUtensorMap tmB0_hi, const __grid_constant__ CUtensorMap tmB0_lo,
                        const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
@@ -1503,7 +1225,7 @@ conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid
     for (int s = 0; s < 2 * AS + 2 * BS; ++s) mbar_init(afull0 + 8 * s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 2 * PEW + 2);
+      mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS + 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1616,9 +1338,9 @@ conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory");
     const int ew = warp & 3;
-    const int cg = (warp - 4) >> 2;  // column group of this warp
+    const int eg = (warp - 4) >> 2;
     auto tile_at = [&](int it) {
       EpiTile e;
       int p, t;
@@ -1635,9 +1357,9 @@ conv_gemm_tc2dr_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid
       e.n0 = nt * BN;
       return e;
     };
-    pair_epilogue_loop16<BN / 64, EPI_GATE, EPI_RES_SKIP>(P.q[0].e, P.q[1].e, tile_at, xpose + (warp - 4) * 128,
+    pair_epilogue_loop<BN / 64, EPI_GATE, EPI_RES_SKIP>(P.q[0].e, P.q[1].e, tile_at, xpose + (warp - 4) * 256,
                                                         tmem_base + ((uint32_t)(ew * 32) << 16), K::ACC_STRIDE, tfull0,
-                                                        mapa_u32(tempty0, 0), cg, lane, 0);
+                                                        mapa_u32(tempty0, 0), eg, lane, 0);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1883,7 +1605,7 @@ int launch_pair_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
       lk.lock();
       pair_guard_begin(dev, ctx.stream);
     }
-    conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, PNT, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
+    conv_gemm_tc2_kernel<HB, MODE><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, ta2_hi, ta2_lo,
                                                                              w2.tm2_hi, w2.tm2_lo, tp);
     const cudaError_t le = cudaGetLastError();
     if (guard) pair_guard_end(dev, ctx.stream);
@@ -1918,7 +1640,7 @@ int launch_pair_reuse_m(Ctx& ctx, const GemmTC& p, TCParams tp, int num_sms) {
       lk.lock();
       pair_guard_begin(dev, ctx.stream);
     }
-    conv_gemm_tc2r_kernel<HB, MODE><<<2 * ncl, PNT, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, tp);
+    conv_gemm_tc2r_kernel<HB, MODE><<<2 * ncl, NTHREADS, KCfg::SMEM, ctx.stream>>>(ta_hi, ta_lo, w.tm2_hi, w.tm2_lo, tp);
     const cudaError_t le = cudaGetLastError();
     if (guard) pair_guard_end(dev, ctx.stream);
     SSB_CUDA(le);
@@ -2096,10 +1818,10 @@ int launch_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r, int num_sms) {
       pair_guard_begin(dev, ctx.stream);
     }
     if (REUSE)
-      conv_gemm_tc2dr_kernel<HB><<<2 * ncl, PNT, SMEM_BYTES, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
+      conv_gemm_tc2dr_kernel<HB><<<2 * ncl, NTHREADS, SMEM_BYTES, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
                                                                             r.w->tm2_hi, r.w->tm2_lo, P);
     else
-      conv_gemm_tc2d_kernel<HB><<<2 * ncl, PNT, SMEM_BYTES, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
+      conv_gemm_tc2d_kernel<HB><<<2 * ncl, NTHREADS, SMEM_BYTES, ctx.stream>>>(ta[0][0], ta[0][1], g.w->tm2_hi, g.w->tm2_lo, ta[1][0], ta[1][1],
                                                                            r.w->tm2_hi, r.w->tm2_lo, P);
     const cudaError_t le = cudaGetLastError();
     if (guard) pair_guard_end(dev, ctx.stream);

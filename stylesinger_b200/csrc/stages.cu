@@ -624,9 +624,7 @@ int alloc_denoiser(Ctx& c, const Denoiser& d, const SeqDev& s, bool tc, Denoiser
   // tensor-core heads: the fp32 skip accumulator is private to the RES_SKIP epilogue (the heads read the planes the last
   // layer writes), so it is kept chunk-tiled (every 32 x 32 epilogue chunk one contiguous 4 KB block; conv_gemm_tc.cuh)
   static const bool skip_rowmajor = getenv("SSB_SKIP_ROWMAJOR") != nullptr;  // A/B switch for the layout experiment
-  // (the chunk-tiled layout measured within 1 % of row-major - profiles/r02_probe_layer_v5.md - and the 16-warp epilogue of the
-  //  pair kernels only implements row-major: kept behind the switch for the single-CTA kernels' A/B only)
-  b->skip_tiled = false && b->tc_heads && !skip_rowmajor;
+  b->skip_tiled = b->tc_heads && !skip_rowmajor;
   if (b->skip_tiled) {
     const size_t n = (size_t)s.ntiles * TILE_M * d.C;
     b->skip = c.alloc<float>(n);  // fully written by layer 0 (skip_init) before it is read: no memset
