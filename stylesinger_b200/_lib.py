@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstylesinger_b200.so")
+# SSB_LIB_PATH: another build of the same library (A/B runs of two code states on one GPU box; must export the same symbols)
+LIB_PATH = os.environ.get("SSB_LIB_PATH") or os.path.join(_HERE, "libstylesinger_b200.so")
 
 
 class SsbError(RuntimeError):
