@@ -274,3 +274,38 @@ def test_forward_attention_tensor_cores_match_fp32_kernel():
         sc = float(out[False][k].abs().max())
         print(f"{k}: attention tcgen05 vs fp32 kernel max |diff| {e:.3e} (max |value| {sc:.2f})")
         assert torch.isfinite(out[True][k]).all() and e < 1e-4 * max(1.0, sc), k
+
+
+def test_two_model_handles_on_two_streams_match_sequential():
+    """Two model handles driving CTA-pair (cluster) GEMMs from two torch streams at once (the configuration that hung the GPU
+    in round 1; the library orders pair-kernel launches of different streams on the device, conv_gemm_tc.cu pair guard):
+    both streams must drain and reproduce the sequential results bit for bit.  (With the guard lifted,
+    SSB_TC_PAIR_CONCURRENT=1, tools/repro_two_stream_hang.py ran 100 iterations x 2 streams without a hang on the round-2
+    kernels; the guard stays on because it costs nothing at sizes where pair kernels are used.)"""
+    from stylesinger_b200.engine import AcousticModel
+    from stylesinger_b200._lib import variant_launches
+    T = 6
+    lens = [2900, 1700, 2999, 800, 2300, 1950, 2450, 3000, 1300, 1111]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n = int(offs[-1])
+    g = torch.Generator().manual_seed(21)
+    cond = torch.randn(n, 256, generator=g).to(DEV)
+    lo, hi = torch.full((n,), -1.0, device=DEV), torch.full((n,), 1.0, device=DEV)
+    models = [AcousticModel(acoustic_sd(), hp_for(4, T)) for _ in range(2)]
+    seq = [m.f0_diffusion(i, cond, lo, hi, offs, seed=30 + i) for i, m in enumerate(models)]
+    seq = [(z.clone(), uv.clone()) for z, uv in seq]
+    torch.cuda.synchronize()
+    before = variant_launches()
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(2)]
+    outs = [None, None]
+    for rep in range(3):
+        for i, (m, st) in enumerate(zip(models, streams)):
+            with torch.cuda.stream(st):
+                z, uv = m.f0_diffusion(i, cond, lo, hi, offs, seed=30 + i)
+                outs[i] = (z.clone(), uv.clone())
+    torch.cuda.synchronize()
+    after = variant_launches()
+    ran = {k: v - before.get(k, 0) for k, v in after.items() if v - before.get(k, 0) > 0}
+    assert any(k.startswith("tc2") for k in ran), ran  # CTA-pair kernels were in flight from both streams
+    for i in range(2):
+        assert torch.equal(outs[i][0], seq[i][0]) and torch.equal(outs[i][1], seq[i][1])
