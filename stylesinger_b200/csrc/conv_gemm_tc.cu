@@ -70,6 +70,7 @@ __device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int n
   const int rq = lane >> 3, q4 = (lane & 7) * 4;
   const float* src = nullptr;
   int64_t st = 0;  // floats between consecutive steps (4 rows)
+  bool once = false;  // data this launch reads exactly once and nobody re-reads soon: streaming (evict-first) loads
   if constexpr (MODE == EPI_GENERIC) {
     if (!e.res) return;
     src = e.res + (r0 + rq) * e.ld_res + n + q4; st = 4 * (int64_t)e.ld_res;
@@ -94,13 +95,20 @@ __device__ __forceinline__ void prefetch_chunk(const EpiTC& e, int64_t r0, int n
       } else {
         src = e.skip + (r0 + rq) * e.ld_skip + (n - e.C) + q4; st = 4 * (int64_t)e.ld_skip;
       }
+      once = e.stream_hints != 0;
     } else return;
   } else {  // EPI_GATE: the hoisted conditioner projection of this layer
     if (!e.add) return;
     src = e.add + (r0 + rq) * e.ld_add + n + q4; st = 4 * (int64_t)e.ld_add;
+    once = e.stream_hints != 0;
   }
+  if (once) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i, src += st) p.a[i] = *reinterpret_cast<const float4*>(src);  // one 64-bit add per step
+    for (int i = 0; i < 8; ++i, src += st) p.a[i] = __ldcs(reinterpret_cast<const float4*>(src));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i, src += st) p.a[i] = *reinterpret_cast<const float4*>(src);  // one 64-bit add per step
+  }
 }
 
 // hi/lo split of 4 (2) values as packed words - computed OUTSIDE the row predicate so that a chunk's 8 steps stay one basic
@@ -283,7 +291,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiTC& e, float4* xb, int64
           v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
         }
         const bool ok = i < nsteps;
-        if (ok) *reinterpret_cast<float4*>(ps) = make_float4(v0, v1, v2, v3);
+        if (ok) {
+          if (e.stream_hints) __stcs(reinterpret_cast<float4*>(ps), make_float4(v0, v1, v2, v3));
+          else *reinterpret_cast<float4*>(ps) = make_float4(v0, v1, v2, v3);
+        }
         if (planes) {  // last layer only
           uint2 kh, kl;
           split_pack4(v0, v1, v2, v3, kh, kl);
@@ -1498,6 +1509,10 @@ std::atomic<long long>* variant_counter(const char* name) {
 }
 const char* mode_name(int mode) { return mode == EPI_GATE ? "GATE" : (mode == EPI_RES_SKIP ? "RES_SKIP" : "GENERIC"); }
 
+bool stream_hints_enabled() {
+  static const bool off = getenv("SSB_TC_NO_STREAM_HINTS") != nullptr;
+  return !off;
+}
 bool l2_prefetch_enabled() {
   static const bool off = getenv("SSB_TC_NO_L2_PREFETCH") != nullptr;
   return !off;
@@ -1745,6 +1760,7 @@ int conv_gemm_tc(Ctx& ctx, const GemmTC& p) {
   }
   if (!tp.e.bias) tp.e.bias = w.bias;
   tp.e.l2_prefetch = l2_prefetch_enabled() ? 1 : 0;
+  tp.e.stream_hints = stream_hints_enabled() ? 1 : 0;
   // large problems: CTA pairs (256 x 2*hb tiles) halve the operand bytes each SM pulls through L2
   const bool pair_off = getenv("SSB_TC_NO_PAIR") != nullptr;
   if (!pair_off && w.hb > 0 && (!p.w2 || p.w2->hb == w.hb) &&
@@ -1804,6 +1820,7 @@ int launch_dual(Ctx& ctx, const GemmTC& g, const GemmTC& r, int num_sms) {
     t.dil = w.dil; t.center = w.center; t.N = w.N; t.e = q.e;
     if (!t.e.bias) t.e.bias = w.bias;
     t.e.l2_prefetch = l2_prefetch_enabled() ? 1 : 0;
+    t.e.stream_hints = stream_hints_enabled() ? 1 : 0;
   }
   P.n0 = ((g.ntiles + 1) / 2) * P.q[0].NT;
   P.n1 = ((r.ntiles + 1) / 2) * P.q[1].NT;

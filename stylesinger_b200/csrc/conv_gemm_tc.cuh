@@ -74,6 +74,8 @@ struct EpiTC {
   int tile_base = 0;             //   index of tiles[0] in the full tile table (a GEMM over a sub-range of the row tiles)
   int out_nb = 0;                // GENERIC, > 0: `out` is column-block-major: block j = columns [j*out_nb, (j+1)*out_nb) is its own
   int64_t out_bs = 0;            //   [rows, out_nb] matrix at out + j * out_bs (the hoisted conditioner: one matrix per layer)
+  int stream_hints = 1;          // skip accumulator and conditioner addends are touched once per launch: ld/st.global.cs (evict-first)
+                                 //   so that they do not push the y / z planes (re-read by the next launch) out of L2; SSB_TC_NO_STREAM_HINTS=1: off
   int l2_prefetch = 1;           // warp 3 pulls the next tile's epilogue operands into L2 (SSB_TC_NO_L2_PREFETCH=1: off)
   __half* sh = nullptr;          // RES_SKIP (last layer): the finished skip sum also as fp16 planes [rows, C]
   __half* sl = nullptr;
