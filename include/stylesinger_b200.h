@@ -32,6 +32,7 @@ extern "C" {
 typedef struct ssb_model ssb_model_t;     /* packed StyleSinger acoustic model (immutable after create) */
 typedef struct ssb_vocoder ssb_vocoder_t; /* packed HiFi-GAN(-NSF) generator */
 typedef struct ssb_melspec ssb_melspec_t; /* STFT + mel filterbank of the reference-audio front-end */
+typedef struct ssb_lstm_encoder ssb_lstm_encoder_t; /* LSTM utterance encoder of the reference-audio front-end (emo_embed) */
 
 /* One named fp32 HOST tensor of a reference state_dict (names exactly as in the reference's
  * checkpoints: utils/commons/ckpt_utils.py:26-67 loads state_dict['model']). */
@@ -250,18 +251,46 @@ int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, in
  * Replaces utils/audios/__init__.py:36-84 librosa_wav2spec as called by inference/StyleSinger.py:79-92 (process_audio):
  * librosa.stft(center=True, pad_mode="constant", periodic Hann window) -> |.| -> librosa.filters.mel (Slaney scale and
  * normalisation, built inside create) -> log10(max(eps, .)).  fmin / fmax < 0 mean 0 / sample_rate / 2 like the reference.
- * Constraints of the implicit-GEMM formulation: fft_size / 2 a multiple of hop_size, hop_size a multiple of 16, n_mels of 4
+ * Constraints of the implicit-GEMM formulation: fft_size even, fft_size <= 8 hop_size, hop_size a multiple of 16, n_mels of 4
  * (egs/stylesinger.yaml: 48 kHz, fft 1024, hop 256, win 1024, 80 mels, 20..24000 Hz).  An utterance of n samples yields
  * ssb_melspec_num_frames = 1 + n / hop_size frames.  wav: device fp32, utterances concatenated, sample_offsets: host [B+1];
  * mel_out: device fp32 [sum frames, n_mels].  loud_norm / trim_long_sil of the reference are not implemented (both false in
  * the reference's configuration); the speaker / emotion encoders and the Praat pitch tracker are outside this library. */
 int ssb_melspec_create(ssb_melspec_t** out, int32_t sample_rate, int32_t fft_size, int32_t hop_size, int32_t win_length,
                        int32_t n_mels, float fmin, float fmax, float eps);
+/* Same front-end with the defaults of librosa.feature.melspectrogram selectable, which is what the emotion encoder's features
+ * are (data_gen/tts/emotion/audio.py:43-55: sr 16000, n_fft 400, hop 160, 40 mels, fmin 0, fmax sr / 2): pad_reflect != 0 =
+ * np.pad "reflect" centring instead of zeros (needs more than n_fft / 2 samples per utterance, like numpy), power != 0 = |X|^2
+ * instead of |X|, take_log == 0 = no log10 / eps.  n_fft need not be a multiple of hop_size here (the frame is embedded in
+ * the next multiple of 2 hop_size rows with zero weights).  ssb_melspec_create = (..., 0, 0, 1). */
+int ssb_melspec_create_ex(ssb_melspec_t** out, int32_t sample_rate, int32_t fft_size, int32_t hop_size, int32_t win_length,
+                          int32_t n_mels, float fmin, float fmax, float eps, int32_t pad_reflect, int32_t power, int32_t take_log);
 void ssb_melspec_free(ssb_melspec_t* m);
 int32_t ssb_melspec_num_frames(const ssb_melspec_t* m, int64_t n_samples);
 size_t ssb_melspec_workspace_bytes(const ssb_melspec_t* m, const int32_t* sample_offsets, int32_t B);
 int ssb_melspec_forward(const ssb_melspec_t* m, const float* wav, const int32_t* sample_offsets, int32_t B, float* mel_out,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- f3: LSTM utterance encoder of the reference audio -------------------------------------------
+ * Replaces data_gen/tts/emotion/model.py:10-77 (EmotionEncoder: batch-first torch.nn.LSTM 40 -> 256 x 3 layers from zero
+ * state + linear 256 -> 256) and the aggregation of data_gen/tts/emotion/inference.py:43-55 (embed_frames_batch) and
+ * :150-151 (embed_utterance: mean of the partial embeddings, L2-normalised), which produce the `emo_embed` input of
+ * inference/StyleSinger.py:106.  create: HOST fp32 pointers in torch state_dict layout, one per layer -
+ * weight_ih[l] [4H, input_size or H], weight_hh[l] [4H, H], bias_ih[l] / bias_hh[l] [4H], gate rows i | f | g | o;
+ * linear_weight [embed_size, H] / linear_bias [embed_size] may both be NULL (no `forward` head).  hidden_size must be 256.
+ * forward: frames device fp32 [n_partials, n_frames, input_size] (every partial the same length, as the reference batches
+ * them).  Outputs (device fp32, each may be NULL, at least one not): hidden_out [n_partials, H] = EmotionEncoder.inference
+ * (hidden[-1]); embeds_out [n_partials, embed_size] = EmotionEncoder.forward; utt_embed_out [n_utterances, H] = normalised
+ * mean of hidden over partials utt_offsets[u] .. utt_offsets[u+1] (host int32 [n_utterances + 1], 0 .. n_partials, every
+ * utterance non-empty; only read when utt_embed_out is given). */
+int ssb_lstm_encoder_create(ssb_lstm_encoder_t** out, int32_t input_size, int32_t hidden_size, int32_t num_layers,
+                            const float* const* weight_ih, const float* const* weight_hh, const float* const* bias_ih,
+                            const float* const* bias_hh, int32_t embed_size, const float* linear_weight, const float* linear_bias);
+void ssb_lstm_encoder_free(ssb_lstm_encoder_t* m);
+size_t ssb_lstm_encoder_workspace_bytes(const ssb_lstm_encoder_t* m, int32_t n_partials, int32_t n_frames, int32_t n_utterances);
+int ssb_lstm_encoder_forward(const ssb_lstm_encoder_t* m, const float* frames, int32_t n_partials, int32_t n_frames,
+                             const int32_t* utt_offsets, int32_t n_utterances, float* hidden_out, float* embeds_out,
+                             float* utt_embed_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels this library has launched in this process so far (bench.py reports the delta). */
 int64_t ssb_launch_count(void);

@@ -25,12 +25,13 @@ def pad_center(w, size):
     return np.pad(w, (lpad, size - len(w) - lpad))
 
 
-def stft(y, n_fft, hop_length, win_length):
-    """librosa.stft(y, n_fft, hop_length, win_length, window='hann', center=True, pad_mode='constant') -> complex64 [1 + n_fft/2, T].
+def stft(y, n_fft, hop_length, win_length, pad_mode="constant"):
+    """librosa.stft(y, n_fft, hop_length, win_length, window='hann', center=True, pad_mode=pad_mode) -> complex64 [1 + n_fft/2, T].
+    (librosa_wav2spec passes pad_mode='constant'; librosa's own default, used by melspectrogram, is 'reflect'.)
     librosa multiplies the float64 window into the float32 frames (-> float64), runs the real FFT and stores complex64."""
     y = np.asarray(y, dtype=np.float32)
     w = pad_center(hann_periodic(win_length), n_fft).reshape(-1, 1)
-    yp = np.pad(y, n_fft // 2, mode="constant")
+    yp = np.pad(y, n_fft // 2, mode=pad_mode)
     n_frames = 1 + (len(yp) - n_fft) // hop_length
     idx = np.arange(n_fft)[:, None] + hop_length * np.arange(n_frames)[None, :]
     frames = yp[idx]  # [n_fft, T]
@@ -82,3 +83,103 @@ def wav2mel(wav, fft_size=1024, hop_size=256, win_length=1024, num_mels=80, fmin
     mel = basis @ linear_spc                                      # :69
     mel = np.log10(np.maximum(eps, mel))                          # :70
     return mel.T.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# f3, emotion-encoder half: the reference's OWN network (data_gen/tts/emotion/model.py:10-77) and the utterance aggregation
+# of data_gen/tts/emotion/inference.py:58-155.  PINNED: tests/test_frontend_cpu.py checks these restatements against
+# tests/golden/ref_emotion_encoder.npz, generated by tools/make_golden.py from the unmodified reference classes.
+# (The 40-channel power mel that feeds it, data_gen/tts/emotion/audio.py:43-55, is librosa.feature.melspectrogram - third
+# party, not restated here.)
+
+EMO_HIDDEN = 256        # params_model.py: model_hidden_size
+EMO_EMBED = 256         # params_model.py: model_embedding_size
+EMO_LAYERS = 3          # params_model.py: model_num_layers
+EMO_MELS = 40           # params_data.py: mel_n_channels
+EMO_PARTIAL_FRAMES = 160  # params_data.py: partials_n_frames
+EMO_SR = 16000          # params_data.py: sampling_rate
+EMO_STEP_MS = 10        # params_data.py: mel_window_step
+
+
+def emotion_encoder_weights(seed, hidden=EMO_HIDDEN, n_in=EMO_MELS, layers=EMO_LAYERS, embed=EMO_EMBED):
+    """Seeded synthetic state_dict of the encoder (keys and shapes of model.py:16-21, torch.nn.LSTM layout: gate rows
+    i | f | g | o).  numpy's legacy RandomState stream is stable across versions, so fixtures only carry inputs / outputs."""
+    rs = np.random.RandomState(seed)
+    k = 1.0 / np.sqrt(hidden)
+    u = lambda *shape: rs.uniform(-k, k, size=shape).astype(np.float32)
+    sd = {}
+    for l in range(layers):
+        sd["lstm.weight_ih_l%d" % l] = u(4 * hidden, n_in if l == 0 else hidden)
+        sd["lstm.weight_hh_l%d" % l] = u(4 * hidden, hidden)
+        sd["lstm.bias_ih_l%d" % l] = u(4 * hidden)
+        sd["lstm.bias_hh_l%d" % l] = u(4 * hidden)
+    sd["linear.weight"] = u(embed, hidden)
+    sd["linear.bias"] = u(embed)
+    return sd
+
+
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def lstm_hidden(frames, sd, layers=EMO_LAYERS, dtype=np.float64):
+    """EmotionEncoder.inference (model.py:62-77): batch-first multi-layer LSTM from zero state, returns hidden[-1]
+    (the last layer's h at the last frame), [P, hidden].  Gate arithmetic of torch.nn.LSTM: i, f, o = sigmoid, g = tanh,
+    c = f c + i g, h = o tanh(c)."""
+    x = np.asarray(frames, dtype)
+    P, T, _ = x.shape
+    for l in range(layers):
+        wih = sd["lstm.weight_ih_l%d" % l].astype(dtype)
+        whh = sd["lstm.weight_hh_l%d" % l].astype(dtype)
+        b = (sd["lstm.bias_ih_l%d" % l].astype(dtype) + sd["lstm.bias_hh_l%d" % l].astype(dtype))
+        H = whh.shape[1]
+        h = np.zeros((P, H), dtype)
+        c = np.zeros((P, H), dtype)
+        out = np.empty((P, T, H), dtype)
+        xp = x @ wih.T + b
+        for t in range(T):
+            g = xp[:, t] + h @ whh.T
+            i, f, gg, o = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
+            c = _sigmoid(f) * c + _sigmoid(i) * np.tanh(gg)
+            h = _sigmoid(o) * np.tanh(c)
+            out[:, t] = h
+        x = out
+    return x[:, -1].astype(np.float32)
+
+
+def emotion_embeds(hidden, sd):
+    """EmotionEncoder.forward after the LSTM (model.py:51-57): relu(linear(hidden[-1])), L2-normalised per row."""
+    h = np.asarray(hidden, np.float64)
+    e = np.maximum(0.0, h @ sd["linear.weight"].astype(np.float64).T + sd["linear.bias"].astype(np.float64))
+    return (e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32)
+
+
+def utterance_embed(partial_hidden):
+    """embed_utterance (inference.py:150-151): mean of the partial embeddings, L2-normalised."""
+    raw = np.mean(np.asarray(partial_hidden, np.float32), axis=0)
+    return raw / np.linalg.norm(raw, 2)
+
+
+def emotion_mel(wav):
+    """wav_to_mel_spectrogram (data_gen/tts/emotion/audio.py:43-55): librosa.feature.melspectrogram(y, sr=16000, n_fft=400,
+    hop_length=160, n_mels=40) with librosa 0.8.0's defaults - win_length = n_fft, hann, center=True, pad_mode='reflect',
+    power=2.0, filters.mel(fmin=0, fmax=sr/2, htk=False, norm='slaney') - transposed to [T, 40] float32.  Third-party
+    arithmetic restated from the published algorithm: PARITY UNPINNED against librosa (STFT checked against scipy)."""
+    n_fft, hop = int(EMO_SR * 25 / 1000), int(EMO_SR * EMO_STEP_MS / 1000)
+    S = np.abs(stft(wav, n_fft, hop, n_fft, pad_mode="reflect")) ** 2.0
+    return (mel_basis(EMO_SR, n_fft, EMO_MELS, 0.0, EMO_SR / 2) @ S).astype(np.float32).T
+
+
+def compute_partial_slices(n_samples, partial_utterance_n_frames=EMO_PARTIAL_FRAMES, min_pad_coverage=0.75, overlap=0.5):
+    """inference.py:58-107 as (start, stop) pairs: (wav ranges, mel ranges)."""
+    assert 0 <= overlap < 1 and 0 < min_pad_coverage <= 1
+    spf = int(EMO_SR * EMO_STEP_MS / 1000)
+    n_frames = int(np.ceil((n_samples + 1) / spf))
+    frame_step = max(int(np.round(partial_utterance_n_frames * (1 - overlap))), 1)
+    steps = max(1, n_frames - partial_utterance_n_frames + frame_step + 1)
+    mel = [(i, i + partial_utterance_n_frames) for i in range(0, steps, frame_step)]
+    wav = [(a * spf, b * spf) for a, b in mel]
+    coverage = (n_samples - wav[-1][0]) / (wav[-1][1] - wav[-1][0])
+    if coverage < min_pad_coverage and len(mel) > 1:
+        mel, wav = mel[:-1], wav[:-1]
+    return wav, mel

@@ -61,6 +61,7 @@ EXPORTS = [
     "ssb_mel_diffusion_sample_plms", "ssb_fft_workspace_bytes", "ssb_fft_encoder", "ssb_fft_decoder",
     "ssb_get_style_workspace_bytes", "ssb_get_style", "ssb_set_interleaved_layers", "ssb_op_attention_tc", "ssb_set_attention_tensor_cores",
     "ssb_melspec_create", "ssb_melspec_free", "ssb_melspec_num_frames", "ssb_melspec_workspace_bytes", "ssb_melspec_forward",
+    "ssb_melspec_create_ex", "ssb_lstm_encoder_create", "ssb_lstm_encoder_free", "ssb_lstm_encoder_workspace_bytes", "ssb_lstm_encoder_forward",
 ]
 
 
@@ -115,10 +116,15 @@ def _load():
         "ssb_set_interleaved_layers": (i32, [i32]),
         "ssb_set_attention_tensor_cores": (i32, [i32]),
         "ssb_melspec_create": (C.c_int, [P(vp), i32, i32, i32, i32, i32, C.c_float, C.c_float, C.c_float]),
+        "ssb_melspec_create_ex": (C.c_int, [P(vp), i32, i32, i32, i32, i32, C.c_float, C.c_float, C.c_float, i32, i32, i32]),
         "ssb_melspec_free": (None, [vp]),
         "ssb_melspec_num_frames": (i32, [vp, C.c_int64]),
         "ssb_melspec_workspace_bytes": (sz, [vp, vp, i32]),
         "ssb_melspec_forward": (C.c_int, [vp, vp, vp, i32, vp, vp, sz, vp]),
+        "ssb_lstm_encoder_create": (C.c_int, [P(vp), i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
+        "ssb_lstm_encoder_free": (None, [vp]),
+        "ssb_lstm_encoder_workspace_bytes": (sz, [vp, i32, i32, i32]),
+        "ssb_lstm_encoder_forward": (C.c_int, [vp, vp, i32, i32, vp, i32, vp, vp, vp, vp, sz, vp]),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

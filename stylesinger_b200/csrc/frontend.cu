@@ -25,6 +25,9 @@ struct ssb_melspec {
   ssb::Conv mel;   // [1][nbp][n_mels]
   int sample_rate = 0, n_fft = 0, hop = 0, win = 0, n_mels = 0, nbins = 0, nbp = 0, taps = 0;
   float eps = 1e-6f;
+  int reflect = 0;  // centre padding: 0 = zeros (librosa_wav2spec passes pad_mode="constant"), 1 = np.pad "reflect" (librosa default)
+  int power = 0;    // 0 = |X| (librosa_wav2spec), 1 = |X|^2 (librosa.feature.melspectrogram default power=2.0)
+  int log10 = 1;    // 1 = log10(max(eps, mel)), 0 = the filterbank output itself
 };
 
 namespace ssb {
@@ -49,23 +52,42 @@ __global__ void k_wav_rows(const int4* utt, const int32_t* sample_offs, const fl
   if (i >= (int64_t)u.y * hop) return;
   rows[(int64_t)u.x * hop + i] = i < n ? wav[(int64_t)sample_offs[b] + i] : 0.f;
 }
+// np.pad(y, n_fft / 2, mode="reflect") of librosa.stft's default centring: sample -i is y[i], sample n - 1 + i is y[n - 1 - i].
+// Written into the guard rows in front of the utterance and behind its last sample (pad <= 2 rows each side; the 16 guard
+// rows between neighbours keep the two utterances' pads apart).  Like numpy, needs n > pad.
+__global__ void k_wav_reflect(const int4* utt, const int32_t* sample_offs, const float* wav, int hop, int pad, float* rows) {
+  const int b = blockIdx.y;
+  const int4 u = utt[b];
+  const int64_t n = (int64_t)sample_offs[b + 1] - sample_offs[b];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2 pad: [0, pad) = left pad, [pad, 2 pad) = right pad
+  if (i >= 2 * pad || n <= pad) return;
+  const float* y = wav + sample_offs[b];
+  if (i < pad) {
+    rows[(int64_t)u.x * hop - 1 - i] = y[1 + i];
+  } else {
+    const int j = i - pad;
+    rows[(int64_t)u.x * hop + n + j] = y[n - 2 - j];
+  }
+}
 // |re + i im| for the [rows, 2 * nbp] (re | im) spectrum; columns >= nbins are padding (zero weights -> zero)
-__global__ void k_magnitude(const float* spec, int64_t rows, int nbp, float* mag) {
+__global__ void k_magnitude(const float* spec, int64_t rows, int nbp, int power, float* mag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * nbp) return;
   const int64_t r = i / nbp;
   const int c = (int)(i - r * nbp);
   const float re = spec[r * 2 * nbp + c], im = spec[r * 2 * nbp + nbp + c];
-  mag[i] = sqrtf(re * re + im * im);
+  const float p2 = re * re + im * im;
+  mag[i] = power ? p2 : sqrtf(p2);
 }
-__global__ void k_log10_unpack(const int4* utt, const float* x, int ld, int C, float eps, float* out_tight) {
+__global__ void k_log10_unpack(const int4* utt, const float* x, int ld, int C, float eps, int take_log, float* out_tight) {
   const int b = blockIdx.y;
   const int4 u = utt[b];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)u.y * C) return;
   const int64_t t = i / C;
   const int c = (int)(i - t * C);
-  out_tight[((int64_t)u.z + t) * C + c] = log10f(fmaxf(eps, x[((int64_t)u.x + t) * ld + c]));
+  const float v = x[((int64_t)u.x + t) * ld + c];
+  out_tight[((int64_t)u.z + t) * C + c] = take_log ? log10f(fmaxf(eps, v)) : v;
 }
 
 // librosa 0.8 filters.mel (Slaney scale, htk=False, norm='slaney'), float64 like numpy, then float32
@@ -108,6 +130,14 @@ int run_melspec(Ctx& c, const ssb_melspec& m, const Seq& q, const float* wav, co
     SSB_CUDA(cudaGetLastError());
     ++g_launches;
   }
+  if (m.reflect) {
+    const int pad = m.n_fft / 2;
+    for (int b = 0; b < B; ++b)
+      SSB_CHECK((int64_t)sample_offsets_host[b + 1] - sample_offsets_host[b] > pad, "reflect padding needs more than n_fft / 2 samples per utterance");
+    k_wav_reflect<<<dim3((unsigned)((2 * pad + 255) / 256), (unsigned)B), 256, 0, c.stream>>>(s.utt, offs_dev, wav, m.hop, pad, rows);
+    SSB_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
   {
     ConvGemm g = make_gemm(m.dft, s, rows, m.hop);
     g.e.out = spec; g.e.ldo = 2 * m.nbp;
@@ -115,7 +145,7 @@ int run_melspec(Ctx& c, const ssb_melspec& m, const Seq& q, const float* wav, co
   }
   {
     const int64_t n = s.rows * m.nbp;
-    k_magnitude<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(spec, s.rows, m.nbp, mag);
+    k_magnitude<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(spec, s.rows, m.nbp, m.power, mag);
     SSB_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -126,7 +156,7 @@ int run_melspec(Ctx& c, const ssb_melspec& m, const Seq& q, const float* wav, co
   }
   {
     const int64_t per = (int64_t)s.maxlen * m.n_mels;
-    k_log10_unpack<<<dim3((unsigned)((per + 255) / 256), (unsigned)B), 256, 0, c.stream>>>(s.utt, mel, m.n_mels, m.n_mels, m.eps, mel_out);
+    k_log10_unpack<<<dim3((unsigned)((per + 255) / 256), (unsigned)B), 256, 0, c.stream>>>(s.utt, mel, m.n_mels, m.n_mels, m.eps, m.log10, mel_out);
     SSB_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -143,19 +173,28 @@ extern "C" {
 
 int ssb_melspec_create(ssb_melspec_t** out, int32_t sample_rate, int32_t fft_size, int32_t hop_size, int32_t win_length,
                        int32_t n_mels, float fmin, float fmax, float eps) {
+  return ssb_melspec_create_ex(out, sample_rate, fft_size, hop_size, win_length, n_mels, fmin, fmax, eps, 0, 0, 1);
+}
+
+int ssb_melspec_create_ex(ssb_melspec_t** out, int32_t sample_rate, int32_t fft_size, int32_t hop_size, int32_t win_length,
+                          int32_t n_mels, float fmin, float fmax, float eps, int32_t pad_reflect, int32_t power, int32_t take_log) {
   SSB_CHECK(out, "null argument");
   *out = nullptr;
   SSB_CHECK(sample_rate > 0 && fft_size > 0 && hop_size > 0 && win_length > 0 && win_length <= fft_size && n_mels > 0, "bad front-end geometry");
-  SSB_CHECK(fft_size % hop_size == 0 && (fft_size / 2) % hop_size == 0 && hop_size % 16 == 0,
-            "the implicit-GEMM STFT needs n_fft / 2 to be a multiple of hop_size and hop_size of 16");
-  SSB_CHECK(fft_size / hop_size / 2 <= GUARD, "n_fft / hop_size too large for the guard band");
+  SSB_CHECK(fft_size % 2 == 0 && hop_size % 16 == 0, "the implicit-GEMM STFT needs an even n_fft and hop_size a multiple of 16");
+  // frame = `taps` whole rows of hop samples centred on sample t * hop: span = n_fft rounded up to a multiple of 2 hop, the
+  // DFT weights of the `lead` samples in front of / behind the n_fft window are zero
+  const int span = (fft_size + 2 * hop_size - 1) / (2 * hop_size) * (2 * hop_size);
+  const int lead = (span - fft_size) / 2;
+  SSB_CHECK(span / hop_size / 2 <= 4 && span / hop_size / 2 <= GUARD, "n_fft / hop_size too large for the guard band");
   SSB_CHECK(n_mels % 4 == 0, "n_mels must be a multiple of 4");
   std::unique_ptr<ssb_melspec> m(new ssb_melspec);
   m->sample_rate = sample_rate; m->n_fft = fft_size; m->hop = hop_size; m->win = win_length; m->n_mels = n_mels;
   m->nbins = fft_size / 2 + 1;
   m->nbp = (m->nbins + 15) & ~15;
-  m->taps = fft_size / hop_size;
+  m->taps = span / hop_size;
   m->eps = eps;
+  m->reflect = pad_reflect ? 1 : 0; m->power = power ? 1 : 0; m->log10 = take_log ? 1 : 0;
   if (fmin < 0) fmin = 0.f;                       // librosa_wav2spec: fmin == -1 -> 0, fmax == -1 -> sr / 2
   if (fmax < 0) fmax = 0.5f * (float)sample_rate;
   const double PI = 3.14159265358979323846;
@@ -164,12 +203,12 @@ int ssb_melspec_create(ssb_melspec_t** out, int32_t sample_rate, int32_t fft_siz
   const int lpad = (fft_size - win_length) / 2;
   for (int i = 0; i < win_length; ++i) w[(size_t)lpad + i] = 0.5 - 0.5 * cos(2.0 * PI * i / win_length);
   const int N2 = 2 * m->nbp;
-  std::vector<float> W((size_t)fft_size * N2, 0.f);  // [tap][c][n]: sample j = tap * hop + c of the frame
+  std::vector<float> W((size_t)span * N2, 0.f);  // [tap][c][n]: row sample tap * hop + c = frame sample j + lead
   for (int j = 0; j < fft_size; ++j)
     for (int k = 0; k < m->nbins; ++k) {
       const double ph = 2.0 * PI * (double)(((int64_t)j * k) % fft_size) / fft_size;
-      W[(size_t)j * N2 + k] = (float)(w[(size_t)j] * cos(ph));
-      W[(size_t)j * N2 + m->nbp + k] = (float)(-w[(size_t)j] * sin(ph));
+      W[(size_t)(j + lead) * N2 + k] = (float)(w[(size_t)j] * cos(ph));
+      W[(size_t)(j + lead) * N2 + m->nbp + k] = (float)(-w[(size_t)j] * sin(ph));
     }
   m->dft.W = m->pool.upload(W);
   m->dft.bias = nullptr;

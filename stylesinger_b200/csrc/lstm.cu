@@ -1,0 +1,351 @@
+// f3: the emotion-encoder half of the reference-audio front-end.
+//   EmotionEncoder (reference data_gen/tts/emotion/model.py:10-77): a 3-layer batch-first LSTM (40 -> 256 -> 256 -> 256) run
+//   from zero state over 160-frame partial utterances; `inference` returns hidden[-1] (model.py:62-77), `forward` adds
+//   relu(linear) + L2 normalisation (model.py:51-57); embed_utterance (data_gen/tts/emotion/inference.py:150-151) averages
+//   the partial embeddings and L2-normalises.  The result is the `emo_embed` input of the hot path (inference/StyleSinger.py:106).
+// As kernels (fp32 FFMA; the recurrence is latency-bound, 480 dependent steps of a 1024 x 256 mat-vec per partial):
+//   * per layer the input projection of ALL frames is one plain GEMM  xproj = x W_ih^T + (b_ih + b_hh)   [P T, 1024];
+//   * the recurrence runs on one 8-CTA thread-block CLUSTER per group of up to 8 partials: CTA r keeps the W_hh rows of
+//     hidden units 32 r .. 32 r + 31 (all four gates, 128 x 256 fp32 = 128 KB) resident in shared memory for the whole
+//     sequence, computes those gates for every partial of the group, applies the cell update and writes its 32 new h values
+//     into the (double-buffered) h vector of all 8 CTAs through distributed shared memory; one cluster barrier per frame.
+//     W_hh is read from HBM once per layer instead of once per frame.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <memory>
+#include <vector>
+
+#include "../../include/stylesinger_b200.h"
+#include "common.cuh"
+#include "model.cuh"
+
+namespace cg = cooperative_groups;
+
+struct ssb_lstm_encoder {
+  ssb::DevicePool pool;
+  int n_in = 0, hidden = 0, layers = 0, embed = 0;
+  std::vector<float*> wih_t;   // per layer [K_l][4H]: W_ih^T with cluster-permuted gate columns
+  std::vector<float*> bias;    // per layer [4H]: b_ih + b_hh, same permutation
+  std::vector<float*> whh_p;   // per layer [8][H][128]: CTA r's slice, k-major
+  float* lin_wt = nullptr;     // [H][E] = linear.weight^T
+  float* lin_b = nullptr;      // [E]
+};
+
+namespace ssb {
+namespace {
+
+constexpr int H = 256;            // hidden units (model_hidden_size, params_model.py)
+constexpr int G4 = 4 * H;         // gate rows
+constexpr int NCTA = 8;           // cluster size
+constexpr int UPC = H / NCTA;     // hidden units per CTA (32)
+constexpr int RPC = 4 * UPC;      // gate rows per CTA (128)
+constexpr int PB = 8;             // partials per cluster
+constexpr int LSTM_THREADS = 256;
+constexpr size_t LSTM_SMEM = sizeof(float) * ((size_t)H * RPC + 2 * (size_t)H * PB + (size_t)RPC * PB);
+
+#define RUN(x)                 \
+  do {                         \
+    int rc_ = (x);             \
+    if (rc_ != 0) return rc_;  \
+  } while (0)
+
+// column of the permuted gate axis that holds torch gate row `g` (= q * H + u, q in i|f|g|o): CTA u / 32, local row q * 32 + u % 32
+inline int perm_col(int g) {
+  const int q = g / H, u = g % H;
+  return (u / UPC) * RPC + q * UPC + (u % UPC);
+}
+
+// C[M, N] = A[M, K] B[K, N] + bias[N]; 64 x 64 tiles, 4 x 4 per thread, fp32 FFMA.  N % 64 == 0.
+__global__ void __launch_bounds__(256) k_gemm_bias(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ bias,
+                                                   float* __restrict__ Cm, int64_t M, int N, int K) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * 64;
+  const int n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, kk = i & 15;
+      const int64_t m = m0 + r;
+      As[kk][r] = (m < M && k0 + kk < K) ? A[m * K + k0 + kk] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i >> 6, c = i & 63;
+      Bs[kk][c] = (k0 + kk < K) ? B[(int64_t)(k0 + kk) * N + n0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      Cm[m * N + n] = acc[i][j] + bias[n];
+    }
+  }
+}
+
+// One LSTM layer over T frames for partials [PB * cluster, ...).  xproj [P, T, 4H] (permuted gate columns, biases folded in),
+// whh_p [8][H][128].  hseq [P, T, H] (may be null) receives every h_t, hlast [P, H] (may be null) the final one.
+__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
+    k_lstm_layer(const float* __restrict__ xproj, const float* __restrict__ whh_p, int P, int T, float* __restrict__ hseq,
+                 float* __restrict__ hlast) {
+  extern __shared__ __align__(16) float smem[];
+  float* Wsm = smem;                       // [H][RPC]
+  float* hsm = Wsm + (size_t)H * RPC;      // [2][H][PB]
+  float* gsm = hsm + 2 * (size_t)H * PB;   // [RPC][PB]
+  cg::cluster_group cl = cg::this_cluster();
+  const int r = (int)cl.block_rank();
+  const int p0 = (int)(blockIdx.x / NCTA) * PB;
+  const int tid = threadIdx.x;
+
+  {  // resident W_hh slice (128 KB) and zero initial state
+    const float4* src = reinterpret_cast<const float4*>(whh_p + (size_t)r * H * RPC);
+    float4* dst = reinterpret_cast<float4*>(Wsm);
+    for (int i = tid; i < H * RPC / 4; i += LSTM_THREADS) dst[i] = src[i];
+    for (int i = tid; i < 2 * H * PB; i += LSTM_THREADS) hsm[i] = 0.f;
+  }
+  // mat-vec role: gate row `row` of this CTA for partials pg * 4 .. pg * 4 + 3
+  const int row = tid & (RPC - 1), pg = tid >> 7;
+  // cell role: hidden unit 32 r + uj of partial p0 + up (its c lives in a register for the whole sequence)
+  const int up = tid & (PB - 1), uj = tid >> 3;
+  const bool cell_valid = p0 + up < P;
+  float c_state = 0.f;
+  const float* xp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = min(p0 + pg * 4 + j, P - 1);  // padding partials of the last group recompute the last real one
+    xp[j] = xproj + (size_t)p * T * G4 + (size_t)r * RPC + row;
+  }
+  float nx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) nx[j] = xp[j][0];
+  float* remote[NCTA];
+#pragma unroll
+  for (int d = 0; d < NCTA; ++d) remote[d] = cl.map_shared_rank(hsm, d);
+  cl.sync();  // every CTA of the cluster is resident and has zeroed its h buffers before any remote write
+
+  int cur = 0;
+  for (int t = 0; t < T; ++t) {
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = nx[j];
+    if (t + 1 < T) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nx[j] = xp[j][(size_t)(t + 1) * G4];
+    }
+    const float* hc = hsm + (size_t)cur * H * PB + pg * 4;
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) {
+      const float w = Wsm[k * RPC + row];
+      const float4 hv = *reinterpret_cast<const float4*>(hc + k * PB);
+      acc[0] = fmaf(w, hv.x, acc[0]);
+      acc[1] = fmaf(w, hv.y, acc[1]);
+      acc[2] = fmaf(w, hv.z, acc[2]);
+      acc[3] = fmaf(w, hv.w, acc[3]);
+    }
+    *reinterpret_cast<float4*>(gsm + row * PB + pg * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __syncthreads();
+    {
+      const float gi = gsm[(0 * UPC + uj) * PB + up], gf = gsm[(1 * UPC + uj) * PB + up];
+      const float gg = gsm[(2 * UPC + uj) * PB + up], go = gsm[(3 * UPC + uj) * PB + up];
+      c_state = sigmoidf_(gf) * c_state + sigmoidf_(gi) * tanhf(gg);
+      const float h = sigmoidf_(go) * tanhf(c_state);
+      const int off = (cur ^ 1) * H * PB + (r * UPC + uj) * PB + up;
+#pragma unroll
+      for (int d = 0; d < NCTA; ++d) remote[d][off] = h;
+      if (cell_valid) {
+        if (hseq) hseq[((size_t)(p0 + up) * T + t) * H + r * UPC + uj] = h;
+        if (hlast && t == T - 1) hlast[(size_t)(p0 + up) * H + r * UPC + uj] = h;
+      }
+    }
+    cl.sync();  // h_t complete in every CTA; gsm and the old h buffer are free again
+    cur ^= 1;
+  }
+}
+
+// relu(linear(h)) L2-normalised per partial (model.py:51-57); one block of 256 threads per partial
+__global__ void __launch_bounds__(256) k_embed_norm(const float* __restrict__ hid, const float* __restrict__ wt, const float* __restrict__ b,
+                                                    int E, float* __restrict__ out) {
+  __shared__ float hs[H];
+  __shared__ float red[8];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  hs[tid] = hid[(size_t)p * H + tid];
+  __syncthreads();
+  float ss = 0.f;
+  for (int e = tid; e < E; e += 256) {
+    float a = b[e];
+    for (int k = 0; k < H; ++k) a = fmaf(hs[k], wt[(size_t)k * E + e], a);
+    a = fmaxf(a, 0.f);
+    out[(size_t)p * E + e] = a;
+    ss += a * a;
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = 1.0f / sqrtf(tot);
+  for (int e = tid; e < E; e += 256) out[(size_t)p * E + e] *= inv;
+}
+
+// utterance embedding: mean over the utterance's partials, L2-normalised (inference.py:150-151); one block per utterance
+__global__ void __launch_bounds__(256) k_utt_embed(const float* __restrict__ hid, const int32_t* __restrict__ offs, float* __restrict__ out) {
+  __shared__ float red[8];
+  const int u = blockIdx.x, tid = threadIdx.x;
+  const int a = offs[u], b = offs[u + 1];
+  float s = 0.f;
+  for (int p = a; p < b; ++p) s += hid[(size_t)p * H + tid];
+  s /= (float)(b - a);
+  float ss = warp_sum(s * s);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  out[(size_t)u * H + tid] = s / sqrtf(tot);
+}
+
+int run_lstm(Ctx& c, const ssb_lstm_encoder& m, const float* frames, int P, int T, const int32_t* utt_offsets_host, int U,
+             float* hidden_out, float* embeds_out, float* utt_out) {
+  const size_t rows = (size_t)P * T;
+  float* xproj = c.alloc<float>(rows * G4);
+  float* seq_a = c.alloc<float>(rows * H);
+  float* seq_b = c.alloc<float>(rows * H);
+  float* hid_ws = c.alloc<float>((size_t)P * H);
+  int32_t* offs_dev = c.alloc<int32_t>((size_t)U + 1);
+  SSB_CHECK(c.dry || !c.failed, "workspace too small");
+  if (c.dry || P == 0) return 0;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  SSB_CUDA(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    SSB_CUDA(cudaFuncSetAttribute(k_lstm_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSTM_SMEM));
+    attr_dev = dev;
+  }
+  float* hid = hidden_out ? hidden_out : hid_ws;
+  const float* x = frames;
+  int K = m.n_in;
+  const unsigned groups = (unsigned)((P + PB - 1) / PB);
+  for (int l = 0; l < m.layers; ++l) {
+    k_gemm_bias<<<dim3(G4 / 64, (unsigned)((rows + 63) / 64)), 256, 0, c.stream>>>(x, m.wih_t[(size_t)l], m.bias[(size_t)l], xproj,
+                                                                                   (int64_t)rows, G4, K);
+    SSB_CUDA(cudaGetLastError());
+    ++g_launches;
+    const bool last = l == m.layers - 1;
+    float* out_seq = last ? nullptr : ((l & 1) ? seq_b : seq_a);
+    k_lstm_layer<<<groups * NCTA, LSTM_THREADS, LSTM_SMEM, c.stream>>>(xproj, m.whh_p[(size_t)l], P, T, out_seq, last ? hid : nullptr);
+    SSB_CUDA(cudaGetLastError());
+    ++g_launches;
+    x = out_seq;
+    K = H;
+  }
+  if (embeds_out) {
+    k_embed_norm<<<(unsigned)P, 256, 0, c.stream>>>(hid, m.lin_wt, m.lin_b, m.embed, embeds_out);
+    SSB_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  if (utt_out) {
+    SSB_CUDA(cudaMemcpyAsync(offs_dev, utt_offsets_host, sizeof(int32_t) * ((size_t)U + 1), cudaMemcpyHostToDevice, c.stream));
+    k_utt_embed<<<(unsigned)U, 256, 0, c.stream>>>(hid, offs_dev, utt_out);
+    SSB_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  return 0;
+}
+
+int check_offsets(const int32_t* offs, int U, int P) {
+  SSB_CHECK(offs && U > 0, "utterance offsets missing");
+  SSB_CHECK(offs[0] == 0 && offs[U] == P, "utterance offsets must span [0, n_partials]");
+  for (int u = 0; u < U; ++u) SSB_CHECK(offs[u + 1] > offs[u], "every utterance needs at least one partial");
+  return 0;
+}
+
+}  // namespace
+}  // namespace ssb
+
+using namespace ssb;
+
+extern "C" {
+
+int ssb_lstm_encoder_create(ssb_lstm_encoder_t** out, int32_t input_size, int32_t hidden_size, int32_t num_layers,
+                            const float* const* weight_ih, const float* const* weight_hh, const float* const* bias_ih,
+                            const float* const* bias_hh, int32_t embed_size, const float* linear_weight, const float* linear_bias) {
+  SSB_CHECK(out, "null argument");
+  *out = nullptr;
+  SSB_CHECK(weight_ih && weight_hh && bias_ih && bias_hh, "null weight table");
+  SSB_CHECK(input_size > 0 && num_layers > 0 && num_layers <= 16, "bad LSTM geometry");
+  SSB_CHECK(hidden_size == H, "the cluster LSTM kernel is built for hidden_size 256 (params_model.py: model_hidden_size)");
+  SSB_CHECK((linear_weight == nullptr) == (linear_bias == nullptr) && (linear_weight == nullptr || embed_size > 0), "bad linear head");
+  std::unique_ptr<ssb_lstm_encoder> m(new ssb_lstm_encoder);
+  m->n_in = input_size; m->hidden = hidden_size; m->layers = num_layers; m->embed = linear_weight ? embed_size : 0;
+  for (int l = 0; l < num_layers; ++l) {
+    SSB_CHECK(weight_ih[l] && weight_hh[l] && bias_ih[l] && bias_hh[l], "null layer weight");
+    const int K = l == 0 ? input_size : H;
+    std::vector<float> wt((size_t)K * G4), b((size_t)G4), wp((size_t)NCTA * H * RPC);
+    for (int g = 0; g < G4; ++g) {
+      const int col = perm_col(g);
+      for (int k = 0; k < K; ++k) wt[(size_t)k * G4 + col] = weight_ih[l][(size_t)g * K + k];
+      b[(size_t)col] = bias_ih[l][g] + bias_hh[l][g];
+      const int cta = col / RPC, lr = col % RPC;
+      for (int k = 0; k < H; ++k) wp[((size_t)cta * H + k) * RPC + lr] = weight_hh[l][(size_t)g * H + k];
+    }
+    m->wih_t.push_back(m->pool.upload(wt));
+    m->bias.push_back(m->pool.upload(b));
+    m->whh_p.push_back(m->pool.upload(wp));
+    SSB_CHECK(m->wih_t.back() && m->bias.back() && m->whh_p.back(), "device allocation failed");
+  }
+  if (linear_weight) {
+    std::vector<float> wt((size_t)H * embed_size), b(linear_bias, linear_bias + embed_size);
+    for (int e = 0; e < embed_size; ++e)
+      for (int k = 0; k < H; ++k) wt[(size_t)k * embed_size + e] = linear_weight[(size_t)e * H + k];
+    m->lin_wt = m->pool.upload(wt);
+    m->lin_b = m->pool.upload(b);
+    SSB_CHECK(m->lin_wt && m->lin_b, "device allocation failed");
+  }
+  *out = m.release();
+  return 0;
+}
+
+void ssb_lstm_encoder_free(ssb_lstm_encoder_t* m) { delete m; }
+
+size_t ssb_lstm_encoder_workspace_bytes(const ssb_lstm_encoder_t* m, int32_t n_partials, int32_t n_frames, int32_t n_utterances) {
+  if (!m || n_partials < 0 || n_frames <= 0 || n_utterances < 0) return 0;
+  Ctx c;
+  c.dry = true;
+  if (run_lstm(c, *m, nullptr, n_partials, n_frames, nullptr, n_utterances, nullptr, nullptr, nullptr) != 0) return 0;
+  return c.high + 4096;
+}
+
+int ssb_lstm_encoder_forward(const ssb_lstm_encoder_t* m, const float* frames, int32_t n_partials, int32_t n_frames,
+                             const int32_t* utt_offsets, int32_t n_utterances, float* hidden_out, float* embeds_out,
+                             float* utt_embed_out, void* workspace, size_t workspace_bytes, void* stream) {
+  SSB_CHECK(m && workspace && n_partials >= 0 && n_frames > 0, "bad argument");
+  SSB_CHECK(n_partials == 0 || frames, "null frames");
+  SSB_CHECK(hidden_out || embeds_out || utt_embed_out, "no output requested");
+  SSB_CHECK(!embeds_out || m->lin_wt, "encoder was created without the linear head");
+  if (utt_embed_out) RUN(check_offsets(utt_offsets, n_utterances, n_partials));
+  Ctx c;
+  c.base = (char*)workspace; c.cap = workspace_bytes; c.stream = (cudaStream_t)stream;
+  return run_lstm(c, *m, frames, n_partials, n_frames, utt_offsets, utt_embed_out ? n_utterances : 0, hidden_out, embeds_out, utt_embed_out);
+}
+
+}  // extern "C"

@@ -472,7 +472,9 @@ class MelSpectrogram:
     """log10-mel front-end of the reference audio (ssb_melspec_t): librosa_wav2spec of the reference
     (utils/audios/__init__.py:36-84) with the hparams of egs/stylesinger.yaml by default."""
 
-    def __init__(self, hp=None, device=None, eps=1e-6):
+    def __init__(self, hp=None, device=None, eps=1e-6, pad_reflect=False, power=False, log=True):
+        """pad_reflect / power / log=False select the defaults of librosa.feature.melspectrogram instead of those of
+        librosa_wav2spec (ssb_melspec_create_ex; the emotion encoder's features, data_gen/tts/emotion/audio.py:43-55)."""
         _require_cuda()
         h = dict(audio_sample_rate=48000, fft_size=1024, hop_size=256, win_size=1024, audio_num_mel_bins=80, fmin=20, fmax=24000)
         h.update({k: v for k, v in (hp or {}).items() if k in h})
@@ -480,8 +482,9 @@ class MelSpectrogram:
         self.device = torch.device(device if device is not None else "cuda:0")
         torch.cuda.set_device(self.device)
         handle = C.c_void_p()
-        check(lib.ssb_melspec_create(C.byref(handle), h["audio_sample_rate"], h["fft_size"], h["hop_size"], h["win_size"],
-                                     h["audio_num_mel_bins"], float(h["fmin"]), float(h["fmax"]), float(eps)), "ssb_melspec_create")
+        check(lib.ssb_melspec_create_ex(C.byref(handle), h["audio_sample_rate"], h["fft_size"], h["hop_size"], h["win_size"],
+                                        h["audio_num_mel_bins"], float(h["fmin"]), float(h["fmax"]), float(eps),
+                                        int(bool(pad_reflect)), int(bool(power)), int(bool(log))), "ssb_melspec_create_ex")
         self._h = handle
         self._ws = _Workspace(self.device)
 
@@ -513,6 +516,78 @@ class MelSpectrogram:
               "ssb_melspec_forward")
         mels = list(torch.split(out, frames))
         return mels[0] if single else mels
+
+
+class LstmEncoder:
+    """LSTM utterance encoder of the reference audio (ssb_lstm_encoder_t): the reference's EmotionEncoder
+    (data_gen/tts/emotion/model.py:10-77).  ``state_dict``: the encoder's own keys (``lstm.weight_ih_l0`` ..., optional
+    ``linear.weight`` / ``linear.bias``), torch tensors or numpy arrays."""
+
+    def __init__(self, state_dict, device=None):
+        _require_cuda()
+        self.device = torch.device(device if device is not None else "cuda:0")
+        torch.cuda.set_device(self.device)
+        sd = {k: np.ascontiguousarray(v.detach().cpu().float().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, np.float32))
+              for k, v in state_dict.items() if k.startswith(("lstm.", "linear."))}
+        L = 0
+        while "lstm.weight_ih_l%d" % L in sd:
+            L += 1
+        if L == 0:
+            raise KeyError("state_dict has no lstm.weight_ih_l0")
+        self.layers, self.hidden = L, sd["lstm.weight_hh_l0"].shape[1]
+        self.n_in = sd["lstm.weight_ih_l0"].shape[1]
+        for l in range(L):
+            for k, shape in (("weight_ih", (4 * self.hidden, self.n_in if l == 0 else self.hidden)), ("weight_hh", (4 * self.hidden, self.hidden)),
+                             ("bias_ih", (4 * self.hidden,)), ("bias_hh", (4 * self.hidden,))):
+                name = "lstm.%s_l%d" % (k, l)
+                if name not in sd or sd[name].shape != shape:
+                    raise ValueError(f"{name}: expected shape {shape}, got {sd[name].shape if name in sd else None}")
+        table = lambda k: (C.c_void_p * L)(*[sd["lstm.%s_l%d" % (k, l)].ctypes.data for l in range(L)])
+        lw, lb = sd.get("linear.weight"), sd.get("linear.bias")
+        self.embed = 0 if lw is None else lw.shape[0]
+        if lw is not None and (lb is None or lw.shape != (self.embed, self.hidden) or lb.shape != (self.embed,)):
+            raise ValueError("linear.weight / linear.bias shapes do not match the LSTM")
+        handle = C.c_void_p()
+        check(lib.ssb_lstm_encoder_create(C.byref(handle), self.n_in, self.hidden, L, table("weight_ih"), table("weight_hh"),
+                                          table("bias_ih"), table("bias_hh"), self.embed,
+                                          None if lw is None else lw.ctypes.data, None if lw is None else lb.ctypes.data),
+              "ssb_lstm_encoder_create")
+        self._h = handle
+        self._ws = _Workspace(self.device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.ssb_lstm_encoder_free(h)
+            self._h = None
+
+    def __call__(self, frames, utt_offsets=None, want_embeds=False):
+        """frames: [P, T, n_in] (device or host).  Returns a dict of device tensors: ``hidden`` [P, H] (EmotionEncoder.inference),
+        ``embeds`` [P, E] (EmotionEncoder.forward, if want_embeds) and ``utt_embed`` [U, H] (normalised mean of ``hidden`` over
+        partials utt_offsets[u] .. utt_offsets[u+1], if utt_offsets is given)."""
+        x = torch.as_tensor(frames, dtype=torch.float32).to(self.device).contiguous()
+        if x.dim() != 3 or x.shape[2] != self.n_in:
+            raise ValueError(f"frames must be [partials, frames, {self.n_in}]")
+        Pn, T = int(x.shape[0]), int(x.shape[1])
+        out = {"hidden": torch.empty(Pn, self.hidden, dtype=torch.float32, device=self.device)}
+        if want_embeds:
+            if self.embed == 0:
+                raise _lib.SsbError("encoder was created without the linear head (linear.weight / linear.bias)")
+            out["embeds"] = torch.empty(Pn, self.embed, dtype=torch.float32, device=self.device)
+        offs, U = None, 0
+        if utt_offsets is not None:
+            offs = np.ascontiguousarray(utt_offsets, np.int32)
+            U = len(offs) - 1
+            out["utt_embed"] = torch.empty(U, self.hidden, dtype=torch.float32, device=self.device)
+        n = lib.ssb_lstm_encoder_workspace_bytes(self._h, Pn, T, U)
+        if n == 0:
+            check(-1, "ssb_lstm_encoder_workspace_bytes")
+        ws = self._ws.get(n)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(lib.ssb_lstm_encoder_forward(self._h, _ptr(x), Pn, T, None if offs is None else offs.ctypes.data, U, _ptr(out["hidden"]),
+                                           _ptr(out.get("embeds")), _ptr(out.get("utt_embed")), _ptr(ws), ws.numel(), stream),
+              "ssb_lstm_encoder_forward")
+        return out
 
 
 def op_conv1d(x, offsets, w, b, dilation=1, act=0):

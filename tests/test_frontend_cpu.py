@@ -1,6 +1,7 @@
 """f3 front-end oracle (oracle/frontend_oracle.py) against what can be checked without librosa: scipy's STFT and the defining
 properties of the Slaney mel filterbank."""
 import numpy as np
+import pytest
 import scipy.signal
 
 from oracle import frontend_oracle as FO
@@ -47,3 +48,50 @@ def test_wav2mel_shape_and_floor():
     y = np.zeros(5000, np.float32)
     m = FO.wav2mel(y)
     assert m.shape == (1 + 5000 // 256, 80) and np.allclose(m, -6.0)  # log10(eps)
+
+
+# ---- emotion-encoder half: restatements pinned by the unmodified reference (tests/golden/ref_emotion_encoder.npz) -------------
+def _emo_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_emotion_encoder.npz"))
+
+
+def test_lstm_oracle_matches_the_reference_encoder():
+    g = _emo_golden()
+    sd = FO.emotion_encoder_weights(int(g["seed"]))
+    hidden = FO.lstm_hidden(g["frames"], sd)
+    assert hidden.shape == g["hidden"].shape == (5, 256)
+    assert np.abs(hidden - g["hidden"]).max() < 2e-7          # torch fp32 LSTM vs this float64 restatement
+    assert np.abs(FO.emotion_embeds(hidden, sd) - g["embeds"]).max() < 5e-7
+    assert np.abs(FO.utterance_embed(g["hidden"]) - g["utt_embed"]).max() < 1e-7
+
+
+def test_partial_slices_match_the_reference_and_the_host_mirror():
+    from stylesinger_b200 import emotion
+    g = _emo_golden()["slices"]
+    for n in np.unique(g[:, 0]):
+        want = g[g[:, 0] == n][:, 1:]
+        wav, mel = FO.compute_partial_slices(int(n))
+        assert np.array_equal(np.array([[a, b, c, d] for (a, b), (c, d) in zip(wav, mel)]), want)
+        ws, ms = emotion.compute_partial_slices(int(n))
+        assert np.array_equal(np.array([[w.start, w.stop, m.start, m.stop] for w, m in zip(ws, ms)]), want)
+
+
+def test_reflect_stft_matches_scipy_and_emotion_mel_shape():
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(16000).astype(np.float32)
+    S = FO.stft(y, 400, 160, 400, pad_mode="reflect")
+    w = FO.hann_periodic(400)
+    _, _, Z = scipy.signal.stft(y.astype(np.float64), window=w, nperseg=400, noverlap=240, nfft=400, boundary="even", padded=False)
+    Z = Z * w.sum()
+    T = min(Z.shape[1], S.shape[1])
+    assert T >= S.shape[1] - 1 and np.abs(Z[:, :T] - S[:, :T]).max() < 2e-6 * np.abs(Z).max()
+    m = FO.emotion_mel(y)
+    assert m.shape == (101, 40) and m.dtype == np.float32 and (m >= 0).all()
+
+
+def test_emotion_module_refuses_to_run_without_a_model():
+    from stylesinger_b200 import emotion
+    assert not emotion.is_loaded()
+    with pytest.raises(Exception, match="Model was not loaded"):
+        emotion.embed_frames_batch(np.zeros((1, 160, 40), np.float32))

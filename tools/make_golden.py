@@ -207,10 +207,47 @@ def case_schedules(name, Ts=(4, 25, 50, 100, 200, 500)):
     print("wrote", name, len(d), "arrays")
 
 
+def case_emotion_encoder(name, partials=5, seed=71):
+    """f3: the reference's own EmotionEncoder (data_gen/tts/emotion/model.py:10-77, the network behind `emo_embed`,
+    inference/StyleSinger.py:106) with seeded random weights on seeded random 160-frame x 40-channel partials:
+    `inference` (= hidden[-1], what data_gen/tts/emotion/inference.py:54 uses), `forward` (relu(linear) L2-normalised) and
+    the utterance embedding of embed_utterance (inference.py:150-151: mean of the partial embeddings, L2-normalised)."""
+    import ref_import
+    ref_import.install(T=4)  # reference on sys.path + import shims (hparams unused by the encoder)
+    from data_gen.tts.emotion.model import EmotionEncoder
+    from oracle.frontend_oracle import emotion_encoder_weights
+    cpu = torch.device("cpu")
+    model = EmotionEncoder(cpu, cpu).eval()
+    # weights: numpy legacy RandomState stream (stable across versions), loaded the stock way; the fixture then only holds
+    # inputs and outputs and the tests regenerate the same weights from the seed
+    sd = emotion_encoder_weights(seed)
+    missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not [k for k in missing.missing_keys if k.startswith(("lstm.", "linear."))], missing
+    g = torch.Generator().manual_seed(seed + 1)
+    frames = (torch.randn(partials, 160, 40, generator=g).abs() * 0.3).float()
+    with torch.no_grad():
+        hidden = model.inference(frames)
+        embeds = model.forward(frames)
+    raw = hidden.numpy().mean(axis=0)
+    d = {"seed": np.int64(seed), "frames": np32(frames), "hidden": np32(hidden), "embeds": np32(embeds),
+         "utt_embed": (raw / np.linalg.norm(raw, 2)).astype(np.float32)}
+    # partial-utterance slicing (inference.py:58-107) for a spread of lengths incl. the short / coverage-edge cases
+    from data_gen.tts.emotion.inference import compute_partial_slices
+    ns = [1, 159, 160, 8000, 19199, 19200, 25599, 25600, 31999, 32000, 38400, 44799, 44800, 48000, 160000, 163840, 479999]
+    rows = []
+    for n in ns:
+        wav_sl, mel_sl = compute_partial_slices(n)
+        for w, m in zip(wav_sl, mel_sl):
+            rows.append([n, w.start, w.stop, m.start, m.stop])
+    d["slices"] = np.asarray(rows, np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, len(d), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["small", "t25", "t100", "plms", "sched", "voc"]
+    which = sys.argv[1:] or ["small", "t25", "t100", "plms", "sched", "voc", "emo"]
     if "small" in which:
         case_model("ref_small_T4", T=4, frames=96, phones=12, ref_frames=64, seed=11, utt_idx=100)
     if "t25" in which:
@@ -223,3 +260,5 @@ if __name__ == "__main__":
         case_schedules("ref_schedules")
     if "voc" in which:
         case_vocoder("ref_vocoder_f24", frames=24, seed=31)
+    if "emo" in which:
+        case_emotion_encoder("ref_emotion_encoder")
