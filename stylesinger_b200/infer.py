@@ -73,6 +73,16 @@ class StyleSingerInfer:
         out[:min(n, len(wav))] = wav[:n]
         return out.astype(np.float16), mel
 
+    def emotion_embed(self, processed_wav, weights=None):
+        """`inp['emo_embed'] = Embed_utterance(processed_wav, using_partials=True)` of reference inference/StyleSinger.py:103-106
+        on the CUDA front-end (stylesinger_b200.emotion): ``processed_wav`` is the output of the reference's preprocess_wav
+        (16 kHz, volume-normalised, VAD-trimmed - librosa / webrtcvad, outside this package); the encoder weights come from
+        ``weights`` (path / checkpoint dict / state_dict) or hparams['emotion_encoder_path'] on first use."""
+        from . import emotion
+        if weights is not None or not emotion.is_loaded():
+            emotion.load_model(weights if weights is not None else self.hparams["emotion_encoder_path"], self.device)
+        return emotion.embed_utterance(processed_wav, using_partials=True)
+
     # ---- reference-compatible single-utterance path ------------------------------------------------
     def input_to_batch(self, item) -> PackedBatch:
         """reference inference/StyleSinger.py:139-170 (B=1 assembly).  ``item['f0']`` is the raw extractor output in Hz
