@@ -6,12 +6,13 @@
 // As kernels (fp32 FFMA; the recurrence is latency-bound, 480 dependent steps of a 1024 x 256 mat-vec per partial):
 //   * per layer the input projection of ALL frames is one plain GEMM  xproj = x W_ih^T + (b_ih + b_hh)   [P T, 1024];
 //   * the recurrence runs on one 8-CTA thread-block CLUSTER per group of up to 8 partials: CTA r keeps the W_hh rows of
-//     hidden units 32 r .. 32 r + 31 (all four gates, 128 x 256 fp32 = 128 KB) resident in shared memory for the whole
-//     sequence, computes those gates for every partial of the group, applies the cell update and writes its 32 new h values
-//     into the (double-buffered) h vector of all 8 CTAs through distributed shared memory; one cluster barrier per frame.
-//     W_hh is read from HBM once per layer instead of once per frame.
+//     hidden units 32 r .. 32 r + 31 (all four gates, 128 x 256 fp32 = 128 KB) resident in its REGISTER FILE for the whole
+//     sequence (128 registers per thread), computes those gates for every partial of the group, applies the cell update and
+//     writes its 32 new h values into the (double-buffered) h vector of all 8 CTAs through distributed shared memory; one
+//     cluster barrier per frame.  W_hh is read from HBM once per layer instead of once per frame.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <memory>
 #include <vector>
@@ -41,8 +42,8 @@ constexpr int NCTA = 8;           // cluster size
 constexpr int UPC = H / NCTA;     // hidden units per CTA (32)
 constexpr int RPC = 4 * UPC;      // gate rows per CTA (128)
 constexpr int PB = 8;             // partials per cluster
-constexpr int LSTM_THREADS = 256;
-constexpr size_t LSTM_SMEM = sizeof(float) * ((size_t)H * RPC + 2 * (size_t)H * PB + (size_t)RPC * PB);
+constexpr int LSTM_THREADS = 256;  // = 2 K halves x 128 gate rows (mat-vec role) = 8 partials x 32 units (cell role)
+constexpr int KH = H / 2;          // K range of one mat-vec thread
 
 #define RUN(x)                 \
   do {                         \
@@ -102,83 +103,145 @@ __global__ void __launch_bounds__(256) k_gemm_bias(const float* __restrict__ A, 
   }
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 4-byte store into another CTA's shared memory that reports its bytes to an mbarrier of that CTA
+__device__ __forceinline__ void st_async_f32(uint32_t dst_cluster, float v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster),
+               "r"(__float_as_uint(v)), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void hbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s watchdog: fail loudly instead of hanging the GPU
+  }
+}
+
 // One LSTM layer over T frames for partials [PB * cluster, ...).  xproj [P, T, 4H] (permuted gate columns, biases folded in),
 // whh_p [8][H][128].  hseq [P, T, H] (may be null) receives every h_t, hlast [P, H] (may be null) the final one.
+// Mat-vec role: thread (row, kh) keeps W_hh[row][kh * 128 .. + 128) in REGISTERS for the whole sequence (the CTA's 128 KB
+// slice = 128 registers per thread) and multiplies it with the h vectors of all 8 partials, read as broadcast float4s from
+// shared memory: per frame the SM issues 8 x 128 x 256 FFMAs and only 16 KB of shared-memory reads.
+// Cell role: warp `up` = partial, lane `uj` = hidden unit 32 r + uj (c in a register for the whole sequence): sums the two K
+// halves and the input projection (fetched one frame ahead), applies the gates, stores h_t into every CTA of the cluster.
+// Exchange of h_t, ASYNC = true: `st.async` stores that report their bytes to an mbarrier of the receiving CTA (one per h
+// buffer, 8 KB expected per frame); a CTA starts frame t + 1 as soon as ITS copy of h_t is complete - no cluster-wide
+// barrier.  Double buffering is enough: h_{t+1} values can only be sent by a CTA that has received all of h_t, i.e. after
+// every CTA has finished the mat-vec of frame t - 1 that read the buffer being overwritten.  ASYNC = false: plain remote
+// stores + one barrier.cluster per frame (kept as the A/B reference, SSB_LSTM_CLUSTER_BARRIER=1).
+template <bool ASYNC>
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
     k_lstm_layer(const float* __restrict__ xproj, const float* __restrict__ whh_p, int P, int T, float* __restrict__ hseq,
                  float* __restrict__ hlast) {
-  extern __shared__ __align__(16) float smem[];
-  float* Wsm = smem;                       // [H][RPC]
-  float* hsm = Wsm + (size_t)H * RPC;      // [2][H][PB]
-  float* gsm = hsm + 2 * (size_t)H * PB;   // [RPC][PB]
+  __shared__ __align__(16) float hsm[2 * H * PB];   // [2][H][PB]
+  __shared__ float gsm[2 * PB * RPC];               // [kh][partial][row]
+  __shared__ __align__(8) unsigned long long hbar[2];
   cg::cluster_group cl = cg::this_cluster();
   const int r = (int)cl.block_rank();
   const int p0 = (int)(blockIdx.x / NCTA) * PB;
   const int tid = threadIdx.x;
+  const int row = tid & (RPC - 1), kh = tid >> 7;
+  const int up = tid >> 5, uj = tid & 31;
 
-  {  // resident W_hh slice (128 KB) and zero initial state
-    const float4* src = reinterpret_cast<const float4*>(whh_p + (size_t)r * H * RPC);
-    float4* dst = reinterpret_cast<float4*>(Wsm);
-    for (int i = tid; i < H * RPC / 4; i += LSTM_THREADS) dst[i] = src[i];
-    for (int i = tid; i < 2 * H * PB; i += LSTM_THREADS) hsm[i] = 0.f;
-  }
-  // mat-vec role: gate row `row` of this CTA for partials pg * 4 .. pg * 4 + 3
-  const int row = tid & (RPC - 1), pg = tid >> 7;
-  // cell role: hidden unit 32 r + uj of partial p0 + up (its c lives in a register for the whole sequence)
-  const int up = tid & (PB - 1), uj = tid >> 3;
-  const bool cell_valid = p0 + up < P;
-  float c_state = 0.f;
-  const float* xp[4];
+  float w[KH];
+  {
+    const float* src = whh_p + ((size_t)r * H + (size_t)kh * KH) * RPC + row;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int p = min(p0 + pg * 4 + j, P - 1);  // padding partials of the last group recompute the last real one
-    xp[j] = xproj + (size_t)p * T * G4 + (size_t)r * RPC + row;
+    for (int k = 0; k < KH; ++k) w[k] = src[(size_t)k * RPC];
   }
+  for (int i = tid; i < 2 * H * PB; i += LSTM_THREADS) hsm[i] = 0.f;
+  if (ASYNC && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&hbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&hbar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  const bool cell_valid = p0 + up < P;
+  const int pc = min(p0 + up, P - 1);  // padding partials of the last group recompute the last real one
+  const float* xg = xproj + (size_t)pc * T * G4 + (size_t)r * RPC + uj;
+  float c_state = 0.f;
   float nx[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) nx[j] = xp[j][0];
+  for (int q = 0; q < 4; ++q) nx[q] = xg[q * UPC];
   float* remote[NCTA];
 #pragma unroll
   for (int d = 0; d < NCTA; ++d) remote[d] = cl.map_shared_rank(hsm, d);
+  const uint32_t hsm_a = smem_addr(hsm), bar_a = smem_addr(&hbar[0]);
   cl.sync();  // every CTA of the cluster is resident and has zeroed its h buffers before any remote write
 
   int cur = 0;
   for (int t = 0; t < T; ++t) {
-    float acc[4];
+    float xq[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = nx[j];
+    for (int q = 0; q < 4; ++q) xq[q] = nx[q];
     if (t + 1 < T) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) nx[j] = xp[j][(size_t)(t + 1) * G4];
+      for (int q = 0; q < 4; ++q) nx[q] = xg[(size_t)(t + 1) * G4 + q * UPC];
     }
-    const float* hc = hsm + (size_t)cur * H * PB + pg * 4;
-#pragma unroll 8
-    for (int k = 0; k < H; ++k) {
-      const float w = Wsm[k * RPC + row];
-      const float4 hv = *reinterpret_cast<const float4*>(hc + k * PB);
-      acc[0] = fmaf(w, hv.x, acc[0]);
-      acc[1] = fmaf(w, hv.y, acc[1]);
-      acc[2] = fmaf(w, hv.z, acc[2]);
-      acc[3] = fmaf(w, hv.w, acc[3]);
+    if (ASYNC && t > 0) hbar_wait(bar_a + 8u * (uint32_t)(t & 1), (uint32_t)(((t - 1) >> 1) & 1));  // h_{t-1} has arrived here
+    float acc[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) acc[j] = 0.f;
+    const float4* hc = reinterpret_cast<const float4*>(hsm + (size_t)cur * H * PB + (size_t)kh * KH * PB);
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+      const float4 h0 = hc[2 * k], h1 = hc[2 * k + 1];
+      acc[0] = fmaf(w[k], h0.x, acc[0]);
+      acc[1] = fmaf(w[k], h0.y, acc[1]);
+      acc[2] = fmaf(w[k], h0.z, acc[2]);
+      acc[3] = fmaf(w[k], h0.w, acc[3]);
+      acc[4] = fmaf(w[k], h1.x, acc[4]);
+      acc[5] = fmaf(w[k], h1.y, acc[5]);
+      acc[6] = fmaf(w[k], h1.z, acc[6]);
+      acc[7] = fmaf(w[k], h1.w, acc[7]);
     }
-    *reinterpret_cast<float4*>(gsm + row * PB + pg * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) gsm[(kh * PB + j) * RPC + row] = acc[j];
     __syncthreads();
     {
-      const float gi = gsm[(0 * UPC + uj) * PB + up], gf = gsm[(1 * UPC + uj) * PB + up];
-      const float gg = gsm[(2 * UPC + uj) * PB + up], go = gsm[(3 * UPC + uj) * PB + up];
+      const float* g0 = gsm + up * RPC + uj;
+      const float* g1 = g0 + PB * RPC;
+      const float gi = xq[0] + (g0[0 * UPC] + g1[0 * UPC]), gf = xq[1] + (g0[1 * UPC] + g1[1 * UPC]);
+      const float gg = xq[2] + (g0[2 * UPC] + g1[2 * UPC]), go = xq[3] + (g0[3 * UPC] + g1[3 * UPC]);
       c_state = sigmoidf_(gf) * c_state + sigmoidf_(gi) * tanhf(gg);
       const float h = sigmoidf_(go) * tanhf(c_state);
       const int off = (cur ^ 1) * H * PB + (r * UPC + uj) * PB + up;
+      if (ASYNC) {
+        if (t + 1 < T) {
+          const uint32_t nb = 8u * (uint32_t)((t + 1) & 1);
+          // arm the barrier frame t + 1 waits on: everybody's 32 units x 8 partials x 4 bytes.  Its previous phase (frame
+          // t - 1) has completed (this thread waited on it); bytes that arrive before the arming are simply counted first
+          if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + nb), "r"((uint32_t)(H * PB * 4)) : "memory");
 #pragma unroll
-      for (int d = 0; d < NCTA; ++d) remote[d][off] = h;
+          for (int d = 0; d < NCTA; ++d)
+            st_async_f32(map_rank(hsm_a + 4u * (uint32_t)off, (uint32_t)d), h, map_rank(bar_a + nb, (uint32_t)d));
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < NCTA; ++d) remote[d][off] = h;
+      }
       if (cell_valid) {
         if (hseq) hseq[((size_t)(p0 + up) * T + t) * H + r * UPC + uj] = h;
         if (hlast && t == T - 1) hlast[(size_t)(p0 + up) * H + r * UPC + uj] = h;
       }
     }
-    cl.sync();  // h_t complete in every CTA; gsm and the old h buffer are free again
+    if (!ASYNC) cl.sync();  // h_t complete in every CTA; gsm and the old h buffer are free again
     cur ^= 1;
   }
+  if (ASYNC) cl.sync();  // nobody leaves while a neighbour could still be storing into its shared memory
 }
 
 // relu(linear(h)) L2-normalised per partial (model.py:51-57); one block of 256 threads per partial
@@ -234,17 +297,12 @@ int run_lstm(Ctx& c, const ssb_lstm_encoder& m, const float* frames, int P, int 
   int32_t* offs_dev = c.alloc<int32_t>((size_t)U + 1);
   SSB_CHECK(c.dry || !c.failed, "workspace too small");
   if (c.dry || P == 0) return 0;
-  static thread_local int attr_dev = -1;
-  int dev = 0;
-  SSB_CUDA(cudaGetDevice(&dev));
-  if (attr_dev != dev) {
-    SSB_CUDA(cudaFuncSetAttribute(k_lstm_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSTM_SMEM));
-    attr_dev = dev;
-  }
   float* hid = hidden_out ? hidden_out : hid_ws;
   const float* x = frames;
   int K = m.n_in;
   const unsigned groups = (unsigned)((P + PB - 1) / PB);
+  const char* cb = getenv("SSB_LSTM_CLUSTER_BARRIER");  // A/B: 1 = one barrier.cluster per frame instead of mbarrier-signalled stores
+  const bool cluster_barrier = cb && cb[0] == '1';
   for (int l = 0; l < m.layers; ++l) {
     k_gemm_bias<<<dim3(G4 / 64, (unsigned)((rows + 63) / 64)), 256, 0, c.stream>>>(x, m.wih_t[(size_t)l], m.bias[(size_t)l], xproj,
                                                                                    (int64_t)rows, G4, K);
@@ -252,7 +310,10 @@ int run_lstm(Ctx& c, const ssb_lstm_encoder& m, const float* frames, int P, int 
     ++g_launches;
     const bool last = l == m.layers - 1;
     float* out_seq = last ? nullptr : ((l & 1) ? seq_b : seq_a);
-    k_lstm_layer<<<groups * NCTA, LSTM_THREADS, LSTM_SMEM, c.stream>>>(xproj, m.whh_p[(size_t)l], P, T, out_seq, last ? hid : nullptr);
+    if (cluster_barrier)
+      k_lstm_layer<false><<<groups * NCTA, LSTM_THREADS, 0, c.stream>>>(xproj, m.whh_p[(size_t)l], P, T, out_seq, last ? hid : nullptr);
+    else
+      k_lstm_layer<true><<<groups * NCTA, LSTM_THREADS, 0, c.stream>>>(xproj, m.whh_p[(size_t)l], P, T, out_seq, last ? hid : nullptr);
     SSB_CUDA(cudaGetLastError());
     ++g_launches;
     x = out_seq;
