@@ -42,8 +42,7 @@ constexpr int NCTA = 8;           // cluster size
 constexpr int UPC = H / NCTA;     // hidden units per CTA (32)
 constexpr int RPC = 4 * UPC;      // gate rows per CTA (128)
 constexpr int PB = 8;             // partials per cluster
-constexpr int LSTM_THREADS = 256;  // = 2 K halves x 128 gate rows (mat-vec role) = 8 partials x 32 units (cell role)
-constexpr int KH = H / 2;          // K range of one mat-vec thread
+constexpr int CELL_THREADS = PB * UPC;  // cell role: 8 partials x 32 units = 256 threads
 
 #define RUN(x)                 \
   do {                         \
@@ -141,12 +140,14 @@ __device__ __forceinline__ void hbar_wait(uint32_t bar, uint32_t parity) {
 // barrier.  Double buffering is enough: h_{t+1} values can only be sent by a CTA that has received all of h_t, i.e. after
 // every CTA has finished the mat-vec of frame t - 1 that read the buffer being overwritten.  ASYNC = false: plain remote
 // stores + one barrier.cluster per frame (kept as the A/B reference, SSB_LSTM_CLUSTER_BARRIER=1).
-template <bool ASYNC>
-__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
+// KQ = K splits of the mat-vec: RPC * KQ threads, each with H / KQ weights in registers.
+template <bool ASYNC, int KQ>
+__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(RPC * KQ, 1)
     k_lstm_layer(const float* __restrict__ xproj, const float* __restrict__ whh_p, int P, int T, float* __restrict__ hseq,
                  float* __restrict__ hlast) {
   __shared__ __align__(16) float hsm[2 * H * PB];   // [2][H][PB]
-  __shared__ float gsm[2 * PB * RPC];               // [kh][partial][row]
+  constexpr int LSTM_THREADS = RPC * KQ, KH = H / KQ;
+  __shared__ float gsm[KQ * PB * RPC];              // [kh][partial][row]
   __shared__ __align__(8) unsigned long long hbar[2];
   cg::cluster_group cl = cg::this_cluster();
   const int r = (int)cl.block_rank();
@@ -169,12 +170,15 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
   }
 
   const bool cell_valid = p0 + up < P;
-  const int pc = min(p0 + up, P - 1);  // padding partials of the last group recompute the last real one
+  const int pc = min(p0 + min(up, PB - 1), P - 1);  // padding partials of the last group recompute the last real one
   const float* xg = xproj + (size_t)pc * T * G4 + (size_t)r * RPC + uj;
   float c_state = 0.f;
-  float nx[4];
+  const bool is_cell = tid < CELL_THREADS;
+  float nx[4] = {0.f, 0.f, 0.f, 0.f};
+  if (is_cell) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) nx[q] = xg[q * UPC];
+    for (int q = 0; q < 4; ++q) nx[q] = xg[q * UPC];
+  }
   float* remote[NCTA];
 #pragma unroll
   for (int d = 0; d < NCTA; ++d) remote[d] = cl.map_shared_rank(hsm, d);
@@ -186,7 +190,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
     float xq[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) xq[q] = nx[q];
-    if (t + 1 < T) {
+    if (is_cell && t + 1 < T) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) nx[q] = xg[(size_t)(t + 1) * G4 + q * UPC];
     }
@@ -210,11 +214,17 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
 #pragma unroll
     for (int j = 0; j < PB; ++j) gsm[(kh * PB + j) * RPC + row] = acc[j];
     __syncthreads();
-    {
+    if (tid < CELL_THREADS) {
       const float* g0 = gsm + up * RPC + uj;
-      const float* g1 = g0 + PB * RPC;
-      const float gi = xq[0] + (g0[0 * UPC] + g1[0 * UPC]), gf = xq[1] + (g0[1 * UPC] + g1[1 * UPC]);
-      const float gg = xq[2] + (g0[2 * UPC] + g1[2 * UPC]), go = xq[3] + (g0[3 * UPC] + g1[3 * UPC]);
+      float gs[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float a = g0[q * UPC];
+#pragma unroll
+        for (int h2 = 1; h2 < KQ; ++h2) a += g0[h2 * PB * RPC + q * UPC];
+        gs[q] = xq[q] + a;
+      }
+      const float gi = gs[0], gf = gs[1], gg = gs[2], go = gs[3];
       c_state = sigmoidf_(gf) * c_state + sigmoidf_(gi) * tanhf(gg);
       const float h = sigmoidf_(go) * tanhf(c_state);
       const int off = (cur ^ 1) * H * PB + (r * UPC + uj) * PB + up;
@@ -303,6 +313,8 @@ int run_lstm(Ctx& c, const ssb_lstm_encoder& m, const float* frames, int P, int 
   const unsigned groups = (unsigned)((P + PB - 1) / PB);
   const char* cb = getenv("SSB_LSTM_CLUSTER_BARRIER");  // A/B: 1 = one barrier.cluster per frame instead of mbarrier-signalled stores
   const bool cluster_barrier = cb && cb[0] == '1';
+  const char* k4 = getenv("SSB_LSTM_KSPLIT4");  // A/B: 512 threads, four K quarters per gate row
+  const bool ksplit4 = k4 && k4[0] == '1';
   for (int l = 0; l < m.layers; ++l) {
     k_gemm_bias<<<dim3(G4 / 64, (unsigned)((rows + 63) / 64)), 256, 0, c.stream>>>(x, m.wih_t[(size_t)l], m.bias[(size_t)l], xproj,
                                                                                    (int64_t)rows, G4, K);
@@ -310,10 +322,14 @@ int run_lstm(Ctx& c, const ssb_lstm_encoder& m, const float* frames, int P, int 
     ++g_launches;
     const bool last = l == m.layers - 1;
     float* out_seq = last ? nullptr : ((l & 1) ? seq_b : seq_a);
+    float* hl = last ? hid : nullptr;
+    const float* wp = m.whh_p[(size_t)l];
     if (cluster_barrier)
-      k_lstm_layer<false><<<groups * NCTA, LSTM_THREADS, 0, c.stream>>>(xproj, m.whh_p[(size_t)l], P, T, out_seq, last ? hid : nullptr);
+      k_lstm_layer<false, 2><<<groups * NCTA, RPC * 2, 0, c.stream>>>(xproj, wp, P, T, out_seq, hl);
+    else if (ksplit4)
+      k_lstm_layer<true, 4><<<groups * NCTA, RPC * 4, 0, c.stream>>>(xproj, wp, P, T, out_seq, hl);
     else
-      k_lstm_layer<true><<<groups * NCTA, LSTM_THREADS, 0, c.stream>>>(xproj, m.whh_p[(size_t)l], P, T, out_seq, last ? hid : nullptr);
+      k_lstm_layer<true, 2><<<groups * NCTA, RPC * 2, 0, c.stream>>>(xproj, wp, P, T, out_seq, hl);
     SSB_CUDA(cudaGetLastError());
     ++g_launches;
     x = out_seq;

@@ -1,5 +1,5 @@
-"""Drive the LSTM encoder (12 partials x 160 frames): ncu target (profiles/r02_ncu_lstm.md) and A/B timing of the h exchange
-(SSB_LSTM_CLUSTER_BARRIER=1: one barrier.cluster per frame; default: mbarrier-signalled st.async)."""
+"""Drive the LSTM encoder (12 partials x 160 frames): ncu target (profiles/r02_ncu_lstm.md) and A/B timing of the kernel variants.
+usage: lstm_probe.py [reps] [mode ...]   modes: async2 (default kernel), barrier2 (SSB_LSTM_CLUSTER_BARRIER=1), async4 (SSB_LSTM_KSPLIT4=1)"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,12 +7,16 @@ import torch
 from oracle import frontend_oracle as FO  # seeded synthetic state_dict only; a tool, not the product
 from stylesinger_b200.engine import LstmEncoder
 
+ENV = {"async2": {}, "barrier2": {"SSB_LSTM_CLUSTER_BARRIER": "1"}, "async4": {"SSB_LSTM_KSPLIT4": "1"}}
 enc = LstmEncoder(FO.emotion_encoder_weights(71), "cuda:0")
-x = torch.rand(12, 160, 40, device="cuda:0")
+x = torch.rand(12, 160, 40, generator=torch.Generator().manual_seed(0)).to("cuda:0")
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-res = {}
-for mode in ("0", "1"):
-    os.environ["SSB_LSTM_CLUSTER_BARRIER"] = mode
+modes = sys.argv[2:] or list(ENV)
+ref = torch.from_numpy(FO.lstm_hidden(x.cpu().numpy(), FO.emotion_encoder_weights(71))).to("cuda:0")
+for mode in modes:
+    for k in ("SSB_LSTM_CLUSTER_BARRIER", "SSB_LSTM_KSPLIT4"):
+        os.environ.pop(k, None)
+    os.environ.update(ENV[mode])
     for _ in range(3):
         out = enc(x, utt_offsets=[0, 12])
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -21,6 +25,5 @@ for mode in ("0", "1"):
         out = enc(x, utt_offsets=[0, 12])
     ev[1].record()
     torch.cuda.synchronize()
-    res[mode] = out["hidden"].clone()
-    print(f"SSB_LSTM_CLUSTER_BARRIER={mode}: {ev[0].elapsed_time(ev[1]) / reps:.3f} ms per call (12 partials x 160 frames, 3 layers)")
-print("max |async - barrier| =", float((res["0"] - res["1"]).abs().max()))
+    print(f"{mode}: {ev[0].elapsed_time(ev[1]) / reps:.3f} ms per call (12 partials x 160 frames, 3 layers), "
+          f"max |hidden - float64 oracle| = {float((out['hidden'] - ref).abs().max()):.3e}")
