@@ -251,7 +251,7 @@ int ssb_mel_postprocess(float* mel, int64_t n_frames, float vmin, float vmax, in
  * Replaces utils/audios/__init__.py:36-84 librosa_wav2spec as called by inference/StyleSinger.py:79-92 (process_audio):
  * librosa.stft(center=True, pad_mode="constant", periodic Hann window) -> |.| -> librosa.filters.mel (Slaney scale and
  * normalisation, built inside create) -> log10(max(eps, .)).  fmin / fmax < 0 mean 0 / sample_rate / 2 like the reference.
- * Constraints of the implicit-GEMM formulation: fft_size even, fft_size <= 8 hop_size, hop_size a multiple of 16, n_mels of 4
+ * Constraints of the implicit-GEMM formulation: fft_size even, fft_size <= 32 hop_size (16 with reflect centring), hop_size a multiple of 16, n_mels of 4
  * (egs/stylesinger.yaml: 48 kHz, fft 1024, hop 256, win 1024, 80 mels, 20..24000 Hz).  An utterance of n samples yields
  * ssb_melspec_num_frames = 1 + n / hop_size frames.  wav: device fp32, utterances concatenated, sample_offsets: host [B+1];
  * mel_out: device fp32 [sum frames, n_mels].  loud_norm / trim_long_sil of the reference are not implemented (both false in

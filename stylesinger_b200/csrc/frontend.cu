@@ -53,7 +53,7 @@ __global__ void k_wav_rows(const int4* utt, const int32_t* sample_offs, const fl
   rows[(int64_t)u.x * hop + i] = i < n ? wav[(int64_t)sample_offs[b] + i] : 0.f;
 }
 // np.pad(y, n_fft / 2, mode="reflect") of librosa.stft's default centring: sample -i is y[i], sample n - 1 + i is y[n - 1 - i].
-// Written into the guard rows in front of the utterance and behind its last sample (pad <= 2 rows each side; the 16 guard
+// Written into the guard rows in front of the utterance and behind its last sample (pad <= 8 rows each side; the 16 guard
 // rows between neighbours keep the two utterances' pads apart).  Like numpy, needs n > pad.
 __global__ void k_wav_reflect(const int4* utt, const int32_t* sample_offs, const float* wav, int hop, int pad, float* rows) {
   const int b = blockIdx.y;
@@ -186,7 +186,9 @@ int ssb_melspec_create_ex(ssb_melspec_t** out, int32_t sample_rate, int32_t fft_
   // DFT weights of the `lead` samples in front of / behind the n_fft window are zero
   const int span = (fft_size + 2 * hop_size - 1) / (2 * hop_size) * (2 * hop_size);
   const int lead = (span - fft_size) / 2;
-  SSB_CHECK(span / hop_size / 2 <= 4 && span / hop_size / 2 <= GUARD, "n_fft / hop_size too large for the guard band");
+  // the frame reaches taps / 2 rows into the guard band on either side; with reflect centring both neighbours WRITE their
+  // pads into the guard rows they share, so the two pads together must fit
+  SSB_CHECK(span / hop_size / 2 <= (pad_reflect ? GUARD / 2 : GUARD), "n_fft / hop_size too large for the guard band");
   SSB_CHECK(n_mels % 4 == 0, "n_mels must be a multiple of 4");
   std::unique_ptr<ssb_melspec> m(new ssb_melspec);
   m->sample_rate = sample_rate; m->n_fft = fft_size; m->hop = hop_size; m->win = win_length; m->n_mels = n_mels;
