@@ -447,7 +447,7 @@ int run_style(Ctx& c, const Model& m, const SeqDev& sf, const SeqDev& sr, const 
 // SIMT path: fp32 conv_gemm.  Tensor-core path (b.tc): tcgen05 GEMMs on fp16 hi/lo planes.
 // The two tcgen05 GEMMs of residual layer l over the row tiles [tiles, tiles + ntiles) (net.py:66-78)
 static GemmTC layer_gate_gemm(const Denoiser& d, const DenoiserBufs& b, int64_t rows, const int2* tiles, int ntiles, int l) {
-  const int C = d.C, L = d.L;
+  const int C = d.C;
   GemmTC g;
   g.A_hi = b.yh; g.A_lo = b.yl; g.rows_total = rows; g.w = &d.layers[l].dil_tc; g.tiles = tiles; g.ntiles = ntiles;
   if (b.condpre) {  // conditioner hoisted: K = 3*C only, the projection arrives as an epilogue addend (one [rows, 2C] matrix per layer)
