@@ -137,6 +137,28 @@ def norm_interp_f0(f0_hz: np.ndarray, pitch_norm: str = "log", use_uv: bool = Tr
     return f0.astype(np.float32), uv.astype(np.float32)
 
 
+def pad_f0_to_mel(f0: np.ndarray, n_mel: int, hop_size: int) -> np.ndarray:
+    """The f0 track of the pitch extractor aligned to the mel frames, reference inference/StyleSinger.py:116-137 (the lines after
+    the parselmouth call): hop 128 -> pad_size 4, hop 256 -> pad_size 2 (anything else is refused like the reference's
+    ``assert False``), 2 * pad_size zero frames in front, zeros behind up to ``n_mel`` frames, |length difference| <= 8 asserted,
+    the last value repeated if still short, cut to ``n_mel``."""
+    if hop_size == 128:
+        pad_size = 4
+    elif hop_size == 256:
+        pad_size = 2
+    else:
+        raise AssertionError("hop_size must be 128 or 256 (inference/StyleSinger.py:120-125)")
+    f0 = np.asarray(f0)
+    lpad = pad_size * 2
+    rpad = n_mel - len(f0) - lpad
+    f0 = np.pad(f0, [[lpad, rpad]], mode="constant")  # like the reference, a track longer than the mel raises here
+    delta_l = n_mel - len(f0)
+    assert np.abs(delta_l) <= 8
+    if delta_l > 0:
+        f0 = np.concatenate([f0, [f0[-1]] * delta_l], 0)
+    return f0[:n_mel]
+
+
 def item_to_utterance(item: dict, hparams: dict, with_mel2ph: bool = True) -> Dict[str, torch.Tensor]:
     """One binarised dataset item -> the utterance dict ``engine.pack_batch`` takes, following the test-time sample
     assembly of tasks/StyleSinger/dataset.py (BaseDataset.__getitem__ :41-66, BaseSingerdataset :100-130,

@@ -14,7 +14,7 @@ import torch
 
 from ._lib import check, lib
 from .engine import AcousticModel, PackedBatch, Vocoder, pack_batch
-from .formats import norm_interp_f0
+from .formats import norm_interp_f0, pad_f0_to_mel
 from .hparams import resolve
 
 
@@ -82,6 +82,43 @@ class StyleSingerInfer:
         if weights is not None or not emotion.is_loaded():
             emotion.load_model(weights if weights is not None else self.hparams["emotion_encoder_path"], self.device)
         return emotion.embed_utterance(processed_wav, using_partials=True)
+
+    def preprocess_input(self, inp, spk_embed_fn=None, pitch_fn=None, preprocess_wav_fn=None):
+        """reference inference/StyleSinger.py:94-137 with the reference-owned arithmetic on the GPU (log-mel of the reference
+        audio, emotion embedding) and the third-party models as callables, since their packages are not part of this one:
+
+        * ``inp['ref_audio']``: the decoded reference waveform at hparams['audio_sample_rate'] (the reference passes a path and
+          lets librosa decode it);
+        * ``spk_embed_fn(wav)`` = ``VoiceEncoder().embed_utterance`` (resemblyzer), or ``inp['spk_embed']`` given;
+        * ``preprocess_wav_fn(ref_audio)`` = ``data_gen.tts.emotion.inference.preprocess_wav`` (librosa + webrtcvad) feeding
+          ``emotion_embed`` (hparams['emotion_encoder_path']), or ``inp['emo_embed']`` given;
+        * ``pitch_fn(wav, sample_rate, time_step_s, f0_min, f0_max, voicing_threshold)`` = the parselmouth ``to_pitch_ac``
+          call (:126-129) returning Hz per frame, or ``inp['f0']`` given (already aligned to the mel).
+
+        Fills ``mel``, ``spk_embed``, ``emo_embed``, ``item_name``, ``ph_token``, ``wav_fn``, ``f0`` like the reference."""
+        hp = self.hparams
+        if self.ph_encoder is None:
+            raise ValueError("preprocess_input needs the ph_encoder (utils/text/text_encoder.py build_token_encoder)")
+        ph_token = self.ph_encoder.encode(" ".join(inp["ph"]))
+        ref_audio = inp["ref_audio"]
+        wav, mel = self.process_audio(ref_audio)
+        inp["mel"] = mel
+        if spk_embed_fn is not None:
+            inp["spk_embed"] = spk_embed_fn(wav)
+        elif "spk_embed" not in inp:
+            raise ValueError("spk_embed_fn or inp['spk_embed'] required (resemblyzer VoiceEncoder is third-party)")
+        if preprocess_wav_fn is not None:
+            inp["emo_embed"] = self.emotion_embed(preprocess_wav_fn(ref_audio))
+        elif "emo_embed" not in inp:
+            raise ValueError("preprocess_wav_fn or inp['emo_embed'] required")
+        inp.update({"item_name": inp["name"], "ph_token": ph_token, "wav_fn": ref_audio})
+        if pitch_fn is not None:
+            time_step = hp["hop_size"] / hp["audio_sample_rate"] * 1000
+            f0 = pitch_fn(wav, hp["audio_sample_rate"], time_step / 1000, 80, 800, 0.6)
+            inp["f0"] = pad_f0_to_mel(f0, len(mel), hp["hop_size"])
+        elif "f0" not in inp:
+            raise ValueError("pitch_fn or inp['f0'] required (parselmouth is third-party)")
+        return inp
 
     # ---- reference-compatible single-utterance path ------------------------------------------------
     def input_to_batch(self, item) -> PackedBatch:

@@ -180,3 +180,50 @@ def test_item_to_utterance_feeds_pack_batch():
     pb = pack_batch(utts)
     assert pb.B == 3 and int(pb.frame_offsets[-1]) == sum(len(it["f0"]) for it in items)
     assert int(pb.ph_offsets[-1]) == sum(len(it["ph_token"]) for it in items)
+
+
+def test_pad_f0_to_mel_follows_the_reference_lines():
+    """inference/StyleSinger.py:116-137, restated inline the way the reference writes it."""
+    from stylesinger_b200.formats import pad_f0_to_mel
+    rng = np.random.default_rng(0)
+    for hop, pad_size in ((256, 2), (128, 4)):
+        for n_mel, n_f0 in ((100, 96 - 2 * pad_size + 4), (57, 57 - 2 * pad_size), (40, 30)):
+            f0 = rng.uniform(80, 800, n_f0)
+            lpad = pad_size * 2
+            ref = np.pad(f0, [[lpad, n_mel - len(f0) - lpad]], mode="constant")[:n_mel]
+            got = pad_f0_to_mel(f0, n_mel, hop)
+            assert got.shape == (n_mel,) and np.array_equal(got, ref) and (got[:lpad] == 0).all()
+    with pytest.raises(AssertionError):
+        pad_f0_to_mel(np.zeros(10), 20, 512)
+    with pytest.raises(ValueError):      # a track longer than the mel: np.pad refuses the negative pad, as in the reference
+        pad_f0_to_mel(np.zeros(30), 20, 256)
+
+
+def test_preprocess_input_glue_with_stand_in_front_end():
+    """StyleSingerInfer.preprocess_input: the reference's field names and call order, third-party pieces as callables.
+    (The GPU pieces it calls - process_audio, emotion_embed - have their own parity tests.)"""
+    from stylesinger_b200.infer import StyleSingerInfer
+
+    class Enc:
+        def encode(self, s):
+            return [len(w) for w in s.split(" ")]
+
+    eng = StyleSingerInfer.__new__(StyleSingerInfer)
+    eng.hparams = {"hop_size": 256, "audio_sample_rate": 48000}
+    eng.ph_encoder = Enc()
+    calls = []
+    eng.process_audio = lambda wav: (np.asarray(wav, np.float16), np.zeros((50, 80), np.float32))
+    eng.emotion_embed = lambda w: calls.append(("emo", len(w))) or np.ones(256, np.float32)
+
+    def pitch(wav, sr, step, fmin, fmax, thr):
+        calls.append(("pitch", sr, round(step, 6), fmin, fmax, thr))
+        return np.full(44, 220.0)
+
+    inp = {"name": "x", "ph": ["a", "bb", "ccc"], "ref_audio": np.zeros(12800, np.float32)}
+    out = eng.preprocess_input(inp, spk_embed_fn=lambda w: np.zeros(256, np.float32), pitch_fn=pitch,
+                               preprocess_wav_fn=lambda a: a[:1000])
+    assert out is inp and out["ph_token"] == [1, 2, 3] and out["item_name"] == "x" and out["mel"].shape == (50, 80)
+    assert out["f0"].shape == (50,) and (out["f0"][:4] == 0).all() and (out["f0"][4:48] == 220).all() and (out["f0"][48:] == 0).all()
+    assert calls == [("emo", 1000), ("pitch", 48000, round(256 / 48000, 6), 80, 800, 0.6)]
+    with pytest.raises(ValueError, match="spk_embed"):
+        eng.preprocess_input({"name": "y", "ph": ["a"], "ref_audio": np.zeros(10, np.float32)})
