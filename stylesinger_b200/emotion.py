@@ -67,19 +67,22 @@ def embed_frames_batch(frames_batch):
 
 
 def compute_partial_slices(n_samples, partial_utterance_n_frames=partials_n_frames, min_pad_coverage=0.75, overlap=0.5):
-    """inference.py:58-107: (wav_slices, mel_slices) as lists of python slices."""
-    assert 0 <= overlap < 1
-    assert 0 < min_pad_coverage <= 1
-    samples_per_frame = int(sampling_rate * mel_window_step / 1000)
-    n_frames = int(np.ceil((n_samples + 1) / samples_per_frame))
-    frame_step = max(int(np.round(partial_utterance_n_frames * (1 - overlap))), 1)
-    steps = max(1, n_frames - partial_utterance_n_frames + frame_step + 1)
-    mel_slices = [slice(i, i + partial_utterance_n_frames) for i in range(0, steps, frame_step)]
-    wav_slices = [slice(s.start * samples_per_frame, s.stop * samples_per_frame) for s in mel_slices]
-    last = wav_slices[-1]
-    coverage = (n_samples - last.start) / (last.stop - last.start)
-    if coverage < min_pad_coverage and len(mel_slices) > 1:
-        mel_slices, wav_slices = mel_slices[:-1], wav_slices[:-1]
+    """inference.py:58-107: (wav_slices, mel_slices) as lists of python slices.  Partials start every
+    round(frames * (1 - overlap)) mel frames; the last one is dropped when less than ``min_pad_coverage`` of it lies inside
+    the waveform (unless it is the only one)."""
+    if not (0 <= overlap < 1 and 0 < min_pad_coverage <= 1):
+        raise AssertionError("overlap in [0, 1), min_pad_coverage in (0, 1]")
+    hop = sampling_rate * mel_window_step // 1000                       # samples per mel frame
+    total_frames = -(-(n_samples + 1) // hop)                           # ceil
+    stride = max(int(np.round(partial_utterance_n_frames * (1 - overlap))), 1)
+    last_start_bound = max(1, total_frames - partial_utterance_n_frames + stride + 1)
+    starts = list(range(0, last_start_bound, stride))
+    if len(starts) > 1:
+        inside = n_samples - starts[-1] * hop                           # samples of the last partial that exist
+        if inside / (partial_utterance_n_frames * hop) < min_pad_coverage:
+            starts.pop()
+    mel_slices = [slice(f, f + partial_utterance_n_frames) for f in starts]
+    wav_slices = [slice(f * hop, (f + partial_utterance_n_frames) * hop) for f in starts]
     return wav_slices, mel_slices
 
 
@@ -87,19 +90,17 @@ def embed_utterance(wav, using_partials=True, return_partials=False, **kwargs):
     """inference.py:110-155.  The waveform goes to the GPU once; mel frames, partial batch, LSTM and the normalised mean stay
     on the device, only the 256 (+ partials) floats come back."""
     _need_model()
-    wav = np.asarray(wav, np.float32).reshape(-1)
-    if not using_partials:
-        frames = wav_to_mel_spectrogram(wav, device_out=True)
-        embed = _model(frames[None])["hidden"][0].cpu().numpy()
-        return (embed, None, None) if return_partials else embed
-    wave_slices, mel_slices = compute_partial_slices(len(wav), **kwargs)
-    max_wave_length = wave_slices[-1].stop
-    if max_wave_length >= len(wav):
-        wav = np.pad(wav, (0, max_wave_length - len(wav)), "constant")
-    frames = wav_to_mel_spectrogram(wav, device_out=True)
-    frames_batch = torch.stack([frames[s] for s in mel_slices])
-    out = _model(frames_batch, utt_offsets=[0, len(mel_slices)])
-    embed = out["utt_embed"][0].cpu().numpy()
-    if return_partials:
-        return embed, out["hidden"].cpu().numpy(), wave_slices
-    return embed
+    samples = np.asarray(wav, np.float32).reshape(-1)
+    if using_partials:
+        wave_slices, mel_slices = compute_partial_slices(len(samples), **kwargs)
+        short = wave_slices[-1].stop - len(samples)
+        if short >= 0:                                   # :141-142 (zero-pad up to the end of the last partial)
+            samples = np.concatenate([samples, np.zeros(short, np.float32)])
+        frames = wav_to_mel_spectrogram(samples, device_out=True)
+        batch = torch.stack([frames[s] for s in mel_slices])
+        res = _model(batch, utt_offsets=[0, len(mel_slices)])   # mean of the partial embeddings, L2-normalised (:150-151)
+        embed = res["utt_embed"][0].cpu().numpy()
+        return (embed, res["hidden"].cpu().numpy(), wave_slices) if return_partials else embed
+    frames = wav_to_mel_spectrogram(samples, device_out=True)    # :129-134: the whole spectrogram as one sequence
+    embed = _model(frames[None])["hidden"][0].cpu().numpy()
+    return (embed, None, None) if return_partials else embed
