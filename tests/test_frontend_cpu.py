@@ -95,3 +95,36 @@ def test_emotion_module_refuses_to_run_without_a_model():
     assert not emotion.is_loaded()
     with pytest.raises(Exception, match="Model was not loaded"):
         emotion.embed_frames_batch(np.zeros((1, 160, 40), np.float32))
+
+
+def test_embed_utterance_glue_with_stand_in_kernels(monkeypatch):
+    """emotion.embed_utterance host flow (padding, partial batch, return values) with the oracle standing in for the two CUDA
+    objects: must equal the reference's composition of the same pieces (inference.py:110-155)."""
+    import torch
+    from stylesinger_b200 import emotion
+    sd = FO.emotion_encoder_weights(3)
+
+    def fake_mel(wav):
+        return torch.from_numpy(FO.emotion_mel(np.asarray(wav, np.float32)))
+
+    def fake_model(frames, utt_offsets=None, want_embeds=False):
+        hid = FO.lstm_hidden(np.asarray(frames), sd)
+        out = {"hidden": torch.from_numpy(hid)}
+        if utt_offsets is not None:
+            out["utt_embed"] = torch.from_numpy(np.stack([FO.utterance_embed(hid[a:b]) for a, b in zip(utt_offsets[:-1], utt_offsets[1:])]))
+        return out
+
+    monkeypatch.setattr(emotion, "_mel", fake_mel)
+    monkeypatch.setattr(emotion, "_model", fake_model)
+    rng = np.random.default_rng(5)
+    for n in (3000, 30000):
+        y = (0.1 * rng.standard_normal(n)).astype(np.float32)
+        wav_sl, mel_sl = FO.compute_partial_slices(n)
+        fr = FO.emotion_mel(np.pad(y, (0, max(0, wav_sl[-1][1] - n))))
+        hid = FO.lstm_hidden(np.stack([fr[a:b] for a, b in mel_sl]), sd)
+        emb, partials, wave_slices = emotion.embed_utterance(y, return_partials=True)
+        assert np.allclose(emb, FO.utterance_embed(hid), atol=1e-7) and np.allclose(partials, hid, atol=1e-7)
+        assert [(s.start, s.stop) for s in wave_slices] == wav_sl
+        assert np.allclose(emotion.embed_utterance(y), emb)
+        whole, p2, s2 = emotion.embed_utterance(y, using_partials=False, return_partials=True)
+        assert p2 is None and s2 is None and np.allclose(whole, FO.lstm_hidden(FO.emotion_mel(y)[None], sd)[0], atol=1e-7)
