@@ -306,6 +306,7 @@ int run_lstm(Ctx& c, const ssb_lstm_encoder& m, const float* frames, int P, int 
   float* hid_ws = c.alloc<float>((size_t)P * H);
   int32_t* offs_dev = c.alloc<int32_t>((size_t)U + 1);
   SSB_CHECK(c.dry || !c.failed, "workspace too small");
+  SSB_CHECK((rows + 63) / 64 <= 65535, "too many frames for one call (n_partials * n_frames <= 4 194 240)");
   if (c.dry || P == 0) return 0;
   float* hid = hidden_out ? hidden_out : hid_ws;
   const float* x = frames;
