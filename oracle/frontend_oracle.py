@@ -183,3 +183,23 @@ def compute_partial_slices(n_samples, partial_utterance_n_frames=EMO_PARTIAL_FRA
     if coverage < min_pad_coverage and len(mel) > 1:
         mel, wav = mel[:-1], wav[:-1]
     return wav, mel
+
+
+def resemblyzer_partial_slices(n_samples, rate=1.3, min_coverage=0.75):
+    """VoiceEncoder.compute_partial_slices of resemblyzer 0.1.1.dev0 (third party, requirements.txt:14; the code the reference's
+    data_gen/tts/emotion/inference.py:58-107 was forked from, with `rate` partials per second instead of an overlap fraction),
+    as (start, stop) pairs: (wav ranges, mel ranges).  Restated from the published source; PARITY UNPINNED."""
+    assert 0 < min_coverage <= 1
+    spf = int(EMO_SR * EMO_STEP_MS / 1000)
+    n_frames = int(np.ceil((n_samples + 1) / spf))
+    frame_step = int(np.round((EMO_SR / rate) / spf))
+    assert 0 < frame_step <= EMO_PARTIAL_FRAMES
+    mel, wav = [], []
+    steps = max(1, n_frames - EMO_PARTIAL_FRAMES + frame_step + 1)
+    for i in range(0, steps, frame_step):
+        mel.append((i, i + EMO_PARTIAL_FRAMES))
+        wav.append((i * spf, (i + EMO_PARTIAL_FRAMES) * spf))
+    coverage = (n_samples - wav[-1][0]) / (wav[-1][1] - wav[-1][0])
+    if coverage < min_coverage and len(mel) > 1:
+        mel, wav = mel[:-1], wav[:-1]
+    return wav, mel

@@ -128,3 +128,30 @@ def test_embed_utterance_glue_with_stand_in_kernels(monkeypatch):
         assert np.allclose(emotion.embed_utterance(y), emb)
         whole, p2, s2 = emotion.embed_utterance(y, using_partials=False, return_partials=True)
         assert p2 is None and s2 is None and np.allclose(whole, FO.lstm_hidden(FO.emotion_mel(y)[None], sd)[0], atol=1e-7)
+
+
+def test_voice_encoder_mirror_slicing_and_flow_with_stand_in_kernels():
+    """stylesinger_b200.voice_encoder (resemblyzer's VoiceEncoder on this package's kernels; third party, unpinned): the slicing
+    against the oracle's loop formulation, and embed_utterance's flow with the oracle standing in for the CUDA objects."""
+    import torch
+    from stylesinger_b200.voice_encoder import VoiceEncoder
+    for n in (1, 159, 8000, 25599, 25600, 37919, 37920, 38000, 48000, 160000, 479999):
+        for rate, cov in ((1.3, 0.75), (2.0, 0.5), (0.7, 1.0)):
+            ws, ms = VoiceEncoder.compute_partial_slices(n, rate, cov)
+            want = FO.resemblyzer_partial_slices(n, rate, cov)
+            assert ([(s.start, s.stop) for s in ws], [(s.start, s.stop) for s in ms]) == want
+    with pytest.raises(AssertionError):
+        VoiceEncoder.compute_partial_slices(16000, 0.5, 0.75)    # fewer than one partial per 1.6 s
+    sd = FO.emotion_encoder_weights(9)
+    ve = VoiceEncoder.__new__(VoiceEncoder)
+    ve._mel = lambda wav: torch.from_numpy(FO.emotion_mel(np.asarray(wav, np.float32)))
+    ve._net = lambda mels, want_embeds=False: {"embeds": torch.from_numpy(FO.emotion_embeds(FO.lstm_hidden(np.asarray(mels), sd), sd))}
+    rng = np.random.default_rng(2)
+    y = (0.1 * rng.standard_normal(40000)).astype(np.float32)
+    emb, partials, wav_slices = ve.embed_utterance(y, return_partials=True)
+    wav_sl, mel_sl = FO.resemblyzer_partial_slices(len(y))
+    fr = FO.emotion_mel(np.pad(y, (0, max(0, wav_sl[-1][1] - len(y)))))
+    pe = FO.emotion_embeds(FO.lstm_hidden(np.stack([fr[a:b] for a, b in mel_sl]), sd), sd)
+    raw = pe.mean(0)
+    assert np.allclose(partials, pe, atol=1e-7) and np.allclose(emb, raw / np.linalg.norm(raw), atol=1e-7)
+    assert abs(np.linalg.norm(emb) - 1) < 1e-6 and [(s.start, s.stop) for s in wav_slices] == wav_sl
