@@ -64,6 +64,8 @@ def test_lstm_oracle_matches_the_reference_encoder():
     assert np.abs(hidden - g["hidden"]).max() < 2e-7          # torch fp32 LSTM vs this float64 restatement
     assert np.abs(FO.emotion_embeds(hidden, sd) - g["embeds"]).max() < 5e-7
     assert np.abs(FO.utterance_embed(g["hidden"]) - g["utt_embed"]).max() < 1e-7
+    h2 = FO.lstm_hidden(g["frames2"], sd)                     # 3 sequences of 97 frames (using_partials=False shape)
+    assert h2.shape == (3, 256) and np.abs(h2 - g["hidden2"]).max() < 5e-7
 
 
 def test_partial_slices_match_the_reference_and_the_host_mirror():

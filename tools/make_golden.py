@@ -228,8 +228,10 @@ def case_emotion_encoder(name, partials=5, seed=71):
     with torch.no_grad():
         hidden = model.inference(frames)
         embeds = model.forward(frames)
+        frames2 = (torch.randn(3, 97, 40, generator=g).abs() * 2.0).float()  # another length, louder input
+        hidden2 = model.inference(frames2)
     raw = hidden.numpy().mean(axis=0)
-    d = {"seed": np.int64(seed), "frames": np32(frames), "hidden": np32(hidden), "embeds": np32(embeds),
+    d = {"frames2": np32(frames2), "hidden2": np32(hidden2), "seed": np.int64(seed), "frames": np32(frames), "hidden": np32(hidden), "embeds": np32(embeds),
          "utt_embed": (raw / np.linalg.norm(raw, 2)).astype(np.float32)}
     # partial-utterance slicing (inference.py:58-107) for a spread of lengths incl. the short / coverage-edge cases
     from data_gen.tts.emotion.inference import compute_partial_slices
